@@ -1,0 +1,347 @@
+// Offline subset construction + minimisation.  See determinize.h.
+#include "determinize.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+
+namespace rb {
+
+namespace {
+
+struct EmptyFlags {  // dfa.rs:408-416
+  bool start = false, end = false, start_line = false, end_line = false,
+       word_boundary = false, not_word_boundary = false;
+};
+
+inline bool is_word_byte(int b) {
+  return (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || (b >= '0' && b <= '9') || b == '_';
+}
+inline bool is_word_look(Look l) {
+  return l == Look::WordBoundary || l == Look::NotWordBoundary || l == Look::WordBoundaryAscii ||
+         l == Look::NotWordBoundaryAscii;
+}
+
+// Insertion-ordered set of instruction pointers (the reference's SparseSet,
+// src/sparse.rs): order encodes thread priority.
+struct OrderedSet {
+  std::vector<uint32_t> dense;
+  std::vector<uint32_t> sparse;
+  explicit OrderedSet(size_t n) : sparse(n, 0) { dense.reserve(n); }
+  bool contains(uint32_t v) const {
+    uint32_t i = sparse[v];
+    return i < dense.size() && dense[i] == v;
+  }
+  void insert(uint32_t v) { sparse[v] = (uint32_t)dense.size(); dense.push_back(v); }
+  void clear() { dense.clear(); }
+};
+
+struct VecHash {
+  size_t operator()(const std::vector<uint32_t>& v) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t x : v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+
+struct Builder {
+  const Program& prog;
+  const DfaOptions& opt;
+  uint32_t n_byte_classes, n_classes, mask_words;
+  int rep[256];  // representative byte of each byte class
+  bool prog_has_word_looks = false;
+
+  // raw states: key layout = [word, mask words (lo,hi pairs)..., ips...]
+  std::unordered_map<std::vector<uint32_t>, uint32_t, VecHash> index;
+  std::vector<std::vector<uint32_t>> keys;
+  std::vector<uint32_t> trans;  // raw [state][n_classes], 0 = dead
+  std::vector<uint32_t> stack;
+  OrderedSet qcur, qnext;
+  bool too_big = false;
+
+  Builder(const Program& p, const DfaOptions& o)
+      : prog(p), opt(o), qcur(p.insts.size()), qnext(p.insts.size()) {
+    n_byte_classes = (uint32_t)p.num_classes;
+    n_classes = n_byte_classes + 1;
+    mask_words = (uint32_t)((p.n_patterns + 63) / 64);
+    for (int c = 0; c < 256; c++) rep[c] = -1;
+    for (int b = 255; b >= 0; b--) rep[p.byte_classes[b]] = b;
+    for (const auto& in : p.insts)
+      if (in.op == Op::EmptyLook && is_word_look(in.look)) prog_has_word_looks = true;
+    keys.emplace_back();  // state 0 = dead
+    trans.assign(n_classes, 0);
+  }
+
+  size_t key_header() const { return 1 + 2 * (size_t)mask_words; }
+
+  // dfa.rs:1073-1134
+  void follow_epsilons(uint32_t ip0, OrderedSet& q, const EmptyFlags& f) {
+    stack.push_back(ip0);
+    while (!stack.empty()) {
+      uint32_t ip = stack.back();
+      stack.pop_back();
+      if (q.contains(ip)) continue;
+      q.insert(ip);
+      const Inst& in = prog.insts[ip];
+      switch (in.op) {
+        case Op::Match: case Op::Bytes: break;
+        case Op::Save: stack.push_back(in.a); break;
+        case Op::Split: stack.push_back(in.b); stack.push_back(in.a); break;
+        case Op::EmptyLook: {
+          bool ok = false;
+          switch (in.look) {
+            case Look::StartLine: ok = f.start_line; break;
+            case Look::EndLine: ok = f.end_line; break;
+            case Look::StartText: ok = f.start; break;
+            case Look::EndText: ok = f.end; break;
+            case Look::WordBoundary: case Look::WordBoundaryAscii: ok = f.word_boundary; break;
+            case Look::NotWordBoundary: case Look::NotWordBoundaryAscii: ok = f.not_word_boundary; break;
+          }
+          if (ok) stack.push_back(in.a);
+          break;
+        }
+      }
+    }
+  }
+
+  // dfa.rs:1196-1244 (+ canonicalisation that cannot change results: the word
+  // flag is kept only when a word-boundary look can still read it, and
+  // priority order is dropped when no leftmost-first cut will ever use it).
+  uint32_t intern(const OrderedSet& q, bool word, const std::vector<uint64_t>& mask) {
+    std::vector<uint32_t> key(key_header(), 0);
+    bool any_mask = false;
+    for (uint32_t w = 0; w < mask_words; w++) {
+      key[1 + 2 * w] = (uint32_t)mask[w];
+      key[2 + 2 * w] = (uint32_t)(mask[w] >> 32);
+      any_mask = any_mask || mask[w];
+    }
+    bool word_look = false;
+    for (uint32_t ip : q.dense) {
+      const Inst& in = prog.insts[ip];
+      if (in.op == Op::Save || in.op == Op::Split) continue;
+      key.push_back(ip);
+      if (in.op == Op::EmptyLook && is_word_look(in.look)) word_look = true;
+      if (in.op == Op::Match && opt.leftmost_first) break;
+    }
+    if (key.size() == key_header() && !any_mask) return 0;  // dead
+    key[0] = (word && word_look) ? 1 : 0;
+    if (!opt.leftmost_first) std::sort(key.begin() + key_header(), key.end());
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    uint32_t id = (uint32_t)keys.size();
+    if (id > 400000 || (size_t)(id + 1) * n_classes * 2 > opt.max_table_bytes * 8) { too_big = true; return 0; }
+    index.emplace(key, id);
+    keys.push_back(std::move(key));
+    trans.resize((size_t)(id + 1) * n_classes, 0xFFFFFFFFu);
+    return id;
+  }
+
+  // dfa.rs:910-1048.  b in [0,255] or 256 for EOF.
+  uint32_t step(uint32_t si, int b) {
+    const std::vector<uint32_t> key = keys[si];  // copy: intern() may reallocate keys
+    bool is_word_last = key[0] != 0;
+    bool has_empty = false;
+    qcur.clear();
+    for (size_t k = key_header(); k < key.size(); k++) {
+      qcur.insert(key[k]);
+      if (prog.insts[key[k]].op == Op::EmptyLook) has_empty = true;
+    }
+    bool eof = b == 256;
+    bool is_word = !eof && is_word_byte(b);
+    if (has_empty) {
+      EmptyFlags f;
+      if (eof) { f.end = true; f.end_line = true; }
+      else if (b == '\n') f.end_line = true;
+      if (is_word_last == is_word) f.not_word_boundary = true; else f.word_boundary = true;
+      qnext.clear();
+      for (uint32_t ip : qcur.dense) follow_epsilons(ip, qnext, f);
+      std::swap(qcur.dense, qnext.dense);
+      std::swap(qcur.sparse, qnext.sparse);
+    }
+    EmptyFlags f;
+    f.start_line = !eof && b == '\n';
+    std::vector<uint64_t> mask(mask_words, 0);
+    qnext.clear();
+    for (uint32_t ip : qcur.dense) {
+      const Inst& in = prog.insts[ip];
+      if (in.op == Op::Match) {
+        mask[in.a / 64] |= 1ull << (in.a % 64);
+        if (opt.leftmost_first) break;
+      } else if (in.op == Op::Bytes) {
+        if (!eof && in.lo <= b && b <= in.hi) follow_epsilons(in.a, qnext, f);
+      }
+    }
+    return intern(qnext, is_word, mask);
+  }
+
+  uint32_t start_state(int flagi) {  // dfa.rs:1370-1409
+    EmptyFlags f;
+    f.start = flagi & 1; f.end = flagi & 2; f.start_line = flagi & 4; f.end_line = flagi & 8;
+    f.word_boundary = flagi & 16; f.not_word_boundary = flagi & 32;
+    bool word = flagi & 64;
+    qnext.clear();
+    uint32_t entry = (opt.anchored || !prog.has_prefix) ? prog.start_anchored : prog.start;
+    follow_epsilons(entry, qnext, f);
+    return intern(qnext, word, std::vector<uint64_t>(mask_words, 0));
+  }
+};
+
+}  // namespace
+
+int start_flag_index_forward(const uint8_t* text, size_t len, size_t at) {
+  int f = 0;
+  if (at == 0) f |= 1;
+  if (len == 0) f |= 2 | 8;
+  if (at == 0 || text[at - 1] == '\n') f |= 4;
+  bool last = at > 0 && is_word_byte(text[at - 1]);
+  bool cur = at < len && is_word_byte(text[at]);
+  f |= (last == cur) ? 32 : 16;
+  if (last) f |= 64;
+  return f;
+}
+int start_flag_index_reverse(const uint8_t* text, size_t len, size_t at) {
+  int f = 0;
+  if (at == len) f |= 1;
+  if (len == 0) f |= 2 | 8;
+  if (at == len || text[at] == '\n') f |= 4;
+  bool last = at < len && is_word_byte(text[at]);
+  bool cur = at > 0 && is_word_byte(text[at - 1]);
+  f |= (last == cur) ? 32 : 16;
+  if (last) f |= 64;
+  return f;
+}
+
+bool determinize(const Program& prog, const DfaOptions& opt, Dfa* out, Error* err) {
+  if (prog.has_unicode_word_boundary) {
+    err->kind = Error::UnicodeWordBoundary;
+    err->msg = "Unicode word boundaries (\\b, \\B without (?-u)) need a look-around engine; "
+               "the B200 DFA backend does not support them (use (?-u:\\b)).";
+    return false;
+  }
+  Builder b(prog, opt);
+  uint32_t raw_start[128];
+  for (int f = 0; f < 128; f++) raw_start[f] = b.start_state(f);
+  for (uint32_t si = 1; si < b.keys.size() && !b.too_big; si++) {
+    for (uint32_t c = 0; c < b.n_classes; c++) {
+      int byte = c == b.n_byte_classes ? 256 : b.rep[c];
+      uint32_t t = b.step(si, byte);
+      b.trans[(size_t)si * b.n_classes + c] = t;
+    }
+  }
+  if (b.too_big) {
+    err->kind = Error::DfaTooBig;
+    err->msg = "Compiled regex exceeds size limit: determinized DFA is larger than the " +
+               std::to_string(opt.max_table_bytes) + " byte table budget.";
+    return false;
+  }
+  const uint32_t n = (uint32_t)b.keys.size(), nc = b.n_classes, mw = b.mask_words;
+
+  // ---- minimise (Moore refinement), initial partition = delayed match mask ----
+  std::vector<uint32_t> block(n, 0);
+  uint32_t n_blocks;
+  {
+    std::unordered_map<std::vector<uint32_t>, uint32_t, VecHash> first;
+    first.emplace(std::vector<uint32_t>(2 * mw + 1, 0xFFFFFFFFu), 0);  // dead alone
+    for (uint32_t s = 1; s < n; s++) {
+      std::vector<uint32_t> sig(b.keys[s].begin() + 1, b.keys[s].begin() + 1 + 2 * mw);
+      auto it = first.emplace(sig, (uint32_t)first.size()).first;
+      block[s] = it->second;
+    }
+    n_blocks = (uint32_t)first.size();
+  }
+  for (;;) {
+    std::unordered_map<std::vector<uint32_t>, uint32_t, VecHash> sigs;
+    std::vector<uint32_t> nb(n);
+    std::vector<uint32_t> sig(nc + 1);
+    for (uint32_t s = 0; s < n; s++) {
+      sig[0] = block[s];
+      for (uint32_t c = 0; c < nc; c++) sig[c + 1] = block[b.trans[(size_t)s * nc + c]];
+      auto it = sigs.emplace(sig, (uint32_t)sigs.size()).first;
+      nb[s] = it->second;
+    }
+    bool stable = sigs.size() == n_blocks;
+    n_blocks = (uint32_t)sigs.size();
+    block.swap(nb);
+    if (stable) break;
+  }
+  // A live block that can never reach a match is equivalent to dead only if it
+  // carries no mask itself; Moore already merged those with state 0.
+
+  // ---- renumber: dead, live..., match... (BFS order inside each group) ----
+  std::vector<uint32_t> repr(n_blocks, 0xFFFFFFFFu);
+  for (uint32_t s = 0; s < n; s++) if (repr[block[s]] == 0xFFFFFFFFu) repr[block[s]] = s;
+  auto has_mask = [&](uint32_t s) {
+    for (uint32_t w = 0; w < 2 * mw; w++) if (b.keys[s].size() > 1 + w && b.keys[s][1 + w]) return true;
+    return false;
+  };
+  std::vector<uint32_t> new_id(n_blocks, 0);
+  uint32_t next_id = 0;
+  new_id[block[0]] = next_id++;
+  for (uint32_t bl = 0; bl < n_blocks; bl++)
+    if (bl != block[0] && !has_mask(repr[bl])) new_id[bl] = next_id++;
+  uint32_t match_lo = next_id;
+  for (uint32_t bl = 0; bl < n_blocks; bl++)
+    if (bl != block[0] && has_mask(repr[bl])) new_id[bl] = next_id++;
+  if (n_blocks > 65535 || (size_t)n_blocks * nc * 2 > opt.max_table_bytes) {
+    err->kind = Error::DfaTooBig;
+    err->msg = "Compiled regex exceeds size limit: determinized DFA (" + std::to_string(n_blocks) +
+               " states x " + std::to_string(nc) + " classes) is larger than the " +
+               std::to_string(opt.max_table_bytes) + " byte table budget.";
+    return false;
+  }
+
+  Dfa& d = *out;
+  d = Dfa();
+  d.n_states = n_blocks;
+  d.n_classes = nc;
+  d.match_lo = match_lo;
+  d.mask_words = mw;
+  d.raw_states = n;
+  d.reverse = prog.is_reverse;
+  d.has_looks = prog.has_looks;
+  std::memcpy(d.classes, prog.byte_classes, 256);
+  d.trans.assign((size_t)n_blocks * nc, 0);
+  d.masks.assign((size_t)n_blocks * mw, 0);
+  for (uint32_t bl = 0; bl < n_blocks; bl++) {
+    uint32_t s = repr[bl], id = new_id[bl];
+    for (uint32_t c = 0; c < nc; c++) d.trans[(size_t)id * nc + c] = (uint16_t)new_id[block[b.trans[(size_t)s * nc + c]]];
+    if (s != 0)
+      for (uint32_t w = 0; w < mw; w++)
+        d.masks[(size_t)id * mw + w] = (uint64_t)b.keys[s][1 + 2 * w] | ((uint64_t)b.keys[s][2 + 2 * w] << 32);
+  }
+  d.uniform_start = true;
+  for (int f = 0; f < 128; f++) d.start[f] = (uint16_t)new_id[block[raw_start[f]]];
+  // Only flag combinations that can occur matter for uniformity: exactly one of
+  // word-boundary / not-word-boundary is set, end implies end-line, start implies start-line.
+  int first_feasible = -1;
+  for (int f = 0; f < 128; f++) {
+    bool wb = f & 16, nwb = f & 32;
+    if (wb == nwb) continue;
+    if (((f & 2) != 0) != ((f & 8) != 0)) continue;
+    if ((f & 1) && !(f & 4)) continue;
+    if (first_feasible < 0) first_feasible = f;
+    else if (d.start[f] != d.start[first_feasible]) d.uniform_start = false;
+  }
+  return true;
+}
+
+std::string dump_dfa(const Dfa& d) {
+  std::string s;
+  char buf[96];
+  snprintf(buf, sizeof buf, "states=%u classes=%u match_lo=%u raw=%zu uniform_start=%d\n", d.n_states,
+           d.n_classes, d.match_lo, d.raw_states, (int)d.uniform_start);
+  s += buf;
+  for (uint32_t i = 0; i < d.n_states; i++) {
+    snprintf(buf, sizeof buf, "%5u%s:", i, d.is_match((uint16_t)i) ? "*" : " ");
+    s += buf;
+    for (uint32_t c = 0; c < d.n_classes; c++) {
+      snprintf(buf, sizeof buf, " %u", d.trans[(size_t)i * d.n_classes + c]);
+      s += buf;
+    }
+    s += "\n";
+  }
+  return s;
+}
+
+}  // namespace rb
