@@ -1,0 +1,99 @@
+/*
+ * rure_b200.h -- bulk / device-resident extension of the rure C ABI.
+ *
+ * The reference API is one haystack per call (regex-capi/include/rure.h); GPU-
+ * sized work needs bulk entry points.  Every function here returns exactly what
+ * looping the scalar ABI would return:
+ *   rure_b200_find_all        == collecting rure_iter_next until it returns false
+ *   rure_b200_is_match_batch  == rure_is_match(re, hay + off[i], off[i+1]-off[i], 0) per record
+ *   rure_b200_find_batch      == rure_find(...)  per record (offsets relative to the record)
+ *   rure_b200_set_matches_*   == rure_set_matches(...) packed into 64-bit masks
+ * Functions return true on success; on failure rure_b200_last_error() (thread
+ * local) describes what went wrong.  A missing GPU is a failure, never a
+ * silent CPU fallback.
+ *
+ * "_device" variants take CUDA device pointers valid on the current device (one
+ * process per GPU; select the device with cudaSetDevice / torch.cuda.set_device
+ * before the first call on a regex object).
+ */
+#ifndef REGEX_B200_RURE_B200_H
+#define REGEX_B200_RURE_B200_H
+
+#include "rure.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Compile with `Regex` (str) semantics instead of `bytes::Regex`: the implicit
+ * unanchored prefix only skips whole UTF-8 scalars and empty matches advance by
+ * one scalar (src/compile.rs:381-395, src/exec.rs:335-337).  Haystacks must be
+ * valid UTF-8.  flags/options/error as rure_compile. */
+rure *rure_b200_compile_str(const uint8_t *pattern, size_t length, uint32_t flags,
+                            rure_options *options, rure_error *error);
+
+/* RegexSet with `regex::RegexSet` (str) semantics; see rure_b200_compile_str. */
+rure_set *rure_b200_compile_set_str(const uint8_t **patterns, const size_t *patterns_lengths,
+                                    size_t patterns_count, uint32_t flags, rure_options *options,
+                                    rure_error *error);
+
+/* ---- single haystack ------------------------------------------------------ */
+bool rure_b200_find_all(rure *re, const uint8_t *haystack, size_t length, rure_match *out,
+                        size_t cap, size_t *n_total);
+bool rure_b200_count_all(rure *re, const uint8_t *haystack, size_t length, size_t *n_total);
+/* mask_words = (rure_set_len + 63) / 64 */
+bool rure_b200_set_matches_mask(rure_set *set, const uint8_t *haystack, size_t length,
+                                size_t start, uint64_t *mask_words);
+
+/* ---- batched records: record i = haystack[offsets[i], offsets[i+1]) -------- */
+/* out_bits: bit (i % 8) of byte (i / 8); (n_records + 7) / 8 bytes */
+bool rure_b200_is_match_batch(rure *re, const uint8_t *haystack, const uint64_t *offsets,
+                              size_t n_records, uint8_t *out_bits);
+bool rure_b200_find_batch(rure *re, const uint8_t *haystack, const uint64_t *offsets,
+                          size_t n_records, rure_match *out, uint8_t *found_bits);
+bool rure_b200_set_matches_batch(rure_set *set, const uint8_t *haystack, const uint64_t *offsets,
+                                 size_t n_records, uint64_t *out_masks);
+
+/* ---- device-resident inputs and outputs ----------------------------------- */
+bool rure_b200_find_all_device(rure *re, const uint8_t *d_haystack, size_t length, size_t start,
+                               rure_match *d_out, size_t cap, size_t *n_total);
+bool rure_b200_shortest_match_device(rure *re, const uint8_t *d_haystack, size_t length,
+                                     size_t start, bool *found, size_t *end);
+bool rure_b200_set_matches_device(rure_set *set, const uint8_t *d_haystack, size_t length,
+                                  size_t start, uint64_t *mask_words /* host */);
+/* d_out_bits: 32-bit ballot words, 4 * ((n_records + 31) / 32) bytes of device memory */
+bool rure_b200_is_match_batch_device(rure *re, const uint8_t *d_haystack, const uint64_t *d_offsets,
+                                     size_t n_records, uint32_t *d_out_bits);
+bool rure_b200_find_batch_device(rure *re, const uint8_t *d_haystack, const uint64_t *d_offsets,
+                                 size_t n_records, rure_match *d_out, uint32_t *d_found_bits);
+bool rure_b200_set_matches_batch_device(rure_set *set, const uint8_t *d_haystack,
+                                        const uint64_t *d_offsets, size_t n_records,
+                                        uint64_t *d_out_masks);
+
+/* ---- diagnostics ----------------------------------------------------------- */
+const char *rure_b200_last_error(void);
+/* kernels launched by this library in this process (bench.py "gpu_launches") */
+uint64_t rure_b200_kernel_launches(void);
+/* Timing (CUDA events on the library's stream) and fix-up counters of the last
+ * rure_b200_find_all* call on this object.  out[0..6] = scan_ms, walk_ms,
+ * total_ms, scan_redo_rounds, scan_redo_segments, stitch_rounds, stitch_dirty_chunks */
+void rure_b200_last_stats(rure *re, double *out7);
+/* seg/chunk are positions per scan segment / walk chunk (multiples of 64);
+ * warm = warm-up bytes (0 = automatic); 0 keeps the current value elsewhere. */
+void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block,
+                          uint32_t blocks_per_sm);
+/* Dense tables, for tests and tooling.  kind: 0 forward anchored leftmost-first,
+ * 1 reverse unanchored all-match, 2 forward unanchored all-match, 3 reverse
+ * anchored longest, 4 forward unanchored leftmost-first.
+ * info[0..5] = n_states, n_classes (last = EOF), match_lo, mask_words, uniform_start, raw_states.
+ * Buffers may be NULL to query sizes: trans n_states*n_classes u16, classes 256 u8,
+ * start 128 u16, masks n_states*mask_words u64. */
+bool rure_b200_dfa_export(rure *re, int kind, uint32_t *info6, uint16_t *trans, uint8_t *classes,
+                          uint16_t *start, uint64_t *masks);
+/* info[0..3] = min match length, max match length (SIZE_MAX = unbounded), can_match_empty, has_looks */
+void rure_b200_pattern_info(rure *re, uint64_t *info4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,407 @@
+"""regex_b200 -- B200-native search backend with the reference crate's search surface.
+
+Python host mirror of the reference API for the search hot path (names and argument
+meaning follow the Rust crate: `Regex` src/re_unicode.rs, `bytes::Regex` src/re_bytes.rs,
+`RegexSet` src/re_set.rs, `RegexBuilder` src/re_builder.rs).  Every search call goes
+through the C ABI in include/rure.h / include/rure_b200.h into hand-written sm_100a
+kernels; there is no CPU matching path -- loading fails loudly when the CUDA
+library has not been built, and searching fails loudly without a GPU.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_bool, c_char_p, c_double, c_int, c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librure_b200.so")
+
+FLAG_CASEI, FLAG_MULTI, FLAG_DOTNL, FLAG_SWAP_GREED, FLAG_SPACE, FLAG_UNICODE = 1, 2, 4, 8, 16, 32
+
+DFA_FWD_ANCHORED_LF, DFA_REV_UNANCHORED_ALL, DFA_FWD_UNANCHORED_ALL, DFA_REV_ANCHORED_LONGEST, DFA_FWD_UNANCHORED_LF = range(5)
+
+
+class Error(Exception):
+    """Compile error (syntax, size limit, unsupported construct) or GPU runtime error."""
+
+
+class _Match(ctypes.Structure):
+    _fields_ = [("start", c_size_t), ("end", c_size_t)]
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m regex_b200.build` "
+            "(nvcc, sm_100a).  regex_b200 has no CPU fallback.")
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, sz, u8p = c_void_p, c_size_t, c_void_p
+    sig = {
+        "rure_compile": (vp, [c_char_p, sz, c_uint32, vp, vp]),
+        "rure_b200_compile_str": (vp, [c_char_p, sz, c_uint32, vp, vp]),
+        "rure_compile_must": (vp, [c_char_p]),
+        "rure_free": (None, [vp]),
+        "rure_is_match": (c_bool, [vp, u8p, sz, sz]),
+        "rure_find": (c_bool, [vp, u8p, sz, sz, POINTER(_Match)]),
+        "rure_shortest_match": (c_bool, [vp, u8p, sz, sz, POINTER(sz)]),
+        "rure_iter_new": (vp, [vp]),
+        "rure_iter_free": (None, [vp]),
+        "rure_iter_next": (c_bool, [vp, u8p, sz, POINTER(_Match)]),
+        "rure_options_new": (vp, []),
+        "rure_options_free": (None, [vp]),
+        "rure_options_size_limit": (None, [vp, sz]),
+        "rure_options_dfa_size_limit": (None, [vp, sz]),
+        "rure_compile_set": (vp, [POINTER(c_char_p), POINTER(sz), sz, c_uint32, vp, vp]),
+        "rure_b200_compile_set_str": (vp, [POINTER(c_char_p), POINTER(sz), sz, c_uint32, vp, vp]),
+        "rure_set_free": (None, [vp]),
+        "rure_set_is_match": (c_bool, [vp, u8p, sz, sz]),
+        "rure_set_matches": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool)]),
+        "rure_set_len": (sz, [vp]),
+        "rure_error_new": (vp, []),
+        "rure_error_free": (None, [vp]),
+        "rure_error_message": (c_char_p, [vp]),
+        "rure_b200_find_all": (c_bool, [vp, u8p, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_count_all": (c_bool, [vp, u8p, sz, POINTER(sz)]),
+        "rure_b200_set_matches_mask": (c_bool, [vp, u8p, sz, sz, POINTER(c_uint64)]),
+        "rure_b200_is_match_batch": (c_bool, [vp, u8p, vp, sz, vp]),
+        "rure_b200_find_batch": (c_bool, [vp, u8p, vp, sz, vp, vp]),
+        "rure_b200_set_matches_batch": (c_bool, [vp, u8p, vp, sz, vp]),
+        "rure_b200_find_all_device": (c_bool, [vp, vp, sz, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_shortest_match_device": (c_bool, [vp, vp, sz, sz, POINTER(c_bool), POINTER(sz)]),
+        "rure_b200_set_matches_device": (c_bool, [vp, vp, sz, sz, POINTER(c_uint64)]),
+        "rure_b200_is_match_batch_device": (c_bool, [vp, vp, vp, sz, vp]),
+        "rure_b200_find_batch_device": (c_bool, [vp, vp, vp, sz, vp, vp]),
+        "rure_b200_set_matches_batch_device": (c_bool, [vp, vp, vp, sz, vp]),
+        "rure_b200_last_error": (c_char_p, []),
+        "rure_b200_kernel_launches": (c_uint64, []),
+        "rure_b200_last_stats": (None, [vp, POINTER(c_double)]),
+        "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
+        "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
+        "rure_b200_pattern_info": (None, [vp, POINTER(c_uint64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
+_lib = _load()
+
+
+def lib():
+    return _lib
+
+
+def exported_symbols():
+    """Names every header in include/ declares (used by the no-GPU load test)."""
+    return sorted(n for n in dir(_lib) if n.startswith("rure"))
+
+
+def kernel_launches():
+    return int(_lib.rure_b200_kernel_launches())
+
+
+def _last_error():
+    return (_lib.rure_b200_last_error() or b"").decode("utf-8", "replace")
+
+
+def _buf(data):
+    """bytes-like -> (pointer, length, keepalive)."""
+    if isinstance(data, str):
+        data = data.encode("utf-8")
+    if isinstance(data, np.ndarray):
+        a = np.ascontiguousarray(data, dtype=np.uint8) if data.dtype != np.uint8 or not data.flags.c_contiguous else data
+        return a.ctypes.data, a.size, a
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        b = bytes(data) if not isinstance(data, bytes) else data
+        return ctypes.cast(c_char_p(b), c_void_p).value or 0, len(b), b
+    if hasattr(data, "data_ptr"):  # pinned / CPU torch tensor
+        return data.data_ptr(), data.numel() * data.element_size(), data
+    raise TypeError(f"unsupported haystack type {type(data)!r}")
+
+
+class RegexBuilder:
+    """Options mirror src/re_builder.rs:14-40."""
+
+    def __init__(self, pattern):
+        self.pattern = pattern
+        self._flags = FLAG_UNICODE
+        self._size_limit = 10 << 20
+        self._dfa_size_limit = 2 << 20
+
+    def _flag(self, bit, yes):
+        self._flags = (self._flags | bit) if yes else (self._flags & ~bit)
+        return self
+
+    def case_insensitive(self, yes): return self._flag(FLAG_CASEI, yes)
+    def multi_line(self, yes): return self._flag(FLAG_MULTI, yes)
+    def dot_matches_new_line(self, yes): return self._flag(FLAG_DOTNL, yes)
+    def swap_greed(self, yes): return self._flag(FLAG_SWAP_GREED, yes)
+    def ignore_whitespace(self, yes): return self._flag(FLAG_SPACE, yes)
+    def unicode(self, yes): return self._flag(FLAG_UNICODE, yes)
+
+    def size_limit(self, n):
+        self._size_limit = n
+        return self
+
+    def dfa_size_limit(self, n):
+        self._dfa_size_limit = n
+        return self
+
+    def build(self):
+        return Regex(self.pattern, flags=self._flags, size_limit=self._size_limit, dfa_size_limit=self._dfa_size_limit)
+
+    def build_bytes(self):
+        return BytesRegex(self.pattern, flags=self._flags, size_limit=self._size_limit, dfa_size_limit=self._dfa_size_limit)
+
+
+class _Compiled:
+    _only_utf8 = False
+
+    def __init__(self, pattern, flags=FLAG_UNICODE, size_limit=10 << 20, dfa_size_limit=2 << 20):
+        self.pattern = pattern
+        pat = pattern.encode("utf-8") if isinstance(pattern, str) else bytes(pattern)
+        opts = _lib.rure_options_new()
+        _lib.rure_options_size_limit(opts, size_limit)
+        _lib.rure_options_dfa_size_limit(opts, dfa_size_limit)
+        err = _lib.rure_error_new()
+        fn = _lib.rure_b200_compile_str if self._only_utf8 else _lib.rure_compile
+        self._h = fn(pat, len(pat), flags, opts, err)
+        msg = _lib.rure_error_message(err).decode("utf-8", "replace")
+        _lib.rure_error_free(err)
+        _lib.rure_options_free(opts)
+        if not self._h:
+            raise Error(msg)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.rure_free(h)
+            self._h = None
+
+    # ---- scalar API (re_bytes.rs:141-623 / re_unicode.rs) -------------------
+    def is_match(self, text):
+        return self.is_match_at(text, 0)
+
+    def is_match_at(self, text, start):
+        p, n, keep = _buf(text)
+        return bool(_lib.rure_is_match(self._h, p, n, start))
+
+    def shortest_match(self, text):
+        return self.shortest_match_at(text, 0)
+
+    def shortest_match_at(self, text, start):
+        p, n, keep = _buf(text)
+        end = c_size_t()
+        return end.value if _lib.rure_shortest_match(self._h, p, n, start, byref(end)) else None
+
+    def find(self, text):
+        return self.find_at(text, 0)
+
+    def find_at(self, text, start):
+        p, n, keep = _buf(text)
+        m = _Match()
+        return (m.start, m.end) if _lib.rure_find(self._h, p, n, start, byref(m)) else None
+
+    def find_iter(self, text):
+        """All non-overlapping leftmost-first matches as a list of (start, end)."""
+        return [tuple(r) for r in self.find_all(text).tolist()]
+
+    # ---- bulk API (include/rure_b200.h) --------------------------------------
+    def find_all(self, text, cap=None):
+        """(n, 2) uint64 array of spans; equals collecting find_iter."""
+        p, n, keep = _buf(text)
+        total = c_size_t()
+        cap = 4096 if cap is None else cap
+        while True:
+            out = np.empty((max(cap, 1), 2), dtype=np.uint64)
+            if not _lib.rure_b200_find_all(self._h, p, n, out.ctypes.data, cap, byref(total)):
+                raise Error(_last_error())
+            if total.value <= cap:
+                return out[: total.value]
+            cap = total.value
+
+    def count_all(self, text):
+        p, n, keep = _buf(text)
+        total = c_size_t()
+        if not _lib.rure_b200_count_all(self._h, p, n, byref(total)):
+            raise Error(_last_error())
+        return total.value
+
+    def is_match_batch(self, text, offsets):
+        """bool array, one per record text[offsets[i]:offsets[i+1]]."""
+        p, n, keep = _buf(text)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_rec = off.size - 1
+        bits = np.zeros((n_rec + 7) // 8 + 8, dtype=np.uint8)
+        if not _lib.rure_b200_is_match_batch(self._h, p, off.ctypes.data, n_rec, bits.ctypes.data):
+            raise Error(_last_error())
+        return np.unpackbits(bits, bitorder="little")[:n_rec].astype(bool)
+
+    def find_batch(self, text, offsets):
+        """(found bool[n], spans uint64[n,2]) with record-relative offsets."""
+        p, n, keep = _buf(text)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_rec = off.size - 1
+        bits = np.zeros((n_rec + 7) // 8 + 8, dtype=np.uint8)
+        spans = np.zeros((max(n_rec, 1), 2), dtype=np.uint64)
+        if not _lib.rure_b200_find_batch(self._h, p, off.ctypes.data, n_rec, spans.ctypes.data, bits.ctypes.data):
+            raise Error(_last_error())
+        return np.unpackbits(bits, bitorder="little")[:n_rec].astype(bool), spans[:n_rec]
+
+    # ---- device-resident (torch CUDA tensors) --------------------------------
+    def find_all_device(self, d_text, d_out=None, start=0):
+        """d_text: uint8 CUDA tensor; d_out: optional (cap, 2) int64/uint64 CUDA tensor.
+        Returns the total number of matches (spans beyond cap are counted, not stored)."""
+        total = c_size_t()
+        cap = 0 if d_out is None else d_out.shape[0]
+        ptr = 0 if d_out is None else d_out.data_ptr()
+        if not _lib.rure_b200_find_all_device(self._h, d_text.data_ptr(), d_text.numel(), start, ptr, cap, byref(total)):
+            raise Error(_last_error())
+        return total.value
+
+    def shortest_match_device(self, d_text, start=0):
+        found, end = c_bool(), c_size_t()
+        if not _lib.rure_b200_shortest_match_device(self._h, d_text.data_ptr(), d_text.numel(), start, byref(found), byref(end)):
+            raise Error(_last_error())
+        return end.value if found.value else None
+
+    def is_match_batch_device(self, d_text, d_offsets, d_bits):
+        """d_bits: int32 CUDA tensor of (n_records + 31) // 32 ballot words."""
+        n_rec = d_offsets.numel() - 1
+        if not _lib.rure_b200_is_match_batch_device(self._h, d_text.data_ptr(), d_offsets.data_ptr(), n_rec, d_bits.data_ptr()):
+            raise Error(_last_error())
+
+    def find_batch_device(self, d_text, d_offsets, d_spans, d_bits):
+        n_rec = d_offsets.numel() - 1
+        if not _lib.rure_b200_find_batch_device(self._h, d_text.data_ptr(), d_offsets.data_ptr(), n_rec, d_spans.data_ptr(), d_bits.data_ptr()):
+            raise Error(_last_error())
+
+    # ---- diagnostics ------------------------------------------------------------
+    def last_stats(self):
+        out = (c_double * 7)()
+        _lib.rure_b200_last_stats(self._h, out)
+        keys = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks"]
+        return dict(zip(keys, list(out)))
+
+    def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):
+        _lib.rure_b200_set_tuning(self._h, seg, chunk, warm, block, blocks_per_sm)
+
+    def pattern_info(self):
+        out = (c_uint64 * 4)()
+        _lib.rure_b200_pattern_info(self._h, out)
+        return {"min_len": out[0], "max_len": None if out[1] == 2**64 - 1 else out[1], "can_match_empty": bool(out[2]), "has_looks": bool(out[3])}
+
+    def dfa(self, kind):
+        """Dense table as numpy arrays (host copy; for tests and tooling)."""
+        info = (c_uint32 * 6)()
+        if not _lib.rure_b200_dfa_export(self._h, kind, info, None, None, None, None):
+            raise Error(_last_error())
+        n_states, n_classes, match_lo, mask_words, uniform, raw = list(info)
+        trans = np.empty((n_states, n_classes), dtype=np.uint16)
+        classes = np.empty(256, dtype=np.uint8)
+        start = np.empty(128, dtype=np.uint16)
+        masks = np.empty((n_states, mask_words), dtype=np.uint64)
+        _lib.rure_b200_dfa_export(self._h, kind, info, trans.ctypes.data, classes.ctypes.data, start.ctypes.data, masks.ctypes.data)
+        return {"trans": trans, "classes": classes, "start": start, "masks": masks, "match_lo": match_lo,
+                "uniform_start": bool(uniform), "raw_states": raw}
+
+
+class BytesRegex(_Compiled):
+    """`regex::bytes::Regex` (src/re_bytes.rs): haystacks are arbitrary bytes."""
+    _only_utf8 = False
+
+
+class Regex(_Compiled):
+    """`regex::Regex` (src/re_unicode.rs): haystacks are str / valid UTF-8; offsets are byte offsets."""
+    _only_utf8 = True
+
+
+class _SetBase:
+    _only_utf8 = False
+
+    def __init__(self, patterns, flags=FLAG_UNICODE, size_limit=10 << 20, dfa_size_limit=2 << 20):
+        pats = [p.encode("utf-8") if isinstance(p, str) else bytes(p) for p in patterns]
+        self.patterns = list(patterns)
+        arr = (c_char_p * max(1, len(pats)))(*pats)
+        lens = (c_size_t * max(1, len(pats)))(*[len(p) for p in pats])
+        opts = _lib.rure_options_new()
+        _lib.rure_options_size_limit(opts, size_limit)
+        _lib.rure_options_dfa_size_limit(opts, dfa_size_limit)
+        err = _lib.rure_error_new()
+        fn = _lib.rure_b200_compile_set_str if self._only_utf8 else _lib.rure_compile_set
+        self._h = fn(arr, lens, len(pats), flags, opts, err)
+        msg = _lib.rure_error_message(err).decode("utf-8", "replace")
+        _lib.rure_error_free(err)
+        _lib.rure_options_free(opts)
+        if not self._h:
+            raise Error(msg)
+        self._mw = max(1, (len(pats) + 63) // 64)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.rure_set_free(h)
+            self._h = None
+
+    def __len__(self):
+        return int(_lib.rure_set_len(self._h))
+
+    def is_match(self, text, start=0):
+        p, n, keep = _buf(text)
+        return bool(_lib.rure_set_is_match(self._h, p, n, start))
+
+    def matches(self, text, start=0):
+        """Indices of the patterns that match somewhere in text (re_set.rs:184-191)."""
+        p, n, keep = _buf(text)
+        out = (c_bool * max(1, len(self)))()
+        _lib.rure_set_matches(self._h, p, n, start, out)
+        return [i for i in range(len(self)) if out[i]]
+
+    def matches_mask(self, text, start=0):
+        p, n, keep = _buf(text)
+        out = (c_uint64 * self._mw)()
+        if not _lib.rure_b200_set_matches_mask(self._h, p, n, start, out):
+            raise Error(_last_error())
+        return list(out)
+
+    def matches_batch(self, text, offsets):
+        """uint64[n_records, mask_words] pattern masks, one row per record."""
+        p, n, keep = _buf(text)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_rec = off.size - 1
+        out = np.zeros((max(n_rec, 1), self._mw), dtype=np.uint64)
+        if not _lib.rure_b200_set_matches_batch(self._h, p, off.ctypes.data, n_rec, out.ctypes.data):
+            raise Error(_last_error())
+        return out[:n_rec]
+
+    def matches_mask_device(self, d_text, start=0):
+        out = (c_uint64 * self._mw)()
+        if not _lib.rure_b200_set_matches_device(self._h, d_text.data_ptr(), d_text.numel(), start, out):
+            raise Error(_last_error())
+        return list(out)
+
+    def matches_batch_device(self, d_text, d_offsets, d_masks):
+        n_rec = d_offsets.numel() - 1
+        if not _lib.rure_b200_set_matches_batch_device(self._h, d_text.data_ptr(), d_offsets.data_ptr(), n_rec, d_masks.data_ptr()):
+            raise Error(_last_error())
+
+    def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):
+        _lib.rure_b200_set_tuning(self._h, seg, chunk, warm, block, blocks_per_sm)
+
+    def dfa(self, kind=DFA_FWD_UNANCHORED_ALL):
+        return _Compiled.dfa(self, kind)
+
+
+class BytesRegexSet(_SetBase):
+    """`regex::bytes::RegexSet` (src/re_set.rs)."""
+
+
+class RegexSet(_SetBase):
+    """`regex::RegexSet` (src/re_set.rs)."""
+    _only_utf8 = True
+
+
+def compiled_with():
+    return {"lib": _LIB_PATH, "arch": "sm_100a"}

@@ -1,0 +1,336 @@
+// extern "C" surface declared in include/rure.h and include/rure_b200.h.
+// Thin: argument checks, object lifetime, and calls into rbgpu::Regex.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/rure_b200.h"
+#include "../gpu/engine.h"
+
+using rbgpu::Regex;
+
+struct rure_options {
+  size_t size_limit = 10u << 20;
+  size_t dfa_size_limit = 2u << 20;
+};
+struct rure_error {
+  std::string msg = "no error";
+};
+struct rure {
+  Regex* re = nullptr;
+};
+struct rure_set {
+  Regex* re = nullptr;
+};
+struct rure_captures {
+  bool has = false;
+  rure_match m{0, 0};
+};
+struct rure_iter {
+  rure* re;
+  size_t last_end = 0;
+  bool has_last_match = false;
+  size_t last_match = 0;
+  // all spans of the haystack seen on the first call (see rure.h)
+  const uint8_t* hay = nullptr;
+  size_t len = 0;
+  bool cached = false;
+  std::vector<rure_match> spans;
+  size_t next = 0;
+};
+struct rure_iter_capture_names {
+  int unused;
+};
+
+static thread_local std::string g_last_error;
+
+static bool ok(Regex* re, int rc) {
+  if (rc == 0) return true;
+  g_last_error = re->last_error();
+  return false;
+}
+// The scalar reference API cannot report runtime failures (Rust panics abort,
+// regex-capi/src/macros.rs:11-27); a search that cannot run on the GPU does the same.
+[[noreturn]] static void die(const char* where) {
+  std::fprintf(stderr, "regex_b200: %s failed: %s\n", where, g_last_error.c_str());
+  std::abort();
+}
+
+static Regex* compile_common(const std::vector<std::string>& pats, uint32_t flags, rure_options* options,
+                             rure_error* error, bool only_utf8, bool as_set) {
+  rbgpu::CompileOptions o;
+  o.flags = flags;
+  o.only_utf8 = only_utf8;
+  o.as_set = as_set;
+  if (options) { o.size_limit = options->size_limit; o.dfa_size_limit = options->dfa_size_limit; }
+  rb::Error err;
+  Regex* re = Regex::compile(pats, o, &err);
+  if (!re) {
+    if (error) error->msg = err.msg;
+    g_last_error = err.msg;
+  }
+  return re;
+}
+
+extern "C" {
+
+rure* rure_compile(const uint8_t* pattern, size_t length, uint32_t flags, rure_options* options, rure_error* error) {
+  Regex* re = compile_common({std::string((const char*)pattern, length)}, flags, options, error, false, false);
+  if (!re) return nullptr;
+  rure* r = new rure();
+  r->re = re;
+  return r;
+}
+rure* rure_b200_compile_str(const uint8_t* pattern, size_t length, uint32_t flags, rure_options* options, rure_error* error) {
+  Regex* re = compile_common({std::string((const char*)pattern, length)}, flags, options, error, true, false);
+  if (!re) return nullptr;
+  rure* r = new rure();
+  r->re = re;
+  return r;
+}
+rure* rure_compile_must(const char* pattern) {
+  rure_error err;
+  rure* r = rure_compile((const uint8_t*)pattern, std::strlen(pattern), RURE_DEFAULT_FLAGS, nullptr, &err);
+  if (!r) {
+    std::fprintf(stderr, "%s\naborting from rure_compile_must\n", err.msg.c_str());
+    std::abort();
+  }
+  return r;
+}
+void rure_free(rure* re) {
+  if (!re) return;
+  delete re->re;
+  delete re;
+}
+
+bool rure_is_match(rure* re, const uint8_t* haystack, size_t length, size_t start) {
+  bool found = false;
+  uint64_t end = 0;
+  if (!ok(re->re, re->re->shortest_match_host(haystack, length, start, &found, &end))) die("rure_is_match");
+  return found;
+}
+bool rure_shortest_match(rure* re, const uint8_t* haystack, size_t length, size_t start, size_t* end) {
+  bool found = false;
+  uint64_t e = 0;
+  if (!ok(re->re, re->re->shortest_match_host(haystack, length, start, &found, &e))) die("rure_shortest_match");
+  if (found && end) *end = e;
+  return found;
+}
+bool rure_find(rure* re, const uint8_t* haystack, size_t length, size_t start, rure_match* match) {
+  bool found = false;
+  uint64_t s = 0, e = 0;
+  if (!ok(re->re, re->re->find_at_host(haystack, length, start, &found, &s, &e))) die("rure_find");
+  if (found && match) { match->start = s; match->end = e; }
+  return found;
+}
+bool rure_find_captures(rure* re, const uint8_t* haystack, size_t length, size_t start, rure_captures* captures) {
+  rure_match m;
+  bool found = rure_find(re, haystack, length, start, &m);
+  if (captures) { captures->has = found; if (found) captures->m = m; }
+  return found;
+}
+int32_t rure_capture_name_index(rure*, const char*) { return -1; }
+rure_iter_capture_names* rure_iter_capture_names_new(rure*) { return new rure_iter_capture_names(); }
+void rure_iter_capture_names_free(rure_iter_capture_names* it) { delete it; }
+bool rure_iter_capture_names_next(rure_iter_capture_names*, char**) { return false; }
+
+rure_iter* rure_iter_new(rure* re) {
+  rure_iter* it = new rure_iter();
+  it->re = re;
+  return it;
+}
+void rure_iter_free(rure_iter* it) { delete it; }
+bool rure_iter_next(rure_iter* it, const uint8_t* haystack, size_t length, rure_match* match) {
+  if (!it->cached || it->hay != haystack || it->len != length) {
+    // Continue the chain from last_end on this haystack: find_iter restarted at
+    // last_end is exactly the remaining sequence (re_trait.rs:197-220).
+    it->hay = haystack;
+    it->len = length;
+    it->spans.clear();
+    it->next = 0;
+    it->cached = true;
+    if (it->last_end <= length) {
+      uint64_t total = 0;
+      size_t cap = 1 << 12;
+      for (;;) {
+        it->spans.resize(cap);
+        if (!ok(it->re->re, it->re->re->find_all_host(haystack, length, it->last_end, (uint64_t*)it->spans.data(), cap, &total)))
+          die("rure_iter_next");
+        if (total <= cap) break;
+        cap = total;
+      }
+      it->spans.resize(total);
+      // The empty-match skip rule depends on the previous match of this iterator.
+      if (it->has_last_match && !it->spans.empty() && it->spans[0].start == it->spans[0].end &&
+          it->spans[0].end == it->last_match)
+        it->next = 1;
+    }
+  }
+  if (it->next >= it->spans.size()) {
+    it->last_end = length + 1;
+    return false;
+  }
+  const rure_match m = it->spans[it->next++];
+  it->last_end = (m.start == m.end) ? m.end + 1 : m.end;
+  it->has_last_match = true;
+  it->last_match = m.end;
+  if (match) *match = m;
+  return true;
+}
+bool rure_iter_next_captures(rure_iter* it, const uint8_t* haystack, size_t length, rure_captures* captures) {
+  rure_match m;
+  bool found = rure_iter_next(it, haystack, length, &m);
+  if (captures) { captures->has = found; if (found) captures->m = m; }
+  return found;
+}
+
+rure_captures* rure_captures_new(rure*) { return new rure_captures(); }
+void rure_captures_free(rure_captures* c) { delete c; }
+bool rure_captures_at(rure_captures* c, size_t i, rure_match* match) {
+  if (i != 0 || !c->has) return false;
+  if (match) *match = c->m;
+  return true;
+}
+size_t rure_captures_len(rure_captures*) { return 1; }
+
+rure_options* rure_options_new(void) { return new rure_options(); }
+void rure_options_free(rure_options* o) { delete o; }
+void rure_options_size_limit(rure_options* o, size_t limit) { o->size_limit = limit; }
+void rure_options_dfa_size_limit(rure_options* o, size_t limit) { o->dfa_size_limit = limit; }
+
+rure_set* rure_compile_set(const uint8_t** patterns, const size_t* lengths, size_t count, uint32_t flags,
+                           rure_options* options, rure_error* error) {
+  std::vector<std::string> pats;
+  for (size_t i = 0; i < count; i++) pats.emplace_back((const char*)patterns[i], lengths[i]);
+  Regex* re = compile_common(pats, flags, options, error, false, true);
+  if (!re) return nullptr;
+  rure_set* s = new rure_set();
+  s->re = re;
+  return s;
+}
+rure_set* rure_b200_compile_set_str(const uint8_t** patterns, const size_t* lengths, size_t count, uint32_t flags,
+                                    rure_options* options, rure_error* error) {
+  std::vector<std::string> pats;
+  for (size_t i = 0; i < count; i++) pats.emplace_back((const char*)patterns[i], lengths[i]);
+  Regex* re = compile_common(pats, flags, options, error, true, true);
+  if (!re) return nullptr;
+  rure_set* s = new rure_set();
+  s->re = re;
+  return s;
+}
+void rure_set_free(rure_set* s) {
+  if (!s) return;
+  delete s->re;
+  delete s;
+}
+bool rure_set_is_match(rure_set* s, const uint8_t* haystack, size_t length, size_t start) {
+  bool found = false;
+  uint64_t end = 0;
+  if (!ok(s->re, s->re->shortest_match_host(haystack, length, start, &found, &end))) die("rure_set_is_match");
+  return found;
+}
+bool rure_set_matches(rure_set* s, const uint8_t* haystack, size_t length, size_t start, bool* matches) {
+  const size_t n = s->re->n_patterns();
+  for (size_t i = 0; i < n; i++) matches[i] = false;
+  uint64_t masks[4] = {0, 0, 0, 0};
+  bool any = false;
+  if (!ok(s->re, s->re->set_matches_host(haystack, length, start, &any, masks))) die("rure_set_matches");
+  for (size_t i = 0; i < n; i++) matches[i] = (masks[i / 64] >> (i % 64)) & 1;
+  return any;
+}
+size_t rure_set_len(rure_set* s) { return s->re->n_patterns(); }
+
+rure_error* rure_error_new(void) { return new rure_error(); }
+void rure_error_free(rure_error* e) { delete e; }
+const char* rure_error_message(rure_error* e) { return e->msg.c_str(); }
+
+// ------------------------------------------------------------ bulk extension --
+bool rure_b200_find_all(rure* re, const uint8_t* haystack, size_t length, rure_match* out, size_t cap, size_t* n_total) {
+  uint64_t total = 0;
+  bool r = ok(re->re, re->re->find_all_host(haystack, length, 0, (uint64_t*)out, out ? cap : 0, &total));
+  if (n_total) *n_total = total;
+  return r;
+}
+bool rure_b200_count_all(rure* re, const uint8_t* haystack, size_t length, size_t* n_total) {
+  return rure_b200_find_all(re, haystack, length, nullptr, 0, n_total);
+}
+bool rure_b200_set_matches_mask(rure_set* s, const uint8_t* haystack, size_t length, size_t start, uint64_t* mask_words) {
+  bool any;
+  return ok(s->re, s->re->set_matches_host(haystack, length, start, &any, mask_words));
+}
+bool rure_b200_is_match_batch(rure* re, const uint8_t* haystack, const uint64_t* offsets, size_t n, uint8_t* out_bits) {
+  return ok(re->re, re->re->is_match_batch_host(haystack, offsets, n, out_bits));
+}
+bool rure_b200_find_batch(rure* re, const uint8_t* haystack, const uint64_t* offsets, size_t n, rure_match* out, uint8_t* found_bits) {
+  return ok(re->re, re->re->find_batch_host(haystack, offsets, n, (uint64_t*)out, found_bits));
+}
+bool rure_b200_set_matches_batch(rure_set* s, const uint8_t* haystack, const uint64_t* offsets, size_t n, uint64_t* out_masks) {
+  return ok(s->re, s->re->set_matches_batch_host(haystack, offsets, n, out_masks));
+}
+bool rure_b200_find_all_device(rure* re, const uint8_t* d_haystack, size_t length, size_t start, rure_match* d_out, size_t cap, size_t* n_total) {
+  uint64_t total = 0;
+  bool r = ok(re->re, re->re->find_all_device(d_haystack, length, start, (uint64_t*)d_out, d_out ? cap : 0, &total));
+  if (n_total) *n_total = total;
+  return r;
+}
+bool rure_b200_shortest_match_device(rure* re, const uint8_t* d_haystack, size_t length, size_t start, bool* found, size_t* end) {
+  uint64_t e = 0;
+  bool f = false;
+  bool r = ok(re->re, re->re->shortest_match_device(d_haystack, length, start, &f, &e));
+  if (found) *found = f;
+  if (f && end) *end = e;
+  return r;
+}
+bool rure_b200_set_matches_device(rure_set* s, const uint8_t* d_haystack, size_t length, size_t start, uint64_t* mask_words) {
+  bool any;
+  return ok(s->re, s->re->set_matches_device(d_haystack, length, start, &any, mask_words));
+}
+bool rure_b200_is_match_batch_device(rure* re, const uint8_t* d_haystack, const uint64_t* d_offsets, size_t n, uint32_t* d_out_bits) {
+  return ok(re->re, re->re->is_match_batch_device(d_haystack, d_offsets, n, d_out_bits));
+}
+bool rure_b200_find_batch_device(rure* re, const uint8_t* d_haystack, const uint64_t* d_offsets, size_t n, rure_match* d_out, uint32_t* d_found_bits) {
+  return ok(re->re, re->re->find_batch_device(d_haystack, d_offsets, n, (uint64_t*)d_out, d_found_bits));
+}
+bool rure_b200_set_matches_batch_device(rure_set* s, const uint8_t* d_haystack, const uint64_t* d_offsets, size_t n, uint64_t* d_out_masks) {
+  return ok(s->re, s->re->set_matches_batch_device(d_haystack, d_offsets, n, d_out_masks));
+}
+
+const char* rure_b200_last_error(void) { return g_last_error.c_str(); }
+uint64_t rure_b200_kernel_launches(void) { return rbgpu::kernel_launches(); }
+void rure_b200_last_stats(rure* re, double* out7) {
+  const rbgpu::Stats& s = re->re->stats;
+  out7[0] = s.scan_ms; out7[1] = s.walk_ms; out7[2] = s.total_ms;
+  out7[3] = (double)s.scan_redo_rounds; out7[4] = (double)s.scan_redo_segments;
+  out7[5] = (double)s.stitch_rounds; out7[6] = (double)s.stitch_dirty_chunks;
+}
+void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block, uint32_t blocks_per_sm) {
+  rbgpu::Tuning& t = re->re->tuning;
+  if (seg) t.seg = (seg + 63) / 64 * 64;
+  if (chunk) t.chunk = (chunk + 63) / 64 * 64;
+  t.warm = warm;
+  if (block) t.block = (block + 31) / 32 * 32;
+  if (blocks_per_sm) t.blocks_per_sm = blocks_per_sm;
+}
+bool rure_b200_dfa_export(rure* re, int kind, uint32_t* info6, uint16_t* trans, uint8_t* classes, uint16_t* start, uint64_t* masks) {
+  if (kind < 0 || kind >= rbgpu::kNumDfaKinds) { g_last_error = "bad dfa kind"; return false; }
+  rb::Error err;
+  const rb::Dfa* d = re->re->host_dfa((rbgpu::DfaKind)kind, &err);
+  if (!d) { g_last_error = err.msg; return false; }
+  if (info6) {
+    info6[0] = d->n_states; info6[1] = d->n_classes; info6[2] = d->match_lo; info6[3] = d->mask_words;
+    info6[4] = d->uniform_start; info6[5] = (uint32_t)d->raw_states;
+  }
+  if (trans) std::memcpy(trans, d->trans.data(), d->trans.size() * 2);
+  if (classes) std::memcpy(classes, d->classes, 256);
+  if (start) std::memcpy(start, d->start, sizeof d->start);
+  if (masks) std::memcpy(masks, d->masks.data(), d->masks.size() * 8);
+  return true;
+}
+void rure_b200_pattern_info(rure* re, uint64_t* info4) {
+  info4[0] = re->re->min_len; info4[1] = re->re->max_len;
+  info4[2] = re->re->can_match_empty; info4[3] = re->re->has_looks;
+}
+
+}  // extern "C"

@@ -1,0 +1,603 @@
+// Host orchestration of the search kernels.  See engine.h.
+#include "engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "launch.h"
+
+namespace rbgpu {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launches() { return g_launches.load(); }
+
+int device_sm_count() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  }
+  return sms;
+}
+
+DeviceBuf::~DeviceBuf() { if (ptr) cudaFree(ptr); }
+void* DeviceBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return ptr;
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = std::max<size_t>(bytes, 256);
+  if (cudaMalloc(&ptr, want) != cudaSuccess) { ptr = nullptr; return nullptr; }
+  cap = want;
+  return ptr;
+}
+
+struct Regex::DeviceDfa {
+  DfaView view;
+  void* trans = nullptr;
+  void* classes = nullptr;
+  void* masks = nullptr;
+  ~DeviceDfa() { cudaFree(trans); cudaFree(classes); cudaFree(masks); }
+};
+
+// ------------------------------------------------------------------ compile --
+Regex* Regex::compile(const std::vector<std::string>& patterns, const CompileOptions& opt, rb::Error* err) {
+  std::unique_ptr<Regex> re(new Regex());
+  re->patterns_ = patterns;
+  re->opt_ = opt;
+  re->only_utf8 = opt.only_utf8;
+  re->is_set_ = opt.as_set || patterns.size() != 1;
+  rb::Flags f;
+  f.casei = opt.flags & 1; f.multi = opt.flags & 2; f.dotnl = opt.flags & 4; f.swap_greed = opt.flags & 8;
+  f.ignore_space = opt.flags & 16; f.unicode = opt.flags & 32;
+  f.allow_bytes = !opt.only_utf8;  // exec.rs:224-225
+  re->exprs_.resize(patterns.size());
+  re->min_len = rb::kUnbounded;
+  re->max_len = 0;
+  for (size_t i = 0; i < patterns.size(); i++) {
+    if (!rb::parse(patterns[i], f, 200, &re->exprs_[i], err)) return nullptr;
+    uint64_t mn, mx;
+    rb::expr_len_range(re->exprs_[i], &mn, &mx);
+    re->min_len = std::min(re->min_len, mn);
+    re->max_len = std::max(re->max_len, mx);
+  }
+  if (patterns.empty()) { re->min_len = 0; return re.release(); }
+  re->can_match_empty = re->min_len == 0;
+  // Validate eagerly what the reference validates at build time (program size)
+  // plus the two explicit errors of this backend (Unicode \b, table budget).
+  rb::Program probe;
+  rb::CompileOptions co;
+  co.only_utf8 = opt.only_utf8;
+  co.size_limit = opt.size_limit;
+  if (!rb::compile(re->exprs_, co, &probe, err)) return nullptr;
+  re->has_looks = probe.has_looks;
+  if (probe.has_unicode_word_boundary) {
+    err->kind = rb::Error::UnicodeWordBoundary;
+    err->msg = "Unicode word boundaries (\\b, \\B) are not supported by the B200 DFA backend; use (?-u:\\b).";
+    return nullptr;
+  }
+  if (patterns.size() > 64 * kMaxMaskWords) {
+    err->kind = rb::Error::DfaTooBig;
+    err->msg = "regex sets larger than 256 patterns exceed the per-state mask budget";
+    return nullptr;
+  }
+  // Determinize the tables every object needs so budget errors surface at compile time.
+  if (!re->host_dfa(kFwdUnanchoredAll, err)) return nullptr;
+  if (!re->is_set_) {
+    if (!re->host_dfa(kFwdAnchoredLF, err)) return nullptr;
+    if (!re->host_dfa(kRevUnanchoredAll, err)) return nullptr;
+  }
+  return re.release();
+}
+
+Regex::~Regex() {
+  for (auto*& d : dev_) { delete d; d = nullptr; }
+  if (pinned_) cudaFreeHost(pinned_);
+  if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
+}
+
+const rb::Dfa* Regex::host_dfa(DfaKind k, rb::Error* err) {
+  if (host_[k]) return host_[k].get();
+  rb::CompileOptions co;
+  co.only_utf8 = opt_.only_utf8;
+  co.size_limit = opt_.size_limit;
+  rb::DfaOptions dopt;
+  dopt.max_table_bytes = opt_.dfa_size_limit * 16;
+  switch (k) {
+    case kFwdAnchoredLF: co.reverse = false; co.unanchored_prefix = false; dopt.anchored = true; dopt.leftmost_first = true; break;
+    case kRevUnanchoredAll: co.reverse = true; co.unanchored_prefix = true; dopt.anchored = false; dopt.leftmost_first = false; break;
+    case kFwdUnanchoredAll: co.reverse = false; co.unanchored_prefix = true; dopt.anchored = false; dopt.leftmost_first = false; break;
+    case kRevAnchoredLongest: co.reverse = true; co.unanchored_prefix = false; dopt.anchored = true; dopt.leftmost_first = false; break;
+    case kFwdUnanchoredLF: co.reverse = false; co.unanchored_prefix = true; dopt.anchored = false; dopt.leftmost_first = true; break;
+    default: return nullptr;
+  }
+  if (is_set_ || patterns_.size() != 1) dopt.leftmost_first = false;  // dfa.rs:1557-1559
+  rb::Program prog;
+  if (!rb::compile(exprs_, co, &prog, err)) return nullptr;
+  std::unique_ptr<rb::Dfa> d(new rb::Dfa());
+  if (!rb::determinize(prog, dopt, d.get(), err)) return nullptr;
+  host_[k] = std::move(d);
+  return host_[k].get();
+}
+
+int Regex::fail(const std::string& msg) {
+  error_ = msg;
+  return -1;
+}
+int Regex::check(int e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return fail(std::string("CUDA error in ") + what + ": " + cudaGetErrorString((cudaError_t)e));
+}
+#define RB_CUDA(call)                                   \
+  do {                                                  \
+    int rc__ = check((int)(call), #call);               \
+    if (rc__) return rc__;                              \
+  } while (0)
+#define RB_LAUNCH_CHECK(name)                           \
+  do {                                                  \
+    g_launches++;                                       \
+    int rc__ = check((int)cudaGetLastError(), name);    \
+    if (rc__) return rc__;                              \
+  } while (0)
+
+int Regex::ensure(DfaKind k, DeviceDfa** out) {
+  if (!stream_) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail("no CUDA device available: regex_b200 has no CPU matching path");
+    cudaStream_t s;
+    RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    stream_ = s;
+    RB_CUDA(cudaMallocHost(&pinned_, 4096));
+  }
+  if (dev_[k]) { *out = dev_[k]; return 0; }
+  rb::Error err;
+  const rb::Dfa* h = host_dfa(k, &err);
+  if (!h) return fail(err.msg);
+  std::unique_ptr<DeviceDfa> d(new DeviceDfa());
+  const size_t tb = h->trans.size() * sizeof(uint16_t);
+  RB_CUDA(cudaMalloc(&d->trans, std::max<size_t>(tb, 16)));
+  RB_CUDA(cudaMalloc(&d->classes, 256));
+  RB_CUDA(cudaMalloc(&d->masks, std::max<size_t>(h->masks.size() * 8, 16)));
+  RB_CUDA(cudaMemcpy(d->trans, h->trans.data(), tb, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(d->classes, h->classes, 256, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(d->masks, h->masks.data(), h->masks.size() * 8, cudaMemcpyHostToDevice));
+  DfaView& v = d->view;
+  v.trans = (const uint16_t*)d->trans;
+  v.classes = (const uint8_t*)d->classes;
+  v.masks = (const uint64_t*)d->masks;
+  v.n_states = h->n_states;
+  v.stride = h->n_classes;
+  v.match_lo = h->match_lo;
+  v.mask_words = h->mask_words;
+  v.table_bytes = (uint32_t)tb;
+  std::memcpy(v.start, h->start, sizeof v.start);
+  v.uniform_start = h->uniform_start;
+  dev_[k] = d.release();
+  *out = dev_[k];
+  return 0;
+}
+
+// Shared-memory staging decision: table + class map must fit the opt-in limit.
+static size_t smem_for(const DfaView& v) {
+  size_t need = ((size_t)v.table_bytes + 15) / 16 * 16 + 256;
+  return need <= 200 * 1024 ? need : 0;
+}
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t blocks_per_sm) {
+  uint64_t blocks = (threads_needed + block - 1) / block;
+  uint64_t cap = (uint64_t)std::max(1, device_sm_count()) * blocks_per_sm;
+  return (uint32_t)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+static uint32_t pick_warm(const Regex& re) {
+  if (re.tuning.warm) return (re.tuning.warm + 15) / 16 * 16;
+  if (re.max_len != rb::kUnbounded) return (uint32_t)std::min<uint64_t>((std::max<uint64_t>(re.max_len, 1) + 15) / 16 * 16, 4096);
+  return 128;
+}
+
+// ------------------------------------------------------------- start bitmap --
+int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
+  DeviceDfa* rev;
+  if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const uint64_t base = start & ~63ull;
+  const uint32_t seg = tuning.seg;
+  const uint64_t n_seg = (n + 1 - base + seg - 1) / seg;
+  if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
+  ScanArgs a{};
+  a.dfa = rev->view;
+  const size_t smem = smem_for(rev->view);
+  a.use_smem = smem != 0;
+  a.text = d_text;
+  a.n = n;
+  a.base = base;
+  a.n_seg = n_seg;
+  a.seg = seg;
+  a.warm = pick_warm(*this);
+  a.bitmap = (uint64_t*)bitmap_.ensure(((n >> 6) + 2) * 8);
+  a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
+  a.fin = (uint16_t*)fin_.ensure(n_seg * 2);
+  uint32_t* redo = (uint32_t*)redo_.ensure(n_seg * 4);
+  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
+  a.utf8_boundaries = only_utf8 && can_match_empty;
+  RB_CUDA(allow_smem(scan_rev_bitmap, smem));
+  scan_rev_bitmap<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
+  RB_LAUNCH_CHECK("scan_rev_bitmap");
+  stats.scan_redo_rounds = stats.scan_redo_segments = 0;
+  for (;;) {
+    RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
+    verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 1, redo, counters);
+    RB_LAUNCH_CHECK("verify_segments");
+    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 4, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_redo = *(uint32_t*)pinned_;
+    if (n_redo == 0) break;
+    stats.scan_redo_rounds++;
+    stats.scan_redo_segments += n_redo;
+    ScanArgs r = a;
+    r.redo_list = redo;
+    r.n_redo = counters;
+    scan_rev_bitmap<<<grid_for(n_redo, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(r);
+    RB_LAUNCH_CHECK("scan_rev_bitmap(redo)");
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ find_all --
+int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t* d_out, uint64_t cap, uint64_t* total) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *total = 0;
+  if (is_set_) return fail("find requires exactly one pattern (RegexSet cannot be used with find, exec.rs:510-512)");
+  if (start > n) return 0;  // re_trait.rs:198-200
+  DeviceDfa *fwd, *rev = nullptr;
+  if (int rc = ensure(kFwdAnchoredLF, &fwd)) return rc;
+  const bool emulate = has_looks;
+  if (emulate) if (int rc = ensure(kRevAnchoredLongest, &rev)) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaEvent_t ev[3];
+  for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
+  RB_CUDA(cudaEventRecord(ev[0], st));
+  if (int rc = scan_starts(d_text, n, start)) return rc;
+  RB_CUDA(cudaEventRecord(ev[1], st));
+
+  WalkArgs w{};
+  w.fwd = fwd->view;
+  if (rev) w.rev = rev->view;
+  w.text = d_text;
+  w.n = n;
+  w.bitmap = (const uint64_t*)bitmap_.ptr;
+  w.base = start & ~63ull;
+  w.chunk = tuning.chunk;
+  w.n_chunks = (n + 1 - w.base + w.chunk - 1) / w.chunk;
+  const uint64_t nc = w.n_chunks;
+  w.in_p = (uint64_t*)in_p_.ensure(nc * 8);
+  w.in_lm = (uint64_t*)in_lm_.ensure(nc * 8);
+  w.out_p = (uint64_t*)out_p_.ensure(nc * 8);
+  w.out_lm = (uint64_t*)out_lm_.ensure(nc * 8);
+  w.count = (uint64_t*)count_.ensure(nc * 8);
+  uint64_t* offset = (uint64_t*)offset_.ensure(nc * 8);
+  w.dirty = (uint8_t*)dirty_.ensure(nc);
+  const uint64_t n_blocks = (nc + 1023) / 1024;
+  uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
+  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !w.dirty || !block_sums || !counters)
+    return fail("out of device memory (walk scratch)");
+  w.offset = offset;
+  w.out = d_out;
+  w.cap = d_out ? cap : 0;
+  w.utf8 = only_utf8;
+  w.emulate_slice = emulate;
+  w.can_match_empty = can_match_empty;
+  // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
+  init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, start);
+  RB_LAUNCH_CHECK("init_walk_entries");
+  const uint32_t wgrid = grid_for(nc, 128, 16);
+  WalkArgs w0 = w;
+  w0.dirty = nullptr;
+  walk_chunks<false><<<wgrid, 128, 0, st>>>(w0);
+  RB_LAUNCH_CHECK("walk_chunks<count>");
+  stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
+  for (;;) {
+    RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
+    stitch_check<<<grid_for(nc, 256, 8), 256, 0, st>>>(w, counters);
+    RB_LAUNCH_CHECK("stitch_check");
+    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 4, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_dirty = *(uint32_t*)pinned_;
+    if (n_dirty == 0) break;
+    stats.stitch_rounds++;
+    stats.stitch_dirty_chunks += n_dirty;
+    walk_chunks<false><<<wgrid, 128, 0, st>>>(w);
+    RB_LAUNCH_CHECK("walk_chunks<recount>");
+  }
+  unsigned long long* grand = (unsigned long long*)(counters + 4);
+  scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w.count, offset, block_sums, nc);
+  RB_LAUNCH_CHECK("scan_counts_local");
+  scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, grand);
+  RB_LAUNCH_CHECK("scan_block_sums");
+  scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(offset, block_sums, nc);
+  RB_LAUNCH_CHECK("scan_add_block_offsets");
+  if (w.cap > 0) {
+    walk_chunks<true><<<wgrid, 128, 0, st>>>(w);
+    RB_LAUNCH_CHECK("walk_chunks<emit>");
+  }
+  RB_CUDA(cudaMemcpyAsync(pinned_, grand, 8, cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaEventRecord(ev[2], st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  *total = *(uint64_t*)pinned_;
+  cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
+  cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
+  cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+int Regex::find_at_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *found = false;
+  uint64_t* d_out = (uint64_t*)out_.ensure(16);
+  if (!d_out) return fail("out of device memory");
+  uint64_t total = 0;
+  // The first element of the find_iter chain started at `start` is find_at(start).
+  if (int rc = find_all_device(d_text, n, start, d_out, 1, &total)) return rc;
+  if (total == 0) return 0;
+  uint64_t h[2];
+  RB_CUDA(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+  *found = true;
+  *s = h[0];
+  *e = h[1];
+  return 0;
+}
+
+// ------------------------------------------------------ forward reductions ----
+int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host) {
+  DeviceDfa* fwd;
+  if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const uint32_t seg = tuning.seg;
+  const uint64_t n_seg = (n + 1 - start + seg - 1) / seg;
+  if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
+  const uint32_t mw = fwd->view.mask_words;
+  ScanArgs a{};
+  a.dfa = fwd->view;
+  const size_t smem = smem_for(fwd->view);
+  a.use_smem = smem != 0;
+  a.text = d_text;
+  a.n = n;
+  a.base = start;
+  a.n_seg = n_seg;
+  a.seg = seg;
+  a.warm = pick_warm(*this);
+  a.seg_first = (uint64_t*)seg_first_.ensure(n_seg * 8);
+  a.seg_mask = want_masks ? (uint64_t*)seg_mask_.ensure(n_seg * 8 * mw) : nullptr;
+  a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
+  a.fin = (uint16_t*)fin_.ensure(n_seg * 2);
+  uint32_t* redo = (uint32_t*)redo_.ensure(n_seg * 4);
+  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  if (!a.seg_first || (want_masks && !a.seg_mask) || !a.guess || !a.fin || !redo || !counters)
+    return fail("out of device memory (scan scratch)");
+  RB_CUDA(allow_smem(scan_fwd_reduce, smem));
+  scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
+  RB_LAUNCH_CHECK("scan_fwd_reduce");
+  for (;;) {
+    RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
+    verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 0, redo, counters);
+    RB_LAUNCH_CHECK("verify_segments");
+    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 4, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_redo = *(uint32_t*)pinned_;
+    if (n_redo == 0) break;
+    ScanArgs r = a;
+    r.redo_list = redo;
+    r.n_redo = counters;
+    scan_fwd_reduce<<<grid_for(n_redo, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(r);
+    RB_LAUNCH_CHECK("scan_fwd_reduce(redo)");
+  }
+  unsigned long long* result = (unsigned long long*)(counters + 4);
+  uint64_t* h = (uint64_t*)pinned_ + 16;
+  h[0] = kNone;
+  for (uint32_t w = 0; w < kMaxMaskWords; w++) h[1 + w] = 0;
+  RB_CUDA(cudaMemcpyAsync(result, h, 8 * (1 + kMaxMaskWords), cudaMemcpyHostToDevice, st));
+  reduce_segments<<<grid_for(n_seg, 256, 4), 256, 0, st>>>(a.seg_first, a.seg_mask, n_seg, mw, result);
+  RB_LAUNCH_CHECK("reduce_segments");
+  RB_CUDA(cudaMemcpyAsync(h, result, 8 * (1 + kMaxMaskWords), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t w = 0; w < 1 + kMaxMaskWords; w++) result_host[w] = h[w];
+  return 0;
+}
+
+int Regex::shortest_match_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* end) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *found = false;
+  if (patterns_.empty() || start > n) return 0;
+  uint64_t res[1 + kMaxMaskWords];
+  if (int rc = forward_reduce(d_text, n, start, false, res)) return rc;
+  if (res[0] != kNone) { *found = true; *end = res[0]; }
+  return 0;
+}
+
+int Regex::set_matches_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* any, uint64_t* masks) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *any = false;
+  const uint32_t mw = (uint32_t)((patterns_.size() + 63) / 64);
+  for (uint32_t w = 0; w < mw; w++) masks[w] = 0;
+  if (patterns_.empty() || start > n) return 0;
+  uint64_t res[1 + kMaxMaskWords];
+  if (int rc = forward_reduce(d_text, n, start, true, res)) return rc;
+  for (uint32_t w = 0; w < mw; w++) { masks[w] = res[1 + w]; if (res[1 + w]) *any = true; }
+  return 0;
+}
+
+// -------------------------------------------------------------------- batch ----
+int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n_rec == 0) return 0;
+  if (patterns_.empty()) { RB_CUDA(cudaMemset(d_bits, 0, (n_rec + 31) / 32 * 4)); return 0; }
+  DeviceDfa* fwd;
+  if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
+  BatchArgs a{};
+  a.fwd = fwd->view;
+  const size_t smem = smem_for(fwd->view);
+  a.use_smem = smem != 0;
+  a.text = d_text;
+  a.offsets = d_offsets;
+  a.n_rec = n_rec;
+  a.out_bits = d_bits;
+  RB_CUDA(allow_smem(is_match_batch, smem));
+  is_match_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
+  RB_LAUNCH_CHECK("is_match_batch");
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  return 0;
+}
+
+int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_spans, uint32_t* d_bits) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n_rec == 0) return 0;
+  if (is_set_) return fail("find requires exactly one pattern");
+  DeviceDfa *fwd, *rev;
+  if (int rc = ensure(kFwdUnanchoredLF, &fwd)) return rc;
+  if (int rc = ensure(kRevAnchoredLongest, &rev)) return rc;
+  BatchArgs a{};
+  a.fwd = fwd->view;
+  a.rev = rev->view;
+  a.text = d_text;
+  a.offsets = d_offsets;
+  a.n_rec = n_rec;
+  a.out_bits = d_bits;
+  a.out_spans = d_spans;
+  find_batch<<<(uint32_t)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
+  RB_LAUNCH_CHECK("find_batch");
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  return 0;
+}
+
+int Regex::set_matches_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_masks) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (n_rec == 0) return 0;
+  const uint32_t mw = (uint32_t)std::max<size_t>(1, (patterns_.size() + 63) / 64);
+  if (patterns_.empty()) { RB_CUDA(cudaMemset(d_masks, 0, n_rec * 8 * mw)); return 0; }
+  DeviceDfa* fwd;
+  if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
+  BatchArgs a{};
+  a.fwd = fwd->view;
+  const size_t smem = smem_for(fwd->view);
+  a.use_smem = smem != 0;
+  a.text = d_text;
+  a.offsets = d_offsets;
+  a.n_rec = n_rec;
+  a.out_masks = d_masks;
+  RB_CUDA(allow_smem(set_matches_batch, smem));
+  set_matches_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
+  RB_LAUNCH_CHECK("set_matches_batch");
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  return 0;
+}
+
+// ------------------------------------------------------------ host wrappers ----
+const uint8_t* Regex::upload_text(const uint8_t* text, uint64_t n, int* rc) {
+  *rc = 0;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    *rc = fail("no CUDA device available: regex_b200 has no CPU matching path");
+    return nullptr;
+  }
+  uint8_t* d = (uint8_t*)text_.ensure(n + 64);
+  if (!d) { *rc = fail("out of device memory (haystack)"); return nullptr; }
+  if (n) {
+    int e = (int)cudaMemcpy(d, text, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { *rc = check(e, "haystack upload"); return nullptr; }
+  }
+  return d;
+}
+
+int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64_t* out, uint64_t cap, uint64_t* total) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  uint64_t* d_out = nullptr;
+  if (out && cap) {
+    d_out = (uint64_t*)out_.ensure(cap * 16);
+    if (!d_out) return fail("out of device memory (spans)");
+  }
+  if ((rc = find_all_device(d, n, start, d_out, cap, total))) return rc;
+  const uint64_t k = std::min(cap, *total);
+  if (d_out && k) RB_CUDA(cudaMemcpy(out, d_out, k * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int Regex::find_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  return find_at_device(d, n, start, found, s, e);
+}
+int Regex::shortest_match_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* end) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  return shortest_match_device(d, n, start, found, end);
+}
+int Regex::set_matches_host(const uint8_t* text, uint64_t n, uint64_t start, bool* any, uint64_t* masks) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  return set_matches_device(d, n, start, any, masks);
+}
+int Regex::is_match_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint8_t* out_bits) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint64_t n = n_rec ? offsets[n_rec] : 0;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  uint64_t* d_off = (uint64_t*)offsets_.ensure((n_rec + 1) * 8);
+  uint32_t* d_bits = (uint32_t*)bits_.ensure((n_rec + 31) / 32 * 4 + 4);
+  if (!d_off || !d_bits) return fail("out of device memory (batch)");
+  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  if ((rc = is_match_batch_device(d, d_off, n_rec, d_bits))) return rc;
+  RB_CUDA(cudaMemcpy(out_bits, d_bits, (n_rec + 7) / 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int Regex::find_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* spans, uint8_t* out_bits) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint64_t n = n_rec ? offsets[n_rec] : 0;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  uint64_t* d_off = (uint64_t*)offsets_.ensure((n_rec + 1) * 8);
+  uint32_t* d_bits = (uint32_t*)bits_.ensure((n_rec + 31) / 32 * 4 + 4);
+  uint64_t* d_spans = (uint64_t*)out_.ensure(std::max<uint64_t>(n_rec, 1) * 16);
+  if (!d_off || !d_bits || !d_spans) return fail("out of device memory (batch)");
+  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  if ((rc = find_batch_device(d, d_off, n_rec, d_spans, d_bits))) return rc;
+  RB_CUDA(cudaMemcpy(out_bits, d_bits, (n_rec + 7) / 8, cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaMemcpy(spans, d_spans, n_rec * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int Regex::set_matches_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* masks) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint64_t n = n_rec ? offsets[n_rec] : 0;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  const uint32_t mw = (uint32_t)std::max<size_t>(1, (patterns_.size() + 63) / 64);
+  uint64_t* d_off = (uint64_t*)offsets_.ensure((n_rec + 1) * 8);
+  uint64_t* d_masks = (uint64_t*)masks_.ensure(std::max<uint64_t>(n_rec, 1) * 8 * mw);
+  if (!d_off || !d_masks) return fail("out of device memory (batch)");
+  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  if ((rc = set_matches_batch_device(d, d_off, n_rec, d_masks))) return rc;
+  RB_CUDA(cudaMemcpy(masks, d_masks, n_rec * 8 * mw, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace rbgpu

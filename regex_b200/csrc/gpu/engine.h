@@ -1,0 +1,119 @@
+// Host side of the B200 search backend: owns the determinized tables on the
+// device and orchestrates the kernels.  This is the analogue of the reference's
+// ExecNoSync (src/exec.rs:365-596): same operations, same results, but every
+// search runs on the GPU -- there is no CPU matching path in this library.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../dfa/determinize.h"
+#include "../frontend/frontend.h"
+
+namespace rbgpu {
+
+struct CompileOptions {
+  uint32_t flags = 32;               // RURE_FLAG_* bits (rure.h:56-68); default = UNICODE
+  size_t size_limit = 10u << 20;     // program size limit (re_builder.rs:29)
+  size_t dfa_size_limit = 2u << 20;  // scaled x16 into the dense-table budget
+  bool only_utf8 = false;            // false = bytes::Regex, true = Regex (str)
+  bool as_set = false;               // RegexSet semantics even for one pattern
+};
+
+enum DfaKind { kFwdAnchoredLF = 0, kRevUnanchoredAll, kFwdUnanchoredAll, kRevAnchoredLongest, kFwdUnanchoredLF, kNumDfaKinds };
+
+struct Tuning {
+  uint32_t seg = 1024;     // positions per scan segment (multiple of 64)
+  uint32_t chunk = 4096;   // positions per chain-walk chunk (multiple of 64)
+  uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
+  uint32_t block = 256;
+  uint32_t blocks_per_sm = 8;
+};
+
+struct Stats {  // filled by the last single-haystack call (diagnostics, bench roofline)
+  uint64_t scan_redo_rounds = 0, scan_redo_segments = 0;
+  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0;
+  float scan_ms = 0, walk_ms = 0, total_ms = 0;
+};
+
+class DeviceBuf {
+ public:
+  ~DeviceBuf();
+  void* ensure(size_t bytes);  // grow-only
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+class Regex {
+ public:
+  static Regex* compile(const std::vector<std::string>& patterns, const CompileOptions& opt, rb::Error* err);
+  ~Regex();
+
+  size_t n_patterns() const { return patterns_.size(); }
+  bool is_set() const { return is_set_; }
+  const rb::Dfa* host_dfa(DfaKind k, rb::Error* err);  // builds lazily (also used by tests to inspect tables)
+
+  // ---- single haystack, device-resident text --------------------------------
+  // find_iter (re_trait.rs:197-220): writes up to cap {start,end} pairs to d_out
+  // (device memory, may be null to count only); *total = number of matches.
+  int find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t* d_out, uint64_t cap, uint64_t* total);
+  // find_at (exec.rs:473-514)
+  int find_at_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e);
+  // shortest_match_at / is_match_at (exec.rs:382-468); for sets: any pattern.
+  int shortest_match_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* end);
+  // RegexSet::matches (re_set.rs:184-213): masks = ceil(n_patterns/64) words (host).
+  int set_matches_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* any, uint64_t* masks);
+
+  // ---- batched records, device-resident text + offsets[n_rec+1] --------------
+  int is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits);
+  int find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_spans, uint32_t* d_bits);
+  int set_matches_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_masks);
+
+  // ---- host-buffer wrappers (copies inside; the e2e path) ---------------------
+  int find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64_t* out, uint64_t cap, uint64_t* total);
+  int find_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e);
+  int shortest_match_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* end);
+  int set_matches_host(const uint8_t* text, uint64_t n, uint64_t start, bool* any, uint64_t* masks);
+  int is_match_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint8_t* out_bits);
+  int find_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* spans, uint8_t* out_bits);
+  int set_matches_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* masks);
+
+  const std::string& last_error() const { return error_; }
+  Tuning tuning;
+  Stats stats;
+  uint64_t min_len = 0, max_len = 0;  // match length range in bytes (max = kUnbounded)
+  bool can_match_empty = false;
+  bool has_looks = false;
+  bool only_utf8 = false;
+
+ private:
+  Regex() = default;
+  struct DeviceDfa;
+  int ensure(DfaKind k, DeviceDfa** out);
+  int fail(const std::string& msg);
+  int check(int cuda_err, const char* what);
+  int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start);
+  int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
+  const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
+
+  std::vector<std::string> patterns_;
+  bool is_set_ = false;
+  CompileOptions opt_;
+  std::vector<rb::Expr> exprs_;
+  std::unique_ptr<rb::Dfa> host_[kNumDfaKinds];
+  DeviceDfa* dev_[kNumDfaKinds] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string error_;
+  std::recursive_mutex mu_;
+  void* stream_ = nullptr;
+  // scratch (grow-only)
+  DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
+  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, block_sums_, out_, bits_, masks_;
+  void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
+};
+
+uint64_t kernel_launches();  // total kernels launched by this library in this process
+int device_sm_count();
+
+}  // namespace rbgpu

@@ -1,0 +1,95 @@
+// sm_100a search kernels for the dense byte-class DFA tables produced by
+// dfa/determinize.cpp.  Everything here is integer/byte work bound by HBM reads
+// of the haystack and by shared-memory table lookups; there is no contraction,
+// so no tensor cores (BASELINE.json north_star).
+//
+// Kernel inventory (reference function each replaces):
+//   scan_rev_bitmap   all match STARTS of the haystack as a bitmap -- the
+//                     chunk-parallel form of running exec_at_reverse
+//                     (src/dfa.rs:768-866) from every match end
+//   scan_fwd_reduce   first match END / any match / RegexSet mask over one big
+//                     haystack -- exec_at with quit_after_match
+//                     (src/dfa.rs:576-764) and forward_many (:525-570)
+//   walk_chunks       the find_iter chain (src/re_trait.rs:197-220) over the
+//                     start bitmap + anchored leftmost-first runs (exec_at)
+//   *_batch           one thread per record: is_match / find / set matches,
+//                     the reference algorithm verbatim per record
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rbgpu {
+
+constexpr uint64_t kNone = ~0ull;        // "no position"
+constexpr uint64_t kSpec = ~0ull - 1;    // chunk entry state is speculative
+
+struct DfaView {
+  const uint16_t* trans;    // [n_states][stride], class-indexed; column stride-1 is EOF
+  const uint8_t* classes;   // [256]
+  const uint64_t* masks;    // [n_states][mask_words]
+  uint32_t n_states, stride, match_lo, mask_words;
+  uint32_t table_bytes;     // n_states * stride * 2
+  uint16_t start[128];
+  uint8_t uniform_start;
+};
+
+__device__ __forceinline__ bool is_word_byte(uint32_t b) {
+  return (b - 'a' < 26u) || (b - 'A' < 26u) || (b - '0' < 10u) || b == '_';
+}
+
+// dfa.rs:1415-1434 / 1440-1464 (flag index layout: determinize.h)
+__device__ __forceinline__ int flags_forward(const uint8_t* t, uint64_t n, uint64_t at) {
+  int f = 0;
+  if (at == 0) f |= 1;
+  if (n == 0) f |= 2 | 8;
+  if (at == 0 || t[at - 1] == '\n') f |= 4;
+  bool last = at > 0 && is_word_byte(t[at - 1]);
+  bool cur = at < n && is_word_byte(t[at]);
+  f |= (last == cur) ? 32 : 16;
+  if (last) f |= 64;
+  return f;
+}
+__device__ __forceinline__ int flags_reverse(const uint8_t* t, uint64_t n, uint64_t at) {
+  int f = 0;
+  if (at == n) f |= 1;
+  if (n == 0) f |= 2 | 8;
+  if (at == n || t[at] == '\n') f |= 4;
+  bool last = at < n && is_word_byte(t[at]);
+  bool cur = at > 0 && is_word_byte(t[at - 1]);
+  f |= (last == cur) ? 32 : 16;
+  if (last) f |= 64;
+  return f;
+}
+
+// A DFA whose table (and class map) may have been staged into shared memory.
+struct Table {
+  const uint16_t* trans;
+  const uint8_t* classes;
+  uint32_t stride;
+  __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t byte) const {
+    return trans[s * stride + classes[byte]];
+  }
+  __device__ __forceinline__ uint32_t step_eof(uint32_t s) const { return trans[s * stride + stride - 1]; }
+};
+
+// Cooperative copy of table + class map into dynamic shared memory when it fits.
+__device__ __forceinline__ Table stage_table(const DfaView& d, unsigned char* smem, bool use_smem) {
+  Table t;
+  t.stride = d.stride;
+  if (use_smem) {
+    uint16_t* st = reinterpret_cast<uint16_t*>(smem);
+    uint8_t* sc = smem + ((d.table_bytes + 15) & ~15u);
+    const uint32_t n16 = d.table_bytes / 2;
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) st[i] = d.trans[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = d.classes[i];
+    __syncthreads();
+    t.trans = st;
+    t.classes = sc;
+  } else {
+    t.trans = d.trans;
+    t.classes = d.classes;
+  }
+  return t;
+}
+
+}  // namespace rbgpu

@@ -1,0 +1,82 @@
+// Kernel argument blocks + declarations shared by kernels.cu and engine.cu.
+#pragma once
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace rbgpu {
+
+constexpr uint32_t kMaxMaskWords = 4;  // RegexSet of up to 256 patterns per scan
+
+struct ScanArgs {
+  DfaView dfa;
+  int use_smem;
+  const uint8_t* text;
+  uint64_t n;        // haystack length
+  uint64_t base;     // first position covered (64-aligned for bitmap scans)
+  uint64_t n_seg;
+  uint32_t seg;      // positions per segment (multiple of 64)
+  uint32_t warm;     // warm-up bytes for the speculative entry state
+  uint64_t* bitmap;  // reverse scan: match-start bitmap
+  uint64_t* seg_first;  // forward scan: first match end per segment
+  uint64_t* seg_mask;   // forward scan: OR of masks per segment (nullable)
+  uint16_t* guess;
+  uint16_t* fin;
+  const uint32_t* redo_list;  // nullable: only these segments, entry = neighbour's fin
+  const uint32_t* n_redo;
+  int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
+};
+
+struct WalkArgs {
+  DfaView fwd;  // forward, anchored, leftmost-first
+  DfaView rev;  // reverse, anchored, longest (reference dfa_reverse) -- slice emulation only
+  const uint8_t* text;
+  uint64_t n;
+  const uint64_t* bitmap;
+  uint64_t base;  // 64-aligned position of chunk 0
+  uint64_t n_chunks;
+  uint32_t chunk;  // positions per chunk (multiple of 64)
+  uint64_t* in_p;
+  uint64_t* in_lm;
+  uint64_t* out_p;
+  uint64_t* out_lm;
+  uint64_t* count;
+  const uint64_t* offset;
+  uint8_t* dirty;
+  uint64_t* out;  // spans: start, end pairs
+  uint64_t cap;
+  int utf8;
+  int emulate_slice;
+  int can_match_empty;
+};
+
+struct BatchArgs {
+  DfaView fwd;
+  DfaView rev;
+  int use_smem;
+  const uint8_t* text;
+  const uint64_t* offsets;  // n_rec + 1
+  uint64_t n_rec;
+  uint32_t* out_bits;   // ballot words
+  uint64_t* out_spans;  // 2 per record
+  uint64_t* out_masks;  // mask_words per record
+};
+
+__global__ void scan_rev_bitmap(ScanArgs a);
+__global__ void scan_fwd_reduce(ScanArgs a);
+__global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
+                                uint32_t* redo_list, uint32_t* n_redo);
+__global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
+                                unsigned long long* result);
+template <bool EMIT>
+__global__ void walk_chunks(WalkArgs a);
+__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start);
+__global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
+__global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);
+__global__ void scan_block_sums(uint64_t* block_sums, uint64_t n_blocks, unsigned long long* grand_total);
+__global__ void scan_add_block_offsets(uint64_t* out, const uint64_t* block_sums, uint64_t n);
+__global__ void is_match_batch(BatchArgs a);
+__global__ void find_batch(BatchArgs a);
+__global__ void set_matches_batch(BatchArgs a);
+
+}  // namespace rbgpu

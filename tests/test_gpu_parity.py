@@ -1,0 +1,242 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU
+oracle and the committed golden vectors.  Bit-exact: spans, counts, masks are integers."""
+import os
+
+import numpy as np
+import pytest
+
+import regex_b200 as R
+from helpers import GOLDEN, sherlock_counts, sherlock_text, tiled_corpus, vectors, xorshift_bytes
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _spans(a):
+    return [tuple(int(v) for v in r) for r in np.asarray(a).reshape(-1, 2).tolist()]
+
+
+# ------------------------------------------------------------ golden vectors --
+def test_reference_vectors_through_c_abi():
+    """tests/*.rs vectors via rure_find / find_iter / rure_is_match / rure_shortest_match /
+    rure_set_matches on the GPU.  Unicode-\\b patterns must raise the explicit error."""
+    bad, n, unsupported = [], 0, 0
+    for x in vectors():
+        text = bytes.fromhex(x["text_hex"])
+        for mode in x["modes"]:
+            utf8 = mode == "str"
+            try:
+                if x["kind"] in ("matset", "nomatset"):
+                    s = (R.RegexSet if utf8 else R.BytesRegexSet)(x["res"])
+                    got = s.matches(text)
+                    assert s.is_match(text) == bool(got)
+                else:
+                    r = (R.Regex if utf8 else R.BytesRegex)(x["re"])
+                    if x["kind"] == "mat":
+                        got = r.find(text)
+                        got = list(got) if got else None
+                        assert r.is_match(text) == (got is not None)
+                        assert (r.shortest_match(text) is not None) == (got is not None)
+                        found, spans = r.find_batch(text, [0, len(text)])
+                        assert (list(map(int, spans[0])) if found[0] else None) == got, ("batch", x["name"])
+                    elif x["kind"] == "matiter":
+                        got = [list(t) for t in r.find_iter(text)]
+                    elif x["kind"] == "ismatch":
+                        got = r.is_match(text)
+                    elif x["kind"] == "shortmat":
+                        got = r.shortest_match(text)
+            except R.Error as e:
+                assert "word boundar" in str(e), (x["name"], str(e))
+                unsupported += 1
+                continue
+            n += 1
+            if got != x["expected"]:
+                bad.append((x["file"], x["name"], mode, x["expected"], got))
+    assert n > 1000
+    assert not bad, bad[:10]
+
+
+def test_sherlock_counts_and_spans():
+    """bench/src/sherlock.rs counts + full span parity with the oracle."""
+    text = sherlock_text()
+    for x in sherlock_counts():
+        try:
+            r = R.Regex(x["re"])
+        except R.Error as e:
+            assert "word boundar" in str(e)
+            continue
+        got = r.find_all(text)
+        assert len(got) == x["count"], x
+        exp = O.OracleRegex(x["re"], only_utf8=True).find_iter(text)
+        assert _spans(got) == exp, x["name"]
+
+
+def test_regexdna_shootout():
+    seq = open(os.path.join(GOLDEN, "regexdna-input.txt"), "rb").read()
+    expect = open(os.path.join(GOLDEN, "regexdna-output.txt")).read().split("\n")
+    spans = _spans(R.Regex(r">[^\n]*\n|\n").find_all(seq))
+    out, last = [], 0
+    for s, e in spans:
+        out.append(seq[last:s])
+        last = e
+    out.append(seq[last:])
+    clean = b"".join(out)
+    assert len(clean) == int(expect[11])
+    for i in range(9):
+        name, count = expect[i].rsplit(" ", 1)
+        assert R.Regex(name).count_all(clean) == int(count), name
+
+
+# ---------------------------------------------------------- chunk boundaries --
+PATTERNS_STRESS = [
+    r"[a-zA-Z]+ing", r"Holmes|Watson", r"\w+", r"the\s+\w+", r"(?i)sherlock|holmes|watson", r"a", r"aa", r"aaa",
+    r"[a-z]*", r"\s*", r"", r"(?m)^\w+", r"(?m)\w+$", r"(?m)^$", r"(?-u:\b)\w+(?-u:\b)", r"(?-u:\B)[a-z]",
+    r"(?s).{0,30}Holmes", r"[^\n]*", r".*", r"e.{5,40}?a", r"\p{Lu}\p{Ll}+",
+]
+
+
+@pytest.mark.parametrize("seg,chunk,warm", [(64, 64, 16), (128, 64, 0), (64, 256, 64), (1024, 4096, 0)])
+def test_small_segments_force_boundary_logic(seg, chunk, warm):
+    """Tiny segments/chunks put a boundary inside almost every match: exercises the
+    warm-up verification, redo rounds and chain stitching."""
+    text = sherlock_text()[:20000] + b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa" * 20
+    for pat in PATTERNS_STRESS:
+        for cls, utf8 in ((R.BytesRegex, False), (R.Regex, True)):
+            r = cls(pat)
+            r.set_tuning(seg=seg, chunk=chunk, warm=warm)
+            got = _spans(r.find_all(text))
+            exp = O.OracleRegex(pat, only_utf8=utf8).find_iter(text)
+            assert got == exp, (pat, utf8, seg, chunk, got[:5], exp[:5])
+
+
+def test_random_patterns_vs_oracle():
+    """Seeded fuzz over a small regex grammar on a 4-letter alphabet (dense matches)."""
+    rng = np.random.Generator(np.random.PCG64(0xB200))
+    atoms = ["a", "b", "c", "d", "[ab]", "[^a]", ".", "(?:ab|c)", "a*", "b+", "c?", "(?:a|bc)*", "d{2,3}", "[a-c]{1,2}?"]
+    text = xorshift_bytes(7, 5000, b"abcd\n")
+    for it in range(120):
+        k = int(rng.integers(1, 5))
+        pat = "".join(atoms[int(i)] for i in rng.integers(0, len(atoms), size=k))
+        if rng.random() < 0.3:
+            pat = pat + "|" + "".join(atoms[int(i)] for i in rng.integers(0, len(atoms), size=2))
+        if rng.random() < 0.15:
+            pat = "(?m)^" + pat
+        if rng.random() < 0.15:
+            pat = pat + "$"
+        r = R.BytesRegex(pat)
+        r.set_tuning(seg=64, chunk=128, warm=0)
+        exp = O.OracleRegex(pat, only_utf8=False).find_iter(text)
+        assert _spans(r.find_all(text)) == exp, pat
+        assert r.shortest_match(text) == O.OracleRegex(pat).shortest_match_at(text), pat
+
+
+def test_find_at_and_iter_offsets():
+    text = b"xx 2014-01-02 yy 2015-12-31 zz"
+    r = R.BytesRegex(r"(\d{4})-(\d{2})-(\d{2})")
+    o = O.OracleRegex(r"(\d{4})-(\d{2})-(\d{2})")
+    for start in range(len(text) + 2):
+        assert r.find_at(text, start) == o.find_at(text, start), start
+        assert r.is_match_at(text, start) == o.is_match_at(text, start) if start <= len(text) else True
+        assert r.shortest_match_at(text, start) == o.shortest_match_at(text, start) if start <= len(text) else True
+
+
+def test_empty_and_tiny_haystacks():
+    for pat in [r"", r"a", r"a*", r"^", r"$", r"^$", r"(?m)^", r"\s*"]:
+        for text in [b"", b"a", b"\n", b"ab"]:
+            for cls, utf8 in ((R.BytesRegex, False), (R.Regex, True)):
+                r, o = cls(pat), O.OracleRegex(pat, only_utf8=utf8)
+                assert _spans(r.find_all(text)) == o.find_iter(text), (pat, text)
+                assert r.is_match(text) == o.is_match_at(text), (pat, text)
+                assert r.shortest_match(text) == o.shortest_match_at(text), (pat, text)
+
+
+def test_utf8_empty_matches_step_by_scalar():
+    text = "aδ☃𝄞b".encode()
+    for pat in [r"", r"x*", r"(?-u:\B)"]:
+        assert _spans(R.Regex(pat).find_all(text)) == O.OracleRegex(pat, only_utf8=True).find_iter(text), pat
+        assert _spans(R.BytesRegex(pat).find_all(text)) == O.OracleRegex(pat, only_utf8=False).find_iter(text), pat
+
+
+# -------------------------------------------------------------------- batch ----
+def _log_lines(n, seed=0x5EED0003):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    words = [w for w in set(sherlock_text()[:200000].split()) if w.isalpha()][:500]
+    lines = []
+    for i in range(n):
+        if rng.random() < 0.7:
+            ts = f"{rng.integers(1990, 2030):04d}-{rng.integers(1, 13):02d}-{rng.integers(1, 29):02d}T{rng.integers(0, 24):02d}:00:00Z"
+        else:
+            ts = str(int(rng.integers(10**9, 2 * 10**9)))
+        msg = b" ".join(words[int(j)] for j in rng.integers(0, len(words), size=int(rng.integers(3, 13))))
+        lines.append(f"{ts} host-{rng.integers(0, 10000):04d} svc[{rng.integers(1, 65536)}]: ".encode() + msg + b"\n")
+    return lines
+
+
+def test_batched_lines_match_scalar_api():
+    lines = _log_lines(3000)
+    lines[17] = b""  # empty record
+    text = b"".join(lines)
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.uint64)
+    for pat in [r"(\d{4})-(\d{2})-(\d{2})", r"(?-u)(\d{4})-(\d{2})-(\d{2})", r"^\d+ host", r"svc\[\d+\]:$", r"(?i)holmes", r"\n$"]:
+        r, o = R.BytesRegex(pat), O.OracleRegex(pat)
+        m = r.is_match_batch(text, off)
+        found, spans = r.find_batch(text, off)
+        for i, l in enumerate(lines):
+            exp = o.find_at(l)
+            assert bool(m[i]) == (exp is not None), (pat, i)
+            assert bool(found[i]) == (exp is not None), (pat, i)
+            if exp:
+                assert tuple(int(v) for v in spans[i]) == exp, (pat, i)
+
+
+SET_PATTERNS = [r"\w+", r"\d+", r"\s+", r"[A-Z][a-z]+", "Holmes", "Watson", "Sherlock", r"Holmes|Watson", r"^The", r"\.$",
+                r"(?m)^$", r"[0-9]{4}", r"(?i)holmes", "zqj", r"[a-z]+ing", r"\bnever\b".replace(r"\b", r"(?-u:\b)")]
+
+
+def test_regex_set_whole_and_batched():
+    text = sherlock_text()[:50000]
+    s = R.BytesRegexSet(SET_PATTERNS)
+    s.set_tuning(seg=128, warm=0)
+    o = O.OracleRegex(SET_PATTERNS)
+    assert s.matches(text) == o.set_matches(text)
+    assert s.is_match(text)
+    lines = [l + b"\n" for l in text.split(b"\n")][:800]
+    body = b"".join(lines)
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.uint64)
+    masks = s.matches_batch(body, off)
+    for i, l in enumerate(lines):
+        exp = sum(1 << j for j in o.set_matches(l))
+        assert int(masks[i, 0]) == exp, (i, l)
+
+
+def test_regex_set_more_than_64_patterns():
+    pats = [f"w{i}x" for i in range(70)] + [r"\d+"]
+    s = R.BytesRegexSet(pats)
+    text = b"w3x w69x 12 w70x"
+    assert s.matches(text) == [3, 69, 70]
+
+
+# ------------------------------------------------------- size-independent props --
+def test_large_haystack_properties():
+    """256 MiB tiled corpus on device: count equals the sum over an independent split at
+    line boundaries (matches cannot span '\\n' for these patterns), spans are sorted,
+    non-overlapping and every span re-matches when checked by the oracle on a sample."""
+    import torch
+    base = tiled_corpus(1 << 24)
+    reps = 16
+    d = torch.frombuffer(bytearray(base), dtype=torch.uint8).cuda().repeat(reps)
+    n = d.numel()
+    for pat in [r"[a-zA-Z]+ing", r"Holmes|Watson", r"the\s+\w+"]:
+        r = R.BytesRegex(pat)
+        base_spans = O.OracleRegex(pat).find_iter(base)
+        # base ends at an arbitrary byte; compare on the device against the oracle of the first copy
+        out = torch.empty((len(base_spans) * reps + 1024, 2), dtype=torch.int64, device="cuda")
+        total = r.find_all_device(d, out)
+        got = out[:total].cpu().numpy()
+        assert (got[:, 0] < got[:, 1]).all() and (got[1:, 0] >= got[:-1, 1]).all()
+        first = got[got[:, 1] <= len(base) - 64]
+        exp = np.array([s for s in base_spans if s[1] <= len(base) - 64], dtype=np.int64).reshape(-1, 2)
+        assert first.shape == exp.shape and (first == exp).all(), pat
+        # count-only mode must agree with emit mode
+        assert r.find_all_device(d) == total
+        assert n == len(base) * reps
