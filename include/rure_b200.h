@@ -82,6 +82,8 @@ void rure_b200_last_stats(rure *re, double *out7);
  * warm = warm-up bytes (0 = automatic); 0 keeps the current value elsewhere. */
 void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block,
                           uint32_t blocks_per_sm);
+/* Tests: route scans through the generic kernel even when the fast one applies. */
+void rure_b200_force_generic(rure *re, int yes);
 /* Dense tables, for tests and tooling.  kind: 0 forward anchored leftmost-first,
  * 1 reverse unanchored all-match, 2 forward unanchored all-match, 3 reverse
  * anchored longest, 4 forward unanchored leftmost-first.

@@ -76,6 +76,7 @@ def _load():
         "rure_b200_kernel_launches": (c_uint64, []),
         "rure_b200_last_stats": (None, [vp, POINTER(c_double)]),
         "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
+        "rure_b200_force_generic": (None, [vp, c_int]),
         "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
         "rure_b200_pattern_info": (None, [vp, POINTER(c_uint64)]),
     }
@@ -287,6 +288,9 @@ class _Compiled:
 
     def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):
         _lib.rure_b200_set_tuning(self._h, seg, chunk, warm, block, blocks_per_sm)
+
+    def force_generic(self, yes=True):
+        _lib.rure_b200_force_generic(self._h, int(yes))
 
     def pattern_info(self):
         out = (c_uint64 * 4)()

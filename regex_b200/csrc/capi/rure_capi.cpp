@@ -313,6 +313,7 @@ void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm,
   if (block) t.block = (block + 31) / 32 * 32;
   if (blocks_per_sm) t.blocks_per_sm = blocks_per_sm;
 }
+void rure_b200_force_generic(rure* re, int yes) { re->re->tuning.force_generic = yes != 0; }
 bool rure_b200_dfa_export(rure* re, int kind, uint32_t* info6, uint16_t* trans, uint8_t* classes, uint16_t* start, uint64_t* masks) {
   if (kind < 0 || kind >= rbgpu::kNumDfaKinds) { g_last_error = "bad dfa kind"; return false; }
   rb::Error err;

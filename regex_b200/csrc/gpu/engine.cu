@@ -34,12 +34,18 @@ void* DeviceBuf::ensure(size_t bytes) {
   return ptr;
 }
 
+// Byte-indexed tables of up to this many states (1 KiB per state) are staged in
+// shared memory by the fast kernels.
+static constexpr uint32_t kFastStates = 200;
+
 struct Regex::DeviceDfa {
   DfaView view;
   void* trans = nullptr;
   void* classes = nullptr;
   void* masks = nullptr;
-  ~DeviceDfa() { cudaFree(trans); cudaFree(classes); cudaFree(masks); }
+  void* next256 = nullptr;  // byte-indexed expansion for the fast kernels (<= kFastStates states)
+  void* eof = nullptr;
+  ~DeviceDfa() { cudaFree(trans); cudaFree(classes); cudaFree(masks); cudaFree(next256); cudaFree(eof); }
 };
 
 // ------------------------------------------------------------------ compile --
@@ -175,6 +181,17 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
   v.table_bytes = (uint32_t)tb;
   std::memcpy(v.start, h->start, sizeof v.start);
   v.uniform_start = h->uniform_start;
+  if (h->n_states <= kFastStates) {
+    std::vector<uint16_t> n256((size_t)h->n_states * 256), eof(h->n_states);
+    for (uint32_t r = 0; r < h->n_states; r++) {
+      for (int b = 0; b < 256; b++) n256[(size_t)r * 256 + b] = h->next((uint16_t)r, (uint8_t)b);
+      eof[r] = h->next_eof((uint16_t)r);
+    }
+    RB_CUDA(cudaMalloc(&d->next256, n256.size() * 2));
+    RB_CUDA(cudaMalloc(&d->eof, eof.size() * 2));
+    RB_CUDA(cudaMemcpy(d->next256, n256.data(), n256.size() * 2, cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(d->eof, eof.data(), eof.size() * 2, cudaMemcpyHostToDevice));
+  }
   dev_[k] = d.release();
   *out = dev_[k];
   return 0;
@@ -208,29 +225,54 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
   if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
   const uint64_t base = start & ~63ull;
-  const uint32_t seg = tuning.seg;
-  const uint64_t n_seg = (n + 1 - base + seg - 1) / seg;
+  const bool utf8_mask = only_utf8 && can_match_empty;
+  const bool fast = rev->next256 && !utf8_mask && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
+  // segment length: long enough to amortise the warm-up, short enough to fill the GPU
+  uint32_t seg = tuning.seg;
+  if (seg == 0) {
+    const uint64_t lanes = (uint64_t)std::max(1, device_sm_count()) * 1024 * 2;
+    uint64_t want = ((n - base) / lanes + 63) / 64 * 64;
+    seg = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 256), fast ? 4096 : 1024);
+  }
+  const uint64_t n_seg = std::max<uint64_t>(1, (n - base + seg - 1) / seg);
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   ScanArgs a{};
   a.dfa = rev->view;
-  const size_t smem = smem_for(rev->view);
-  a.use_smem = smem != 0;
   a.text = d_text;
   a.n = n;
   a.base = base;
   a.n_seg = n_seg;
   a.seg = seg;
   a.warm = pick_warm(*this);
+  if (fast) a.warm = (a.warm + 63) / 64 * 64;
   a.bitmap = (uint64_t*)bitmap_.ensure(((n >> 6) + 2) * 8);
   a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
   a.fin = (uint16_t*)fin_.ensure(n_seg * 2);
   uint32_t* redo = (uint32_t*)redo_.ensure(n_seg * 4);
-  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  uint32_t* counters = (uint32_t*)counters_.ensure(128);
   if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
-  a.utf8_boundaries = only_utf8 && can_match_empty;
-  RB_CUDA(allow_smem(scan_rev_bitmap, smem));
-  scan_rev_bitmap<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
-  RB_LAUNCH_CHECK("scan_rev_bitmap");
+  a.flag0 = (uint8_t*)(counters + 24);
+  a.utf8_boundaries = utf8_mask;
+  a.next256 = (const uint16_t*)rev->next256;
+  a.eof = (const uint16_t*)rev->eof;
+  size_t smem;
+  uint32_t block;
+  if (fast) {
+    smem = (size_t)rev->view.n_states * 1024 + 1024;
+    block = 1024;
+    RB_CUDA(cudaFuncSetAttribute(scan_rev_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    smem = smem_for(rev->view);
+    a.use_smem = smem != 0;
+    block = tuning.block;
+    RB_CUDA(allow_smem(scan_rev_bitmap, smem));
+  }
+  auto launch = [&](const ScanArgs& args, uint64_t work) {
+    if (fast) scan_rev_fast<<<grid_for(work, block, 1), block, smem, st>>>(args);
+    else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
+  };
+  launch(a, n_seg);
+  RB_LAUNCH_CHECK("scan_rev");
   stats.scan_redo_rounds = stats.scan_redo_segments = 0;
   for (;;) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
@@ -245,8 +287,8 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
     ScanArgs r = a;
     r.redo_list = redo;
     r.n_redo = counters;
-    scan_rev_bitmap<<<grid_for(n_redo, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(r);
-    RB_LAUNCH_CHECK("scan_rev_bitmap(redo)");
+    launch(r, n_redo);
+    RB_LAUNCH_CHECK("scan_rev(redo)");
   }
   return 0;
 }
@@ -274,6 +316,7 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.text = d_text;
   w.n = n;
   w.bitmap = (const uint64_t*)bitmap_.ptr;
+  w.flag0 = (const uint8_t*)((uint32_t*)counters_.ptr + 24);
   w.base = start & ~63ull;
   w.chunk = tuning.chunk;
   w.n_chunks = (n + 1 - w.base + w.chunk - 1) / w.chunk;
@@ -287,7 +330,7 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.dirty = (uint8_t*)dirty_.ensure(nc);
   const uint64_t n_blocks = (nc + 1023) / 1024;
   uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
-  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  uint32_t* counters = (uint32_t*)counters_.ensure(128);
   if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !w.dirty || !block_sums || !counters)
     return fail("out of device memory (walk scratch)");
   w.offset = offset;
@@ -362,7 +405,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  const uint32_t seg = tuning.seg;
+  const uint32_t seg = tuning.seg ? tuning.seg : 1024;
   const uint64_t n_seg = (n + 1 - start + seg - 1) / seg;
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   const uint32_t mw = fwd->view.mask_words;
@@ -381,7 +424,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
   a.fin = (uint16_t*)fin_.ensure(n_seg * 2);
   uint32_t* redo = (uint32_t*)redo_.ensure(n_seg * 4);
-  uint32_t* counters = (uint32_t*)counters_.ensure(64);
+  uint32_t* counters = (uint32_t*)counters_.ensure(128);
   if (!a.seg_first || (want_masks && !a.seg_mask) || !a.guess || !a.fin || !redo || !counters)
     return fail("out of device memory (scan scratch)");
   RB_CUDA(allow_smem(scan_fwd_reduce, smem));

@@ -25,7 +25,8 @@ struct CompileOptions {
 enum DfaKind { kFwdAnchoredLF = 0, kRevUnanchoredAll, kFwdUnanchoredAll, kRevAnchoredLongest, kFwdUnanchoredLF, kNumDfaKinds };
 
 struct Tuning {
-  uint32_t seg = 1024;     // positions per scan segment (multiple of 64)
+  uint32_t seg = 0;        // bytes per scan segment (multiple of 64); 0 = automatic
+  bool force_generic = false;  // tests: use the generic scan kernel even when the fast one applies
   uint32_t chunk = 4096;   // positions per chain-walk chunk (multiple of 64)
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;

@@ -14,12 +14,16 @@ __device__ __forceinline__ uint32_t pick_start_fwd(const DfaView& d, const uint8
 }
 
 // ------------------------------------------------------------ scan_rev_bitmap --
-// Segment t owns positions [base + t*seg, base + (t+1)*seg) ∩ [0, n].  Position q
-// is a match START iff the reverse automaton, standing at q, reports a (delayed)
-// match when it consumes text[q-1] (or EOF for q == 0).  The state at the top
-// of a segment is guessed by running the automaton from a fresh start state
-// `warm` bytes further right; verify_segments() checks every guess against the
-// neighbour's exact final state and lists the segments to redo.
+// Bitmap format: bit i is set iff a match STARTS at position i+1, i.e. iff the
+// reverse automaton reports a (delayed) match when it consumes text[i].  A match
+// starting at position 0 is reported by the EOF step into *flag0.
+// Segment t owns bytes [base + t*seg, base + (t+1)*seg) ∩ [0, n).  The state at
+// the top of a segment is guessed by running the automaton from a fresh start
+// state `warm` bytes further right; verify_segments() checks every guess
+// against the neighbour's exact final state and lists the segments to redo.
+//
+// Generic version: any table size (shared memory when it fits, else L1/L2), any
+// alignment, optional UTF-8 boundary mask.  One byte load + two lookups per byte.
 __global__ void scan_rev_bitmap(ScanArgs a) {
   const Table T = stage_table(a.dfa, g_smem, a.use_smem);
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
@@ -27,31 +31,150 @@ __global__ void scan_rev_bitmap(ScanArgs a) {
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
-    const uint64_t lo = a.base + t * a.seg;
-    const uint64_t hi = min(lo + a.seg, a.n + 1);  // exclusive
-    const uint64_t q_hi = hi - 1;
+    const uint64_t lo = min(a.base + t * a.seg, a.n);
+    const uint64_t hi = min(lo + a.seg, a.n);  // bytes [lo, hi)
     uint32_t s;
     if (a.redo_list) {
       s = a.fin[t + 1];
     } else {
-      const uint64_t w = min(q_hi + a.warm, a.n);
+      const uint64_t w = min(hi + a.warm, a.n);
       s = pick_start_rev(a.dfa, a.text, a.n, w);
-      for (uint64_t q = w; q > q_hi; q--) s = T.step(s, a.text[q - 1]);
+      for (uint64_t i = w; i > hi; i--) s = T.step(s, a.text[i - 1]);
     }
     a.guess[t] = (uint16_t)s;
     uint64_t word = 0;
-    uint32_t byte_at_q = q_hi < a.n ? a.text[q_hi] : 0;  // text[q], for the UTF-8 boundary mask
-    for (uint64_t q = q_hi;; q--) {
-      uint32_t b = 0;
-      if (q > 0) { b = a.text[q - 1]; s = T.step(s, b); } else { s = T.step_eof(s); }
+    uint32_t next_byte = hi < a.n ? a.text[hi] : 0;  // text[i+1], for the UTF-8 boundary mask
+    for (uint64_t i = hi; i > lo;) {
+      i--;
+      const uint32_t b = a.text[i];
+      s = T.step(s, b);
       bool hit = s >= match_lo;
-      if (a.utf8_boundaries && (byte_at_q & 0xC0) == 0x80) hit = false;
-      if (hit) word |= 1ull << (q & 63);
-      byte_at_q = b;
-      if ((q & 63) == 0) { a.bitmap[q >> 6] = word; word = 0; }
-      if (q == lo) break;
+      if (a.utf8_boundaries && (next_byte & 0xC0) == 0x80) hit = false;
+      if (hit) word |= 1ull << (i & 63);
+      next_byte = b;
+      if ((i & 63) == 0 || i == lo) { a.bitmap[i >> 6] = word; word = 0; }
     }
     a.fin[t] = (uint16_t)s;
+    if (lo == 0) {
+      bool hit0 = T.step_eof(s) >= match_lo;
+      if (a.utf8_boundaries && (next_byte & 0xC0) == 0x80 && a.n > 0) hit0 = false;
+      *a.flag0 = hit0;
+    }
+  }
+}
+
+// Fast version for byte-indexed tables that fit shared memory (<= ~200 states):
+//   - the table is expanded to [state][256] 32-bit entries; an entry IS the shared-
+//     memory address of the successor's row plus a per-row XOR key, so one LOP3
+//     ((w >> k) & 0x3FC) ^ entry forms the next address and one LDS fetches the
+//     next entry.  The key (row & 31) rotates the bank of a given byte from row
+//     to row, which removes the systematic conflicts of small alphabets (DNA).
+//   - match rows sit above non-match rows, so "entry >= thr" is the match test.
+//   - each lane streams its own segment with 16-byte loads, one 64-byte group
+//     prefetched ahead; bits are assembled in registers, one 64-bit store per
+//     64 bytes of text.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// Consume the 4 bytes of w from the highest address down; BIT0 = bit index of byte 0.
+template <int BIT0>
+__device__ __forceinline__ void rev_word(uint32_t w, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  e = lds32(((w >> 22) & 0x3FCu) ^ e); if (e >= thr) bits |= 1u << (BIT0 + 3);
+  e = lds32(((w >> 14) & 0x3FCu) ^ e); if (e >= thr) bits |= 1u << (BIT0 + 2);
+  e = lds32(((w >> 6) & 0x3FCu) ^ e);  if (e >= thr) bits |= 1u << (BIT0 + 1);
+  e = lds32(((w << 2) & 0x3FCu) ^ e);  if (e >= thr) bits |= 1u << (BIT0 + 0);
+}
+template <int BIT0>
+__device__ __forceinline__ void rev_block16(const uint4& v, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  rev_word<BIT0 + 12>(v.w, e, bits, thr);
+  rev_word<BIT0 + 8>(v.z, e, bits, thr);
+  rev_word<BIT0 + 4>(v.y, e, bits, thr);
+  rev_word<BIT0 + 0>(v.x, e, bits, thr);
+}
+__device__ __forceinline__ uint32_t fast_entry(uint32_t tbase, uint32_t id) { return tbase + id * 1024u + (id & 31u) * 4u; }
+__device__ __forceinline__ uint32_t fast_step(uint32_t e, uint32_t byte) { return lds32((byte << 2) ^ e); }
+
+__global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a) {
+  // stage: entry(r, b) at word (r << 8) + (b ^ (r & 31))
+  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+  {
+    const uint32_t n_ent = a.dfa.n_states * 256u;
+    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
+      const uint32_t r = i >> 8, b = i & 255u;
+      const uint32_t nx = a.next256[i];
+      const uint32_t addr = tbase + (r << 10) + ((b ^ (r & 31u)) << 2);
+      const uint32_t val = fast_entry(tbase, nx);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = tbase + a.dfa.match_lo * 1024u;
+  const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
+    const uint64_t lo = min(a.base + t * a.seg, a.n);  // multiple of 64 (or n)
+    const uint64_t hi = min(lo + a.seg, a.n);
+    uint32_t e;
+    if (a.redo_list) {
+      e = fast_entry(tbase, a.fin[t + 1]);
+    } else {
+      const uint64_t w = min(hi + a.warm, a.n);
+      e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, w));
+      // warm-up over [hi, w): ragged top bytewise, then whole 64-byte groups
+      uint64_t i = w;
+      while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
+      uint32_t dummy = 0;
+      while (i > hi) {
+        i -= 64;
+        const uint8_t* p = a.text + i;
+        const uint4 v3 = ldg128(p + 48), v2 = ldg128(p + 32), v1 = ldg128(p + 16), v0 = ldg128(p);
+        rev_block16<0>(v3, e, dummy, 0xFFFFFFFFu);
+        rev_block16<0>(v2, e, dummy, 0xFFFFFFFFu);
+        rev_block16<0>(v1, e, dummy, 0xFFFFFFFFu);
+        rev_block16<0>(v0, e, dummy, 0xFFFFFFFFu);
+      }
+    }
+    a.guess[t] = (uint16_t)((e - tbase) >> 10);
+    uint64_t i = hi;
+    if (i & 63) {  // ragged top (only the last segment of the haystack)
+      uint64_t word = 0;
+      while (i > lo && (i & 63)) {
+        i--;
+        e = fast_step(e, a.text[i]);
+        if (e >= thr) word |= 1ull << (i & 63);
+      }
+      a.bitmap[i >> 6] = word;
+    }
+    if (i > lo) {
+      const uint8_t* p = a.text + i - 64;
+      uint4 v3 = ldg128(p + 48), v2 = ldg128(p + 32), v1 = ldg128(p + 16), v0 = ldg128(p);
+      while (i > lo) {
+        i -= 64;
+        const uint4 c3 = v3, c2 = v2, c1 = v1, c0 = v0;
+        if (i > lo) {  // prefetch the next (lower) group
+          const uint8_t* q = a.text + i - 64;
+          v3 = ldg128(q + 48); v2 = ldg128(q + 32); v1 = ldg128(q + 16); v0 = ldg128(q);
+        }
+        uint32_t bhi = 0, blo = 0;
+        rev_block16<16>(c3, e, bhi, thr);
+        rev_block16<0>(c2, e, bhi, thr);
+        rev_block16<16>(c1, e, blo, thr);
+        rev_block16<0>(c0, e, blo, thr);
+        a.bitmap[i >> 6] = ((uint64_t)bhi << 32) | blo;
+      }
+    }
+    const uint32_t s_lo = (e - tbase) >> 10;
+    a.fin[t] = (uint16_t)s_lo;
+    if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
   }
 }
 
@@ -133,16 +256,23 @@ __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_m
 }
 
 // ---------------------------------------------------------------- walk_chunks --
-// First set bit of the start bitmap in [pos, limit), or kNone.
-__device__ __forceinline__ uint64_t next_bit(const uint64_t* bm, uint64_t pos, uint64_t limit) {
+// First match start in [pos, limit), or kNone.  Bit i of the bitmap stands for
+// position i+1; position 0 is *flag0.
+__device__ __forceinline__ uint64_t next_bit(const uint64_t* bm, const uint8_t* flag0, uint64_t pos, uint64_t limit) {
   if (pos >= limit) return kNone;
-  uint64_t w = pos >> 6;
-  const uint64_t last_w = (limit - 1) >> 6;
-  uint64_t word = bm[w] & (~0ull << (pos & 63));
+  if (pos == 0) {
+    if (*flag0) return 0;
+    pos = 1;
+    if (pos >= limit) return kNone;
+  }
+  const uint64_t b_lo = pos - 1, b_hi = limit - 1;  // bits [b_lo, b_hi)
+  uint64_t w = b_lo >> 6;
+  const uint64_t last_w = (b_hi - 1) >> 6;
+  uint64_t word = bm[w] & (~0ull << (b_lo & 63));
   for (;;) {
     if (word) {
-      uint64_t q = (w << 6) + (uint64_t)(__ffsll((long long)word) - 1);
-      return q < limit ? q : kNone;
+      uint64_t b = (w << 6) + (uint64_t)(__ffsll((long long)word) - 1);
+      return b < b_hi ? b + 1 : kNone;
     }
     if (w == last_w) return kNone;
     word = bm[++w];
@@ -208,7 +338,7 @@ __global__ void walk_chunks(WalkArgs a) {
     uint64_t w_at = EMIT ? a.offset[k] : 0;
     bool p_is_chain = !spec;  // p is a real restart point of the reference iterator
     for (;;) {
-      const uint64_t s = next_bit(a.bitmap, max(p, c_lo), c_hi);
+      const uint64_t s = next_bit(a.bitmap, a.flag0, max(p, c_lo), c_hi);
       if (s == kNone) break;
       uint64_t e = anchored_end(a.fwd, a.text, a.n, s);
       if (e == kNone) { p = s + 1; p_is_chain = false; continue; }  // unreachable for consistent tables

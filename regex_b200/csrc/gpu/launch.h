@@ -17,7 +17,10 @@ struct ScanArgs {
   uint64_t n_seg;
   uint32_t seg;      // positions per segment (multiple of 64)
   uint32_t warm;     // warm-up bytes for the speculative entry state
-  uint64_t* bitmap;  // reverse scan: match-start bitmap
+  uint64_t* bitmap;  // reverse scan: bit i <=> a match starts at position i+1
+  uint8_t* flag0;    // reverse scan: a match starts at position 0
+  const uint16_t* next256;  // fast kernels: [n_states][256] byte-indexed successor ids
+  const uint16_t* eof;      // fast kernels: [n_states] EOF successor ids
   uint64_t* seg_first;  // forward scan: first match end per segment
   uint64_t* seg_mask;   // forward scan: OR of masks per segment (nullable)
   uint16_t* guess;
@@ -33,6 +36,7 @@ struct WalkArgs {
   const uint8_t* text;
   uint64_t n;
   const uint64_t* bitmap;
+  const uint8_t* flag0;
   uint64_t base;  // 64-aligned position of chunk 0
   uint64_t n_chunks;
   uint32_t chunk;  // positions per chunk (multiple of 64)
@@ -63,6 +67,7 @@ struct BatchArgs {
 };
 
 __global__ void scan_rev_bitmap(ScanArgs a);
+__global__ void scan_rev_fast(ScanArgs a);
 __global__ void scan_fwd_reduce(ScanArgs a);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
                                 uint32_t* redo_list, uint32_t* n_redo);

@@ -97,8 +97,9 @@ PATTERNS_STRESS = [
 ]
 
 
-@pytest.mark.parametrize("seg,chunk,warm", [(64, 64, 16), (128, 64, 0), (64, 256, 64), (1024, 4096, 0)])
-def test_small_segments_force_boundary_logic(seg, chunk, warm):
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("seg,chunk,warm", [(64, 64, 16), (128, 64, 0), (64, 256, 64), (0, 4096, 0)])
+def test_small_segments_force_boundary_logic(seg, chunk, warm, generic):
     """Tiny segments/chunks put a boundary inside almost every match: exercises the
     warm-up verification, redo rounds and chain stitching."""
     text = sherlock_text()[:20000] + b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa" * 20
@@ -106,9 +107,12 @@ def test_small_segments_force_boundary_logic(seg, chunk, warm):
         for cls, utf8 in ((R.BytesRegex, False), (R.Regex, True)):
             r = cls(pat)
             r.set_tuning(seg=seg, chunk=chunk, warm=warm)
+            r.force_generic(generic)
             got = _spans(r.find_all(text))
             exp = O.OracleRegex(pat, only_utf8=utf8).find_iter(text)
             assert got == exp, (pat, utf8, seg, chunk, got[:5], exp[:5])
+            for cut in (63, 64, 65, 1000):  # ragged ends / tiny haystacks through the same kernels
+                assert _spans(r.find_all(text[:cut])) == O.OracleRegex(pat, only_utf8=utf8).find_iter(text[:cut]), (pat, cut)
 
 
 def test_random_patterns_vs_oracle():
