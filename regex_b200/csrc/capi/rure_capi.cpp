@@ -308,7 +308,7 @@ void rure_b200_last_stats(rure* re, double* out7) {
 void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block, uint32_t blocks_per_sm) {
   rbgpu::Tuning& t = re->re->tuning;
   if (seg) t.seg = (seg + 63) / 64 * 64;
-  if (chunk) t.chunk = (chunk + 63) / 64 * 64;
+  if (chunk) t.chunk = (chunk + 255) / 256 * 256;
   t.warm = warm;
   if (block) t.block = (block + 31) / 32 * 32;
   if (blocks_per_sm) t.blocks_per_sm = blocks_per_sm;

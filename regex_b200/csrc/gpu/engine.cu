@@ -36,7 +36,7 @@ void* DeviceBuf::ensure(size_t bytes) {
 
 // Byte-indexed tables of up to this many states (1 KiB per state) are staged in
 // shared memory by the fast kernels.
-static constexpr uint32_t kFastStates = 200;
+static constexpr uint32_t kFastStates = 56;
 
 struct Regex::DeviceDfa {
   DfaView view;
@@ -224,7 +224,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
   DeviceDfa* rev;
   if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  const uint64_t base = start & ~63ull;
+  const uint64_t base = start ? ((start - 1) & ~255ull) : 0;  // bit i <-> position i+1
   const bool utf8_mask = only_utf8 && can_match_empty;
   const bool fast = rev->next256 && !utf8_mask && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
   // segment length: long enough to amortise the warm-up, short enough to fill the GPU
@@ -256,10 +256,11 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
   a.next256 = (const uint16_t*)rev->next256;
   a.eof = (const uint16_t*)rev->eof;
   size_t smem;
-  uint32_t block;
+  uint32_t block, fast_blocks = 1;
   if (fast) {
-    smem = (size_t)rev->view.n_states * 1024 + 1024;
     block = 1024;
+    smem = (size_t)rev->view.n_states * 1024 + 1024 + (block / 32) * (2 * 32 * 80 + 16);
+    fast_blocks = 1;
     RB_CUDA(cudaFuncSetAttribute(scan_rev_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   } else {
     smem = smem_for(rev->view);
@@ -268,7 +269,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
     RB_CUDA(allow_smem(scan_rev_bitmap, smem));
   }
   auto launch = [&](const ScanArgs& args, uint64_t work) {
-    if (fast) scan_rev_fast<<<grid_for(work, block, 1), block, smem, st>>>(args);
+    if (fast) scan_rev_fast<<<grid_for(work, block, fast_blocks), block, smem, st>>>(args);
     else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
   };
   launch(a, n_seg);
@@ -317,9 +318,10 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.n = n;
   w.bitmap = (const uint64_t*)bitmap_.ptr;
   w.flag0 = (const uint8_t*)((uint32_t*)counters_.ptr + 24);
-  w.base = start & ~63ull;
-  w.chunk = tuning.chunk;
-  w.n_chunks = (n + 1 - w.base + w.chunk - 1) / w.chunk;
+  w.base = start ? ((start - 1) & ~255ull) : 0;
+  w.chunk = std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
+  w.stage_cap = std::max<uint32_t>(4, w.chunk / 64);
+  w.n_chunks = std::max<uint64_t>(1, (n - std::min(n, w.base) + w.chunk - 1) / w.chunk);
   const uint64_t nc = w.n_chunks;
   w.in_p = (uint64_t*)in_p_.ensure(nc * 8);
   w.in_lm = (uint64_t*)in_lm_.ensure(nc * 8);
@@ -328,10 +330,12 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.count = (uint64_t*)count_.ensure(nc * 8);
   uint64_t* offset = (uint64_t*)offset_.ensure(nc * 8);
   w.dirty = (uint8_t*)dirty_.ensure(nc);
+  w.first_cand = (uint64_t*)first_cand_.ensure(nc * 8);
+  w.stage = (uint64_t*)stage_.ensure(nc * (uint64_t)w.stage_cap * 16);
   const uint64_t n_blocks = (nc + 1023) / 1024;
   uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
-  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !w.dirty || !block_sums || !counters)
+  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !w.dirty || !w.first_cand || !w.stage || !block_sums || !counters)
     return fail("out of device memory (walk scratch)");
   w.offset = offset;
   w.out = d_out;
@@ -342,11 +346,15 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
   init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, start);
   RB_LAUNCH_CHECK("init_walk_entries");
-  const uint32_t wgrid = grid_for(nc, 128, 16);
+  const size_t wsmem = smem_for(fwd->view);
+  w.use_smem = wsmem != 0;
+  RB_CUDA(allow_smem(walk_chunks, wsmem));
+  RB_CUDA(allow_smem(compact_spans, wsmem));
+  const uint32_t wgrid = grid_for(nc, 256, 8);
   WalkArgs w0 = w;
   w0.dirty = nullptr;
-  walk_chunks<false><<<wgrid, 128, 0, st>>>(w0);
-  RB_LAUNCH_CHECK("walk_chunks<count>");
+  walk_chunks<<<wgrid, 256, wsmem, st>>>(w0);
+  RB_LAUNCH_CHECK("walk_chunks");
   stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
   for (;;) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
@@ -358,8 +366,8 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
     if (n_dirty == 0) break;
     stats.stitch_rounds++;
     stats.stitch_dirty_chunks += n_dirty;
-    walk_chunks<false><<<wgrid, 128, 0, st>>>(w);
-    RB_LAUNCH_CHECK("walk_chunks<recount>");
+    walk_chunks<<<wgrid, 256, wsmem, st>>>(w);
+    RB_LAUNCH_CHECK("walk_chunks(dirty)");
   }
   unsigned long long* grand = (unsigned long long*)(counters + 4);
   scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w.count, offset, block_sums, nc);
@@ -369,8 +377,8 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(offset, block_sums, nc);
   RB_LAUNCH_CHECK("scan_add_block_offsets");
   if (w.cap > 0) {
-    walk_chunks<true><<<wgrid, 128, 0, st>>>(w);
-    RB_LAUNCH_CHECK("walk_chunks<emit>");
+    compact_spans<<<wgrid, 256, wsmem, st>>>(w);
+    RB_LAUNCH_CHECK("compact_spans");
   }
   RB_CUDA(cudaMemcpyAsync(pinned_, grand, 8, cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaEventRecord(ev[2], st));

@@ -27,7 +27,7 @@ enum DfaKind { kFwdAnchoredLF = 0, kRevUnanchoredAll, kFwdUnanchoredAll, kRevAnc
 struct Tuning {
   uint32_t seg = 0;        // bytes per scan segment (multiple of 64); 0 = automatic
   bool force_generic = false;  // tests: use the generic scan kernel even when the fast one applies
-  uint32_t chunk = 4096;   // positions per chain-walk chunk (multiple of 64)
+  uint32_t chunk = 2048;   // bitmap bits per chain-walk chunk (one thread; multiple of 256)
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;
   uint32_t blocks_per_sm = 8;
@@ -110,7 +110,7 @@ class Regex {
   void* stream_ = nullptr;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
-  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, block_sums_, out_, bits_, masks_;
+  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
 };
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
@@ -102,9 +102,42 @@ __device__ __forceinline__ void rev_block16(const uint4& v, uint32_t& e, uint32_
 __device__ __forceinline__ uint32_t fast_entry(uint32_t tbase, uint32_t id) { return tbase + id * 1024u + (id & 31u) * 4u; }
 __device__ __forceinline__ uint32_t fast_step(uint32_t e, uint32_t byte) { return lds32((byte << 2) ^ e); }
 
+// ---- TMA ring: per-lane 64-byte groups land in shared memory through cp.async.bulk ----
+// Uncoalesced per-lane LDG.128 costs one L1TEX wavefront per lane (ncu: L1/TEX at 98 %
+// with half of it global loads).  Bulk copies bypass the LSU path; each lane then
+// reads its own 64 bytes with four conflict-free LDS.128 (lane stride 80 bytes).
+constexpr uint32_t kRingLaneStride = 80;                       // 64 data + 16 pad
+constexpr uint32_t kRingStageBytes = 32 * kRingLaneStride;     // per warp
+constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes + 16;  // two stages + two mbarriers
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a) {
-  // stage: entry(r, b) at word (r << 8) + (b ^ (r & 31))
+  // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
   const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t ring = tbase + a.dfa.n_states * 1024u + wid * kRingWarpBytes;
+  const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
   {
     const uint32_t n_ent = a.dfa.n_states * 256u;
     for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
@@ -114,67 +147,95 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a) {
       const uint32_t val = fast_entry(tbase, nx);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
     }
+    if (lane == 0) {
+      mbar_init(bar0, 32);
+      mbar_init(bar0 + 8, 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
   }
   const uint32_t thr = tbase + a.dfa.match_lo * 1024u;
+  const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
-  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
-    const uint64_t lo = min(a.base + t * a.seg, a.n);  // multiple of 64 (or n)
-    const uint64_t hi = min(lo + a.seg, a.n);
-    uint32_t e;
-    if (a.redo_list) {
-      e = fast_entry(tbase, a.fin[t + 1]);
-    } else {
-      const uint64_t w = min(hi + a.warm, a.n);
-      e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, w));
-      // warm-up over [hi, w): ragged top bytewise, then whole 64-byte groups
-      uint64_t i = w;
-      while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
-      uint32_t dummy = 0;
-      while (i > hi) {
-        i -= 64;
-        const uint8_t* p = a.text + i;
-        const uint4 v3 = ldg128(p + 48), v2 = ldg128(p + 32), v1 = ldg128(p + 16), v0 = ldg128(p);
-        rev_block16<0>(v3, e, dummy, 0xFFFFFFFFu);
-        rev_block16<0>(v2, e, dummy, 0xFFFFFFFFu);
-        rev_block16<0>(v1, e, dummy, 0xFFFFFFFFu);
-        rev_block16<0>(v0, e, dummy, 0xFFFFFFFFu);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t rounds = (total + stride - 1) / stride;  // uniform: every warp makes every round
+  uint32_t uses = 0;  // ring uses so far (same for the whole warp): stage = uses & 1, parity = (uses >> 1) & 1
+  for (uint64_t round = 0; round < rounds; round++) {
+    const uint64_t idx = first + round * stride;
+    const bool live = idx < total;
+    uint64_t t = 0, lo = 0, hi = 0, i = 0;
+    uint32_t e = 0;
+    if (live) {
+      t = a.redo_list ? a.redo_list[idx] : idx;
+      lo = min(a.base + t * a.seg, a.n);  // multiple of 64 (or n)
+      hi = min(lo + a.seg, a.n);          // multiple of 64 (or n)
+      i = hi;
+      if (a.redo_list) {
+        e = fast_entry(tbase, a.fin[t + 1]);
+      } else {
+        i = min(hi + a.warm, a.n);
+        e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, i));
+        // ragged top of the warm-up (only next to the end of the haystack)
+        while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
       }
-    }
-    a.guess[t] = (uint16_t)((e - tbase) >> 10);
-    uint64_t i = hi;
-    if (i & 63) {  // ragged top (only the last segment of the haystack)
-      uint64_t word = 0;
-      while (i > lo && (i & 63)) {
-        i--;
-        e = fast_step(e, a.text[i]);
-        if (e >= thr) word |= 1ull << (i & 63);
-      }
-      a.bitmap[i >> 6] = word;
-    }
-    if (i > lo) {
-      const uint8_t* p = a.text + i - 64;
-      uint4 v3 = ldg128(p + 48), v2 = ldg128(p + 32), v1 = ldg128(p + 16), v0 = ldg128(p);
-      while (i > lo) {
-        i -= 64;
-        const uint4 c3 = v3, c2 = v2, c1 = v1, c0 = v0;
-        if (i > lo) {  // prefetch the next (lower) group
-          const uint8_t* q = a.text + i - 64;
-          v3 = ldg128(q + 48); v2 = ldg128(q + 32); v1 = ldg128(q + 16); v0 = ldg128(q);
+      if (i == hi) {
+        a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        if (i & 63) {  // ragged top of the segment itself (last segment only)
+          uint64_t word = 0;
+          while (i > lo && (i & 63)) {
+            i--;
+            e = fast_step(e, a.text[i]);
+            if (e >= thr) word |= 1ull << (i & 63);
+          }
+          a.bitmap[i >> 6] = word;
         }
-        uint32_t bhi = 0, blo = 0;
-        rev_block16<16>(c3, e, bhi, thr);
-        rev_block16<0>(c2, e, bhi, thr);
-        rev_block16<16>(c1, e, blo, thr);
-        rev_block16<0>(c0, e, blo, thr);
-        a.bitmap[i >> 6] = ((uint64_t)bhi << 32) | blo;
       }
     }
-    const uint32_t s_lo = (e - tbase) >> 10;
-    a.fin[t] = (uint16_t)s_lo;
-    if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
+    // bytes [lo, i) remain, i a multiple of 64: whole groups through the ring
+    const uint32_t my_groups = live ? (uint32_t)((i - lo) >> 6) : 0;
+    uint32_t max_groups = my_groups;
+    for (int o = 16; o; o >>= 1) max_groups = max(max_groups, __shfl_xor_sync(0xffffffffu, max_groups, o));
+    const uint8_t* top = a.text + i;  // group k covers [top - 64(k+1), top - 64k)
+    auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
+      const uint32_t u = uses + k;
+      const uint32_t bar = bar0 + (u & 1) * 8;
+      if (k < my_groups) {
+        mbar_arrive_tx(bar, 64);
+        bulk_g2s(my_slot + (u & 1) * kRingStageBytes, top - 64ull * (k + 1), 64, bar);
+      } else {
+        mbar_arrive_tx(bar, 0);
+      }
+    };
+    if (max_groups > 0) issue(0);
+    if (max_groups > 1) issue(1);
+    for (uint32_t k = 0; k < max_groups; k++) {
+      const uint32_t u = uses + k;
+      const uint32_t slot = my_slot + (u & 1) * kRingStageBytes;
+      mbar_wait(bar0 + (u & 1) * 8, (u >> 1) & 1);
+      uint4 c0, c1, c2, c3;
+      if (k < my_groups) { c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48); }
+      if (k < my_groups) {
+        const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
+        if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        const uint32_t th = g < hi ? thr : 0xFFFFFFFFu;
+        uint32_t bhi = 0, blo = 0;
+        rev_block16<16>(c3, e, bhi, th);
+        rev_block16<0>(c2, e, bhi, th);
+        rev_block16<16>(c1, e, blo, th);
+        rev_block16<0>(c0, e, blo, th);
+        if (g < hi) a.bitmap[g >> 6] = ((uint64_t)bhi << 32) | blo;
+      }
+      // the slot's bytes have been consumed: refill it for the group after next
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (k + 2 < max_groups) issue(k + 2);
+    }
+    uses += max_groups;
+    if (live) {
+      const uint32_t s_lo = (e - tbase) >> 10;
+      a.fin[t] = (uint16_t)s_lo;
+      if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
+    }
   }
 }
 
@@ -282,11 +343,11 @@ __device__ __forceinline__ uint64_t next_bit(const uint64_t* bm, const uint8_t* 
 // End of the leftmost-first match anchored at s (src/dfa.rs:576-764 run on the
 // anchored program): last position at which a match state was entered, with the
 // one-byte delay and the EOF flush.
-__device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const uint8_t* text, uint64_t n, uint64_t s) {
+__device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const Table& T, const uint8_t* text, uint64_t n, uint64_t s) {
   uint32_t st = pick_start_fwd(d, text, n, s);
   uint64_t last = kNone;
   for (uint64_t q = s;; q++) {
-    st = q < n ? d.trans[st * d.stride + d.classes[text[q]]] : d.trans[st * d.stride + d.stride - 1];
+    st = q < n ? T.step(st, __ldg(text + q)) : T.step_eof(st);
     if (st >= d.match_lo) last = q;
     if (st == 0 || q >= n) break;
   }
@@ -320,55 +381,130 @@ __device__ __forceinline__ uint64_t next_utf8(const uint8_t* text, uint64_t n, u
   return i + (b <= 0x7F ? 1 : b <= 0xDF ? 2 : b <= 0xEF ? 3 : 4);
 }
 
-template <bool EMIT>
-__global__ void walk_chunks(WalkArgs a) {
+// Chain state of the find_iter iterator (re_trait.rs:174-179) as it moves through
+// the candidates of one 64-bit bitmap word, i.e. positions [bit0+1, bit0+64].
+struct Chain {
+  uint64_t p, lm;  // next search position, end of the previous match (kNone = none)
+  bool chain;      // p is a real restart point of the reference iterator
+};
+// Spans are written to dst[w_at + i] while w_at + i < limit; returns the matches accepted.
+__device__ __forceinline__ uint32_t word_walk(const WalkArgs& a, const Table& T, uint64_t word, uint64_t bit0, Chain& c,
+                                              uint64_t* dst, uint64_t w_at, uint64_t limit) {
+  uint32_t cnt = 0;
+  const uint64_t first_pos = bit0 + 1;
+  while (c.p != kNone) {
+    const uint64_t lob = c.p > first_pos ? c.p - first_pos : 0;
+    if (lob >= 64) break;
+    const uint64_t m = word & (~0ull << lob);
+    if (!m) break;
+    const uint64_t s = first_pos + (uint64_t)(__ffsll((long long)m) - 1);
+    const uint64_t e = anchored_end(a.fwd, T, a.text, a.n, s);
+    if (e == kNone) { c.p = s + 1; c.chain = false; continue; }  // unreachable for consistent tables
+    uint64_t ms = s;
+    if (a.emulate_slice && c.chain && e != c.p) {
+      // exec.rs:647-657: an empty match at the restart point short-circuits; otherwise
+      // the start comes from the reverse DFA over text[p..].
+      ms = slice_start(a.rev, a.text, a.n, c.p, e);
+      if (ms == kNone) { c.p = kNone; break; }  // NoMatch => find_at None => the iteration stops
+    }
+    c.chain = true;
+    if (ms == e) {
+      c.p = a.utf8 ? next_utf8(a.text, a.n, e) : e + 1;
+      if (e == c.lm) continue;  // re_trait.rs:210-214
+    } else {
+      c.p = e;
+    }
+    c.lm = e;
+    if (w_at + cnt < limit) { dst[2 * (w_at + cnt)] = ms; dst[2 * (w_at + cnt) + 1] = e; }
+    cnt++;
+  }
+  return cnt;
+}
+
+// Is a speculative walk that assumed "the chain enters at or before `region_first`"
+// still valid when the chain really enters at (tp, tl)?  (strict: patterns that can
+// match empty or need the slice emulation depend on the exact entry.)
+__device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t tl, uint64_t region_first,
+                                        uint64_t first_cand, uint64_t region_next) {
+  if (tp == kNone) return false;
+  if (a.emulate_slice || a.can_match_empty)
+    return tp < region_first || (tp == region_first && !a.emulate_slice && !(a.can_match_empty && tl == region_first));
+  return tp <= first_cand && tp <= region_next;
+}
+
+// The chain over one chunk (bits [cb, ce) <-> positions [cb+1, ce], plus position 0
+// for the chunk that starts the haystack).  Returns the number of matches.
+__device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Table& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                               uint64_t* dst, uint64_t w_at, uint64_t limit) {
+  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+  const uint64_t ce = min(cb + a.chunk, a.n);
+  uint64_t total = 0;
+  *first_cand = kNone;
+  if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
+    *first_cand = 0;
+    total += word_walk(a, T, 1ull, ~0ull, c, dst, w_at, limit);
+  }
+  for (uint64_t b = cb; b < ce && c.p != kNone; b += 256) {
+    // 4 bitmap words (32 bytes) per load pair
+    const uint4* wp = reinterpret_cast<const uint4*>(a.bitmap + (b >> 6));
+    const uint4 v0 = __ldg(wp), v1 = (b + 128 < ce) ? __ldg(wp + 1) : make_uint4(0, 0, 0, 0);
+    const uint64_t w[4] = {((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v0.w << 32) | v0.z,
+                           ((uint64_t)v1.y << 32) | v1.x, ((uint64_t)v1.w << 32) | v1.z};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint64_t bit0 = b + 64ull * j;
+      if (w[j] == 0 || bit0 >= ce) continue;
+      if (*first_cand == kNone) *first_cand = bit0 + (uint64_t)__ffsll((long long)w[j]);
+      total += word_walk(a, T, w[j], bit0, c, dst, w_at + total, limit);
+    }
+  }
+  return total;
+}
+
+// One thread per chunk: walk the chain speculatively (or from a given entry state),
+// staging up to stage_cap spans per chunk.  Re-run on dirty chunks after stitch_check.
+__global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
+  const Table T = stage_table(a.fwd, g_smem, a.use_smem);
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
        k += (uint64_t)gridDim.x * blockDim.x) {
-    if (!EMIT && a.dirty && !a.dirty[k]) continue;
-    const uint64_t c_lo = a.base + k * a.chunk;
-    const uint64_t c_hi = min(c_lo + a.chunk, a.n + 1);  // candidate positions [c_lo, c_hi)
-    uint64_t p = a.in_p[k], lm = a.in_lm[k];
-    const bool spec = p == kSpec;
-    if (spec) { p = c_lo; lm = kNone; }
-    if (p == kNone) {  // the chain ended upstream (reference iterator returned None)
-      if (!EMIT) { a.out_p[k] = kNone; a.out_lm[k] = lm; a.count[k] = 0; }
-      continue;
-    }
-    uint64_t cnt = 0;
-    uint64_t w_at = EMIT ? a.offset[k] : 0;
-    bool p_is_chain = !spec;  // p is a real restart point of the reference iterator
-    for (;;) {
-      const uint64_t s = next_bit(a.bitmap, a.flag0, max(p, c_lo), c_hi);
-      if (s == kNone) break;
-      uint64_t e = anchored_end(a.fwd, a.text, a.n, s);
-      if (e == kNone) { p = s + 1; p_is_chain = false; continue; }  // unreachable for consistent tables
-      uint64_t ms = s;
-      if (a.emulate_slice && p_is_chain && e != p) {
-        // exec.rs:647-657: empty match at the restart point short-circuits; otherwise
-        // the start comes from the reverse DFA over text[p..].
-        ms = slice_start(a.rev, a.text, a.n, p, e);
-        if (ms == kNone) { p = kNone; break; }  // NoMatch => find_at None => iteration stops
-      }
-      if (ms == e) {
-        p = a.utf8 ? next_utf8(a.text, a.n, e) : e + 1;
-        p_is_chain = true;
-        if (e == lm) continue;  // re_trait.rs:210-214
-      } else {
-        p = e;
-        p_is_chain = true;
-      }
-      lm = e;
-      if (EMIT) {
-        if (w_at < a.cap) { a.out[2 * w_at] = ms; a.out[2 * w_at + 1] = e; }
-        w_at++;
-      }
-      cnt++;
-    }
-    if (!EMIT) { a.out_p[k] = p; a.out_lm[k] = lm; a.count[k] = cnt; }
+    if (a.dirty && !a.dirty[k]) continue;
+    Chain c;
+    c.p = a.in_p[k];
+    c.lm = a.in_lm[k];
+    c.chain = c.p != kSpec;
+    if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
+    uint64_t fc = kNone, total = 0;
+    if (c.p != kNone) total = chunk_walk(a, T, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    a.out_p[k] = c.p;
+    a.out_lm[k] = c.lm;
+    a.count[k] = total;
+    a.first_cand[k] = fc;
   }
 }
-template __global__ void walk_chunks<false>(WalkArgs);
-template __global__ void walk_chunks<true>(WalkArgs);
+
+// Staged spans -> final array at the prefix-summed offsets.  Chunks that overflowed
+// their staging slots are walked again, writing straight to the output.
+__global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
+  const Table T = stage_table(a.fwd, g_smem, a.use_smem);
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
+       k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t cnt = a.count[k], at = a.offset[k];
+    if (cnt == 0) continue;
+    if (cnt <= a.stage_cap) {
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.out);
+      for (uint64_t i = 0; i < cnt && at + i < a.cap; i++) dst[at + i] = src[i];
+    } else {
+      Chain c;
+      c.p = a.in_p[k];
+      c.lm = a.in_lm[k];
+      c.chain = c.p != kSpec;
+      if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
+      uint64_t fc;
+      chunk_walk(a, T, k, c, &fc, a.out, at, a.cap);
+    }
+  }
+}
 
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {
@@ -383,10 +519,10 @@ __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty) {
        k += (uint64_t)gridDim.x * blockDim.x) {
     if (k == 0) { a.dirty[0] = 0; continue; }
     const uint64_t tp = a.out_p[k - 1], tl = a.out_lm[k - 1];
-    const uint64_t c_lo = a.base + k * a.chunk;
+    const uint64_t c_first = a.base + k * (uint64_t)a.chunk + 1;  // first position of the chunk
     const uint64_t cp = a.in_p[k], cl = a.in_lm[k];
     bool ok;
-    if (cp == kSpec) ok = tp != kNone && (tp < c_lo || (tp == c_lo && !a.emulate_slice && !(a.can_match_empty && tl == c_lo)));
+    if (cp == kSpec) ok = spec_ok(a, tp, tl, c_first, a.first_cand[k], c_first + a.chunk);
     else ok = cp == tp && cl == tl;
     if (!ok) {
       a.in_p[k] = tp;

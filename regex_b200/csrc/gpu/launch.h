@@ -37,9 +37,13 @@ struct WalkArgs {
   uint64_t n;
   const uint64_t* bitmap;
   const uint8_t* flag0;
-  uint64_t base;  // 64-aligned position of chunk 0
+  uint64_t base;  // first bitmap bit of chunk 0 (64-aligned); bit i <-> position i+1
   uint64_t n_chunks;
-  uint32_t chunk;  // positions per chunk (multiple of 64)
+  uint32_t chunk;  // bitmap bits per chunk (multiple of 256)
+  uint32_t stage_cap;  // staged spans per chunk
+  uint64_t* stage;     // [n_chunks][stage_cap] spans
+  int use_smem;
+  uint64_t* first_cand;  // per chunk: position of its first candidate (kNone if none)
   uint64_t* in_p;
   uint64_t* in_lm;
   uint64_t* out_p;
@@ -73,8 +77,8 @@ __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint
                                 uint32_t* redo_list, uint32_t* n_redo);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result);
-template <bool EMIT>
 __global__ void walk_chunks(WalkArgs a);
+__global__ void compact_spans(WalkArgs a);
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start);
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
 __global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);
