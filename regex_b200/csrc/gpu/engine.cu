@@ -329,13 +329,13 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.out_lm = (uint64_t*)out_lm_.ensure(nc * 8);
   w.count = (uint64_t*)count_.ensure(nc * 8);
   uint64_t* offset = (uint64_t*)offset_.ensure(nc * 8);
-  w.dirty = (uint8_t*)dirty_.ensure(nc);
+  uint32_t* dirty_list = (uint32_t*)dirty_.ensure(nc * 4);
   w.first_cand = (uint64_t*)first_cand_.ensure(nc * 8);
   w.stage = (uint64_t*)stage_.ensure(nc * (uint64_t)w.stage_cap * 16);
   const uint64_t n_blocks = (nc + 1023) / 1024;
   uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
-  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !w.dirty || !w.first_cand || !w.stage || !block_sums || !counters)
+  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !dirty_list || !w.first_cand || !w.stage || !block_sums || !counters)
     return fail("out of device memory (walk scratch)");
   w.offset = offset;
   w.out = d_out;
@@ -346,19 +346,35 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
   init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, start);
   RB_LAUNCH_CHECK("init_walk_entries");
-  const size_t wsmem = smem_for(fwd->view);
-  w.use_smem = wsmem != 0;
-  RB_CUDA(allow_smem(walk_chunks, wsmem));
-  RB_CUDA(allow_smem(compact_spans, wsmem));
-  const uint32_t wgrid = grid_for(nc, 256, 8);
-  WalkArgs w0 = w;
-  w0.dirty = nullptr;
-  walk_chunks<<<wgrid, 256, wsmem, st>>>(w0);
+  // fast runner: byte-indexed shared-memory table, uniform start state, 8-byte aligned text
+  const bool wfast = fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
+  size_t wsmem;
+  if (wfast) {
+    wsmem = (size_t)fwd->view.n_states * 1024 + 1024;
+    w.fwd_next256 = (const uint16_t*)fwd->next256;
+    w.fwd_eof = (const uint16_t*)fwd->eof;
+    RB_CUDA(allow_smem(walk_chunks<true>, wsmem));
+    RB_CUDA(allow_smem(compact_spans<true>, wsmem));
+  } else {
+    wsmem = smem_for(fwd->view);
+    w.use_smem = wsmem != 0;
+    RB_CUDA(allow_smem(walk_chunks<false>, wsmem));
+    RB_CUDA(allow_smem(compact_spans<false>, wsmem));
+  }
+  auto launch_walk = [&](const WalkArgs& args, uint64_t work) {
+    const uint32_t g = grid_for(work, 256, 6);
+    if (wfast) walk_chunks<true><<<g, 256, wsmem, st>>>(args);
+    else walk_chunks<false><<<g, 256, wsmem, st>>>(args);
+  };
+  launch_walk(w, nc);
   RB_LAUNCH_CHECK("walk_chunks");
   stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
   for (;;) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
-    stitch_check<<<grid_for(nc, 256, 8), 256, 0, st>>>(w, counters);
+    WalkArgs wd = w;
+    wd.dirty_list = dirty_list;
+    wd.n_dirty = counters;
+    stitch_check<<<grid_for(nc, 256, 8), 256, 0, st>>>(wd, counters);
     RB_LAUNCH_CHECK("stitch_check");
     RB_CUDA(cudaMemcpyAsync(pinned_, counters, 4, cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -366,7 +382,7 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
     if (n_dirty == 0) break;
     stats.stitch_rounds++;
     stats.stitch_dirty_chunks += n_dirty;
-    walk_chunks<<<wgrid, 256, wsmem, st>>>(w);
+    launch_walk(wd, n_dirty);
     RB_LAUNCH_CHECK("walk_chunks(dirty)");
   }
   unsigned long long* grand = (unsigned long long*)(counters + 4);
@@ -377,7 +393,9 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(offset, block_sums, nc);
   RB_LAUNCH_CHECK("scan_add_block_offsets");
   if (w.cap > 0) {
-    compact_spans<<<wgrid, 256, wsmem, st>>>(w);
+    const uint32_t g = grid_for(nc, 256, 6);
+    if (wfast) compact_spans<true><<<g, 256, wsmem, st>>>(w);
+    else compact_spans<false><<<g, 256, wsmem, st>>>(w);
     RB_LAUNCH_CHECK("compact_spans");
   }
   RB_CUDA(cudaMemcpyAsync(pinned_, grand, 8, cudaMemcpyDeviceToHost, st));

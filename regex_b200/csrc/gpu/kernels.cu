@@ -381,24 +381,101 @@ __device__ __forceinline__ uint64_t next_utf8(const uint8_t* text, uint64_t n, u
   return i + (b <= 0x7F ? 1 : b <= 0xDF ? 2 : b <= 0xEF ? 3 : 4);
 }
 
-// Chain state of the find_iter iterator (re_trait.rs:174-179) as it moves through
-// the candidates of one 64-bit bitmap word, i.e. positions [bit0+1, bit0+64].
+// Generic anchored runner: class-indexed table (shared memory when it fits), any start flags.
+struct GenericRunner {
+  Table T;
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
+    return anchored_end(a.fwd, T, a.text, a.n, s);
+  }
+};
+// Fast anchored runner: byte-indexed XOR-swizzled table in shared memory (one LDS per
+// byte, see scan_rev_fast), uniform start state, text taken 16 bytes at a time from
+// three aligned 8-byte loads so a typical match costs one memory round trip.
+struct FastRunner {
+  uint32_t tbase, thr, start_e;
+  const uint16_t* eof;
+  uint32_t match_lo;
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
+    uint32_t e = start_e;
+    uint64_t last = kNone;
+    const uint32_t dead = tbase;  // row 0, key 0
+    for (uint64_t q = s;; q += 16) {
+      const uint64_t al = q & ~7ull;
+      const uint64_t* wp = reinterpret_cast<const uint64_t*>(a.text + al);
+      const uint64_t w0 = al < a.n ? __ldg(wp) : 0, w1 = al + 8 < a.n ? __ldg(wp + 1) : 0, w2 = al + 16 < a.n ? __ldg(wp + 2) : 0;
+      const uint32_t sh = (uint32_t)(q & 7) * 8;
+      const uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+      const uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+      const uint64_t avail = a.n - q;  // bytes before EOF (q <= n)
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if ((uint64_t)j >= avail) {  // EOF step (dfa.rs:748-763)
+          const uint32_t st = (e - tbase) >> 10;
+          if (eof[st] >= match_lo) last = a.n;
+          return last;
+        }
+        const uint32_t byte = (uint32_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))) & 0xFF);
+        e = fast_step(e, byte);
+        if (e >= thr) last = q + j;
+        if ((j & 3) == 3 && e == dead) return last;
+      }
+    }
+  }
+};
+
+// Chain state of the find_iter iterator (re_trait.rs:174-179).
 struct Chain {
   uint64_t p, lm;  // next search position, end of the previous match (kNone = none)
   bool chain;      // p is a real restart point of the reference iterator
 };
-// Spans are written to dst[w_at + i] while w_at + i < limit; returns the matches accepted.
-__device__ __forceinline__ uint32_t word_walk(const WalkArgs& a, const Table& T, uint64_t word, uint64_t bit0, Chain& c,
-                                              uint64_t* dst, uint64_t w_at, uint64_t limit) {
-  uint32_t cnt = 0;
-  const uint64_t first_pos = bit0 + 1;
+
+// Is a speculative walk that assumed "the chain enters at or before `region_first`"
+// still valid when the chain really enters at (tp, tl)?  (strict: patterns that can
+// match empty or need the slice emulation depend on the exact entry.)
+__device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t tl, uint64_t region_first,
+                                        uint64_t first_cand, uint64_t region_next) {
+  if (tp == kNone) return false;
+  if (a.emulate_slice || a.can_match_empty)
+    return tp < region_first || (tp == region_first && !a.emulate_slice && !(a.can_match_empty && tl == region_first));
+  return tp <= first_cand && tp <= region_next;
+}
+
+// The chain over one chunk (bits [cb, ce) <-> positions [cb+1, ce], plus position 0
+// for the chunk that starts the haystack).  One flat loop -- find the next candidate,
+// run the anchored automaton, advance the iterator -- so that the lanes of a warp
+// stay in the same phase (the nested per-word version ran at 5.7 of 32 lanes active).
+// Spans are written to dst[w_at + i] while w_at + i < limit.  Returns the match count.
+template <typename Runner>
+__device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                               uint64_t* dst, uint64_t w_at, uint64_t limit) {
+  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+  const uint64_t ce = min(cb + a.chunk, a.n);
+  uint64_t total = 0;
+  uint64_t fc = kNone;
+  uint64_t cached_w = kNone, word = 0;
+  bool at_zero = c.p == 0 && cb == 0 && *a.flag0;  // position 0 has no bitmap bit
   while (c.p != kNone) {
-    const uint64_t lob = c.p > first_pos ? c.p - first_pos : 0;
-    if (lob >= 64) break;
-    const uint64_t m = word & (~0ull << lob);
-    if (!m) break;
-    const uint64_t s = first_pos + (uint64_t)(__ffsll((long long)m) - 1);
-    const uint64_t e = anchored_end(a.fwd, T, a.text, a.n, s);
+    uint64_t s;
+    if (at_zero) {
+      s = 0;
+      at_zero = false;
+    } else {
+      // next candidate position >= max(p, cb + 1): bit index = position - 1
+      uint64_t bit = max(c.p, cb + 1) - 1;
+      uint64_t m = 0;
+      while (bit < ce) {
+        const uint64_t wi = bit >> 6;
+        if (wi != cached_w) { word = a.bitmap[wi]; cached_w = wi; }
+        m = word & (~0ull << (bit & 63));
+        if (m) break;
+        bit = (wi + 1) << 6;
+      }
+      if (bit >= ce) break;
+      s = (bit & ~63ull) + (uint64_t)__ffsll((long long)m);
+      if (s > ce) break;  // candidate beyond the chunk (bits above ce are zero by construction)
+    }
+    if (fc == kNone) fc = s;
+    const uint64_t e = T.end_from(a, s);
     if (e == kNone) { c.p = s + 1; c.chain = false; continue; }  // unreachable for consistent tables
     uint64_t ms = s;
     if (a.emulate_slice && c.chain && e != c.p) {
@@ -415,77 +492,78 @@ __device__ __forceinline__ uint32_t word_walk(const WalkArgs& a, const Table& T,
       c.p = e;
     }
     c.lm = e;
-    if (w_at + cnt < limit) { dst[2 * (w_at + cnt)] = ms; dst[2 * (w_at + cnt) + 1] = e; }
-    cnt++;
+    if (w_at + total < limit) { dst[2 * (w_at + total)] = ms; dst[2 * (w_at + total) + 1] = e; }
+    total++;
   }
-  return cnt;
-}
-
-// Is a speculative walk that assumed "the chain enters at or before `region_first`"
-// still valid when the chain really enters at (tp, tl)?  (strict: patterns that can
-// match empty or need the slice emulation depend on the exact entry.)
-__device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t tl, uint64_t region_first,
-                                        uint64_t first_cand, uint64_t region_next) {
-  if (tp == kNone) return false;
-  if (a.emulate_slice || a.can_match_empty)
-    return tp < region_first || (tp == region_first && !a.emulate_slice && !(a.can_match_empty && tl == region_first));
-  return tp <= first_cand && tp <= region_next;
-}
-
-// The chain over one chunk (bits [cb, ce) <-> positions [cb+1, ce], plus position 0
-// for the chunk that starts the haystack).  Returns the number of matches.
-__device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Table& T, uint64_t k, Chain& c, uint64_t* first_cand,
-                                               uint64_t* dst, uint64_t w_at, uint64_t limit) {
-  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
-  const uint64_t ce = min(cb + a.chunk, a.n);
-  uint64_t total = 0;
-  *first_cand = kNone;
-  if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
-    *first_cand = 0;
-    total += word_walk(a, T, 1ull, ~0ull, c, dst, w_at, limit);
-  }
-  for (uint64_t b = cb; b < ce && c.p != kNone; b += 256) {
-    // 4 bitmap words (32 bytes) per load pair
-    const uint4* wp = reinterpret_cast<const uint4*>(a.bitmap + (b >> 6));
-    const uint4 v0 = __ldg(wp), v1 = (b + 128 < ce) ? __ldg(wp + 1) : make_uint4(0, 0, 0, 0);
-    const uint64_t w[4] = {((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v0.w << 32) | v0.z,
-                           ((uint64_t)v1.y << 32) | v1.x, ((uint64_t)v1.w << 32) | v1.z};
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint64_t bit0 = b + 64ull * j;
-      if (w[j] == 0 || bit0 >= ce) continue;
-      if (*first_cand == kNone) *first_cand = bit0 + (uint64_t)__ffsll((long long)w[j]);
-      total += word_walk(a, T, w[j], bit0, c, dst, w_at + total, limit);
-    }
-  }
+  *first_cand = fc;
   return total;
 }
 
+// Runner set-up shared by the walk kernels.
+template <bool FAST>
+struct RunnerSetup;
+template <>
+struct RunnerSetup<false> {
+  using type = GenericRunner;
+  static __device__ __forceinline__ type make(const WalkArgs& a) {
+    GenericRunner r;
+    r.T = stage_table(a.fwd, g_smem, a.use_smem);
+    return r;
+  }
+};
+template <>
+struct RunnerSetup<true> {
+  using type = FastRunner;
+  static __device__ __forceinline__ type make(const WalkArgs& a) {
+    FastRunner r;
+    r.tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+    const uint32_t n_ent = a.fwd.n_states * 256u;
+    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
+      const uint32_t row = i >> 8, b = i & 255u;
+      const uint32_t addr = r.tbase + (row << 10) + ((b ^ (row & 31u)) << 2);
+      const uint32_t val = fast_entry(r.tbase, a.fwd_next256[i]);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
+    }
+    __syncthreads();
+    r.thr = r.tbase + a.fwd.match_lo * 1024u;
+    r.start_e = fast_entry(r.tbase, a.fwd.start[32]);
+    r.eof = a.fwd_eof;
+    r.match_lo = a.fwd.match_lo;
+    return r;
+  }
+};
+
 // One thread per chunk: walk the chain speculatively (or from a given entry state),
-// staging up to stage_cap spans per chunk.  Re-run on dirty chunks after stitch_check.
+// staging up to stage_cap spans per chunk.  With a dirty list (after stitch_check)
+// only the listed chunks are walked again, densely packed into warps.
+template <bool FAST>
 __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
-  const Table T = stage_table(a.fwd, g_smem, a.use_smem);
-  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
-       k += (uint64_t)gridDim.x * blockDim.x) {
-    if (a.dirty && !a.dirty[k]) continue;
+  const auto R = RunnerSetup<FAST>::make(a);
+  const uint64_t work = a.dirty_list ? (uint64_t)*a.n_dirty : a.n_chunks;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < work;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = a.dirty_list ? a.dirty_list[idx] : idx;
     Chain c;
     c.p = a.in_p[k];
     c.lm = a.in_lm[k];
     c.chain = c.p != kSpec;
     if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
     uint64_t fc = kNone, total = 0;
-    if (c.p != kNone) total = chunk_walk(a, T, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
     a.out_p[k] = c.p;
     a.out_lm[k] = c.lm;
     a.count[k] = total;
     a.first_cand[k] = fc;
   }
 }
+template __global__ void walk_chunks<false>(WalkArgs);
+template __global__ void walk_chunks<true>(WalkArgs);
 
 // Staged spans -> final array at the prefix-summed offsets.  Chunks that overflowed
 // their staging slots are walked again, writing straight to the output.
+template <bool FAST>
 __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
-  const Table T = stage_table(a.fwd, g_smem, a.use_smem);
+  const auto R = RunnerSetup<FAST>::make(a);
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
        k += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t cnt = a.count[k], at = a.offset[k];
@@ -501,10 +579,12 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
       c.chain = c.p != kSpec;
       if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
       uint64_t fc;
-      chunk_walk(a, T, k, c, &fc, a.out, at, a.cap);
+      chunk_walk(a, R, k, c, &fc, a.out, at, a.cap);
     }
   }
 }
+template __global__ void compact_spans<false>(WalkArgs);
+template __global__ void compact_spans<true>(WalkArgs);
 
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {
@@ -517,7 +597,7 @@ __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_ch
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
        k += (uint64_t)gridDim.x * blockDim.x) {
-    if (k == 0) { a.dirty[0] = 0; continue; }
+    if (k == 0) continue;
     const uint64_t tp = a.out_p[k - 1], tl = a.out_lm[k - 1];
     const uint64_t c_first = a.base + k * (uint64_t)a.chunk + 1;  // first position of the chunk
     const uint64_t cp = a.in_p[k], cl = a.in_lm[k];
@@ -527,10 +607,7 @@ __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty) {
     if (!ok) {
       a.in_p[k] = tp;
       a.in_lm[k] = tl;
-      a.dirty[k] = 1;
-      atomicAdd(n_dirty, 1u);
-    } else {
-      a.dirty[k] = 0;
+      a.dirty_list[atomicAdd(n_dirty, 1u)] = (uint32_t)k;
     }
   }
 }

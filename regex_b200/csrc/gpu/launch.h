@@ -50,7 +50,10 @@ struct WalkArgs {
   uint64_t* out_lm;
   uint64_t* count;
   const uint64_t* offset;
-  uint8_t* dirty;
+  uint32_t* dirty_list;     // chunks to walk again (nullable: all chunks)
+  const uint32_t* n_dirty;
+  const uint16_t* fwd_next256;  // fast runner: byte-indexed forward anchored table
+  const uint16_t* fwd_eof;
   uint64_t* out;  // spans: start, end pairs
   uint64_t cap;
   int utf8;
@@ -77,7 +80,9 @@ __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint
                                 uint32_t* redo_list, uint32_t* n_redo);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result);
+template <bool FAST>
 __global__ void walk_chunks(WalkArgs a);
+template <bool FAST>
 __global__ void compact_spans(WalkArgs a);
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start);
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
