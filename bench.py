@@ -181,6 +181,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import regex_b200 as R
+    from regex_b200 import sharded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,12 +192,38 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n = int(args.gib * GIB)
-    text = device_corpus(n, SEED + rank, dev)
+    n = int(args.gib * GIB)          # bytes owned per GPU (multiple of 256)
+    total_len = n * world            # one haystack, byte-range sharded (weak scaling)
+    halo = 1 << 16
+    own = device_corpus(n, SEED + rank, dev)
+    geom = sharded.plan(total_len, world, rank, halo=halo)
+    assert geom.b - geom.a == n
+    if world > 1:
+        # replicate 256 B of left context and `halo` bytes of the right neighbour (NCCL p2p)
+        left = torch.empty(geom.a - geom.buf_lo, dtype=torch.uint8, device=dev)
+        right = torch.empty(geom.buf_hi - geom.b, dtype=torch.uint8, device=dev)
+        ops = []
+        if rank + 1 < world:
+            ops += [dist.P2POp(dist.isend, own[-256:].contiguous(), rank + 1), dist.P2POp(dist.irecv, right, rank + 1)]
+        if rank > 0:
+            ops += [dist.P2POp(dist.isend, own[:halo].contiguous(), rank - 1), dist.P2POp(dist.irecv, left, rank - 1)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        text = torch.cat([left, own, right])
+        del left, right
+        comm = sharded.TorchDistComm(dev)
+    else:
+        text = own
+        comm = sharded.SingleComm()
+    del own
+
     re_ = R.BytesRegex(args.pattern)
-    # generous span buffer: the count pass tells us what is needed
-    total = re_.find_all_device(text)
-    spans = torch.empty((total + 1024, 2), dtype=torch.int64, device=dev)
+    re_.set_stream(torch.cuda.current_stream().cuda_stream)  # so torch events bracket the kernels
+    info = re_.pattern_info()
+    # count pass sizes the span buffer
+    probe = sharded.GpuShardEngine(re_, text, cap=0)
+    n_local, _, _, _ = sharded.find_all_sharded(probe, geom, comm, info["can_match_empty"], info["has_looks"])
+    engine = sharded.GpuShardEngine(re_, text, cap=n_local + 1024)
 
     def barrier():
         if world > 1:
@@ -204,38 +231,35 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step():
-        return re_.find_all_device(text, spans)
+        return sharded.find_all_sharded(engine, geom, comm, info["can_match_empty"], info["has_looks"])
 
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches0 = R.kernel_launches()
-    scan_ms, walk_ms, lib_ms = [], [], []
+    scan_ms, walk_ms = [], []
     with ClockSampler(local_rank) as clk:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
-            got = step()
+            got, offset, grand_total, rounds = step()
             st = re_.last_stats()
-            scan_ms.append(st["scan_ms"]); walk_ms.append(st["walk_ms"]); lib_ms.append(st["total_ms"])
+            scan_ms.append(st["scan_ms"]); walk_ms.append(st["walk_ms"])
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
     launches = R.kernel_launches() - launches0
-    assert got == total
-    # device time of the timed region = sum of the library's own CUDA-event brackets (its
-    # stream is private; torch events on the current stream would not see it)
-    dev_s = sum(lib_ms) / 1e3
+    assert got == n_local
+    dev_s = e0.elapsed_time(e1) / 1e3
     t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall = float(t[0]), float(t[1])
     ms_per_step = dev_s / args.steps * 1e3
-    value = n * world / (dev_s / args.steps) / 1e9
+    value = total_len / (dev_s / args.steps) / 1e9
 
-    # ---- parity spot check on the first 32 MiB against the oracle (rank 0) ----
     result = None
     if rank == 0:
         peaks = {}
@@ -246,19 +270,24 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         scan = sum(scan_ms) / len(scan_ms)
-        alg_bytes = n + (n + 1) / 8 + 16 * total  # haystack read + start bitmap written + spans
+        alg_bytes = n + n / 8  # scan kernel: haystack read + start bitmap written (spans belong to the walk)
         achieved = alg_bytes / (scan / 1e3) / 1e9
         result = {
             "metric": "haystack GB/s scanned (find_iter, bit-exact spans)", "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}` over {args.gib:g} GiB/GPU synthetic English text",
-                       "haystack_bytes_per_gpu": n, "matches_per_gpu": total, "l2": "haystack (16 GiB) far exceeds the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the library stream, max over ranks; wall clock %.3f s" % wall},
+            "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}` over {args.gib:g} GiB/GPU synthetic English text "
+                                   f"({world} byte-range shard(s) of one {args.gib * world:g} GiB haystack)",
+                       "haystack_bytes_per_gpu": n, "matches_rank0": n_local, "matches_total": grand_total,
+                       "l2": "each shard (16 GiB) far exceeds the 126 MB L2; no flush needed",
+                       "timing": "torch CUDA events on the stream the library launches on (set_stream), barrier + synchronize on both sides, "
+                                 "max over ranks; includes the boundary all_gathers; wall clock %.3f s" % wall,
+                       "boundary_fixup_rounds": rounds},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "scan_rev_bitmap (+verify)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(scan, 4), "walk_ms": round(sum(walk_ms) / len(walk_ms), 4)},
+                         "traffic": None, "kernel": "scan_rev_fast", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(scan, 4),
+                         "other_kernels_ms": round(sum(walk_ms) / len(walk_ms), 4)},
             "clocks": clk.summary(),
             "fixups": {k: st[k] for k in ("scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks")},
         }
@@ -266,9 +295,10 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     if not args.no_e2e:
         e2e_n = min(n, 4 * GIB)
+        lo = geom.own_lo
         host = torch.empty(e2e_n, dtype=torch.uint8, pin_memory=True)
-        host.copy_(text[:e2e_n])
-        cap = int(total * (e2e_n / n) * 1.1) + 4096
+        host.copy_(text[lo:lo + e2e_n])
+        cap = int(n_local * (e2e_n / n) * 1.1) + 4096
         out = np.empty((cap, 2), dtype=np.uint64)
         tot = R.ctypes.c_size_t()
         for _ in range(2):
@@ -287,31 +317,35 @@ def run_ours(args):
         if rank == 0:
             result["e2e"] = {"value": round(e2e_n * world / float(t[0]) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": e2e_n,
                              "d2h_bytes_per_step": int(min(tot.value, cap) * 16 + 8), "haystack_bytes": e2e_n,
-                             "note": "rure_b200_find_all on pinned host memory; H2D of the haystack and D2H of all spans inside the timed region"}
+                             "note": "rure_b200_find_all on pinned host memory per rank (independent haystacks); H2D of the haystack and "
+                                     "D2H of all spans inside the timed region"}
         del host
 
     if rank == 0:
         if args.also:
             also = {}
+            spans = torch.empty((n_local * 2 + 4096, 2), dtype=torch.int64, device=dev)
+            local = text[geom.own_lo:geom.own_lo + n]
             for pat in ALSO:
                 r2 = R.BytesRegex(pat)
-                r2.find_all_device(text)
-                c = r2.find_all_device(text, spans)
+                r2.find_all_device(local)
+                c = r2.find_all_device(local, spans)
                 also[pat] = {"GB/s": round(n / (r2.last_stats()["total_ms"] / 1e3) / 1e9, 1), "matches": c}
             result["also"] = also
         if not args.no_cpu:
             from oracle import oracle as O
             sample_bytes = 128 << 20
-            sample = text[:sample_bytes].cpu().numpy().tobytes()
+            sample = text[geom.own_lo:geom.own_lo + sample_bytes].cpu().numpy().tobytes()
             last_nl = sample.rfind(b"\n") + 1
             threads = os.cpu_count() or 1
             gbs, dt, count = cpu_reference(args.pattern, sample[:last_nl], threads, 1, 1)
-            gpu_count = R.BytesRegex(args.pattern).find_all_device(text[:last_nl].contiguous())
+            gpu_count = R.BytesRegex(args.pattern).find_all_device(text[geom.own_lo:geom.own_lo + last_nl].contiguous())
             assert gpu_count == count, ("parity spot check failed", gpu_count, count)
             result["cpu_baseline"] = {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                                      "sample": f"first {last_nl >> 20} MiB of the same haystack, {threads} threads cut at newlines, count {count} == GPU count"}
+                                      "sample": f"first {last_nl >> 20} MiB of rank 0's shard, {threads} threads cut at newlines, count {count} == GPU count"}
         print(json.dumps(result), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

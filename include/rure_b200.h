@@ -70,6 +70,36 @@ bool rure_b200_set_matches_batch_device(rure_set *set, const uint8_t *d_haystack
                                         const uint64_t *d_offsets, size_t n_records,
                                         uint64_t *d_out_masks);
 
+/* ---- byte-range shards of one haystack (multi-GPU; one process per GPU) ------
+ * Each rank holds [left context | owned bytes | right halo] of the haystack in its
+ * own HBM and searches it with the call below; the ranks exchange only the three
+ * boundary values marked (x) -- see regex_b200/sharded.py for the protocol:
+ *   rev_left  -> left neighbour's rev_entry   (reverse-scan state at the shared edge)
+ *   exit_p/lm -> right neighbour's chain_p/lm (find_iter iterator state)
+ *   n_matches -> all ranks (global output offsets)
+ * Positions are relative to the buffer; own_lo and own_hi are multiples of 256
+ * (own_lo = 0 for the first shard, own_hi = n_buf for the last). */
+#define RURE_B200_NO_STATE 0xFFFFFFFFu
+#define RURE_B200_NONE (~(uint64_t)0)
+#define RURE_B200_SPEC (~(uint64_t)0 - 1)
+typedef struct rure_b200_shard {
+  /* in */
+  uint64_t own_lo, own_hi; /* owns match starts at positions (own_lo, own_hi] (+ 0 for the first shard) */
+  int32_t is_first, is_last;
+  uint32_t rev_entry;      /* (x) exact state at own_hi, or RURE_B200_NO_STATE to speculate */
+  uint32_t reuse_scan;     /* keep the start bitmap computed by the previous call on this buffer */
+  uint64_t chain_p, chain_lm; /* (x) iterator state entering the shard, or RURE_B200_SPEC */
+  /* out */
+  uint32_t rev_guess;      /* state the scan assumed at own_hi */
+  uint32_t rev_left;       /* (x) exact state at own_lo */
+  uint64_t exit_p, exit_lm;   /* (x) iterator state leaving the shard */
+  uint64_t n_matches;      /* (x) */
+  uint32_t halo_overflow;  /* a match ran past the end of the right halo (call failed) */
+  uint32_t reserved;
+} rure_b200_shard;
+bool rure_b200_find_all_shard_device(rure *re, const uint8_t *d_buffer, size_t n_buffer,
+                                     rure_b200_shard *io, rure_match *d_out, size_t cap);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 const char *rure_b200_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */
@@ -82,6 +112,9 @@ void rure_b200_last_stats(rure *re, double *out7);
  * warm = warm-up bytes (0 = automatic); 0 keeps the current value elsewhere. */
 void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block,
                           uint32_t blocks_per_sm);
+/* Launch this object's kernels on a caller-owned cudaStream_t (e.g. torch's current
+ * stream) instead of its private stream; pass the stream handle as a pointer value. */
+void rure_b200_set_stream(rure *re, void *cuda_stream);
 /* Tests: route scans through the generic kernel even when the fast one applies. */
 void rure_b200_force_generic(rure *re, int yes);
 /* Dense tables, for tests and tooling.  kind: 0 forward anchored leftmost-first,

@@ -29,6 +29,13 @@ class _Match(ctypes.Structure):
     _fields_ = [("start", c_size_t), ("end", c_size_t)]
 
 
+class _Shard(ctypes.Structure):  # include/rure_b200.h: rure_b200_shard
+    _fields_ = [("own_lo", c_uint64), ("own_hi", c_uint64), ("is_first", ctypes.c_int32), ("is_last", ctypes.c_int32),
+                ("rev_entry", c_uint32), ("reuse_scan", c_uint32), ("chain_p", c_uint64), ("chain_lm", c_uint64),
+                ("rev_guess", c_uint32), ("rev_left", c_uint32), ("exit_p", c_uint64), ("exit_lm", c_uint64),
+                ("n_matches", c_uint64), ("halo_overflow", c_uint32), ("reserved", c_uint32)]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -67,6 +74,7 @@ def _load():
         "rure_b200_find_batch": (c_bool, [vp, u8p, vp, sz, vp, vp]),
         "rure_b200_set_matches_batch": (c_bool, [vp, u8p, vp, sz, vp]),
         "rure_b200_find_all_device": (c_bool, [vp, vp, sz, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_find_all_shard_device": (c_bool, [vp, vp, sz, POINTER(_Shard), vp, sz]),
         "rure_b200_shortest_match_device": (c_bool, [vp, vp, sz, sz, POINTER(c_bool), POINTER(sz)]),
         "rure_b200_set_matches_device": (c_bool, [vp, vp, sz, sz, POINTER(c_uint64)]),
         "rure_b200_is_match_batch_device": (c_bool, [vp, vp, vp, sz, vp]),
@@ -77,6 +85,7 @@ def _load():
         "rure_b200_last_stats": (None, [vp, POINTER(c_double)]),
         "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
         "rure_b200_force_generic": (None, [vp, c_int]),
+        "rure_b200_set_stream": (None, [vp, vp]),
         "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
         "rure_b200_pattern_info": (None, [vp, POINTER(c_uint64)]),
     }
@@ -262,6 +271,17 @@ class _Compiled:
             raise Error(_last_error())
         return total.value
 
+    def find_all_shard_device(self, d_buffer, io, d_out=None):
+        """One shard of a sharded haystack (see regex_b200/sharded.py).  `io` carries the
+        in-fields of rure_b200_shard; returns its out-fields as a dict."""
+        sh = _Shard(own_lo=io["own_lo"], own_hi=io["own_hi"], is_first=int(io["is_first"]), is_last=int(io["is_last"]),
+                    rev_entry=io["rev_entry"], reuse_scan=int(io["reuse_scan"]), chain_p=io["chain_p"], chain_lm=io["chain_lm"])
+        cap = 0 if d_out is None else d_out.shape[0]
+        ptr = 0 if d_out is None else d_out.data_ptr()
+        if not _lib.rure_b200_find_all_shard_device(self._h, d_buffer.data_ptr(), d_buffer.numel(), byref(sh), ptr, cap):
+            raise Error(_last_error())
+        return dict(rev_guess=sh.rev_guess, rev_left=sh.rev_left, exit_p=sh.exit_p, exit_lm=sh.exit_lm, n_matches=sh.n_matches)
+
     def shortest_match_device(self, d_text, start=0):
         found, end = c_bool(), c_size_t()
         if not _lib.rure_b200_shortest_match_device(self._h, d_text.data_ptr(), d_text.numel(), start, byref(found), byref(end)):
@@ -288,6 +308,10 @@ class _Compiled:
 
     def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):
         _lib.rure_b200_set_tuning(self._h, seg, chunk, warm, block, blocks_per_sm)
+
+    def set_stream(self, cuda_stream):
+        """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _lib.rure_b200_set_stream(self._h, cuda_stream)
 
     def force_generic(self, yes=True):
         _lib.rure_b200_force_generic(self._h, int(yes))

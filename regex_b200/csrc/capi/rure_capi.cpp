@@ -297,6 +297,19 @@ bool rure_b200_set_matches_batch_device(rure_set* s, const uint8_t* d_haystack, 
   return ok(s->re, s->re->set_matches_batch_device(d_haystack, d_offsets, n, d_out_masks));
 }
 
+bool rure_b200_find_all_shard_device(rure* re, const uint8_t* d_buffer, size_t n_buffer, rure_b200_shard* io, rure_match* d_out, size_t cap) {
+  rbgpu::ShardIO s;
+  s.own_lo = io->own_lo; s.own_hi = io->own_hi;
+  s.is_first = io->is_first != 0; s.is_last = io->is_last != 0;
+  s.rev_entry = io->rev_entry; s.reuse_scan = io->reuse_scan != 0;
+  s.chain_p = io->chain_p; s.chain_lm = io->chain_lm;
+  bool r = ok(re->re, re->re->find_all_shard_device(d_buffer, n_buffer, &s, (uint64_t*)d_out, d_out ? cap : 0));
+  io->rev_guess = s.rev_guess; io->rev_left = s.rev_left;
+  io->exit_p = s.exit_p; io->exit_lm = s.exit_lm;
+  io->n_matches = s.n_matches; io->halo_overflow = s.halo_overflow;
+  return r;
+}
+
 const char* rure_b200_last_error(void) { return g_last_error.c_str(); }
 uint64_t rure_b200_kernel_launches(void) { return rbgpu::kernel_launches(); }
 void rure_b200_last_stats(rure* re, double* out7) {
@@ -313,6 +326,7 @@ void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm,
   if (block) t.block = (block + 31) / 32 * 32;
   if (blocks_per_sm) t.blocks_per_sm = blocks_per_sm;
 }
+void rure_b200_set_stream(rure* re, void* cuda_stream) { re->re->set_stream(cuda_stream); }
 void rure_b200_force_generic(rure* re, int yes) { re->re->tuning.force_generic = yes != 0; }
 bool rure_b200_dfa_export(rure* re, int kind, uint32_t* info6, uint16_t* trans, uint8_t* classes, uint16_t* start, uint64_t* masks) {
   if (kind < 0 || kind >= rbgpu::kNumDfaKinds) { g_last_error = "bad dfa kind"; return false; }

@@ -101,7 +101,7 @@ Regex* Regex::compile(const std::vector<std::string>& patterns, const CompileOpt
 Regex::~Regex() {
   for (auto*& d : dev_) { delete d; d = nullptr; }
   if (pinned_) cudaFreeHost(pinned_);
-  if (stream_) cudaStreamDestroy((cudaStream_t)stream_);
+  if (own_stream_) cudaStreamDestroy((cudaStream_t)own_stream_);
 }
 
 const rb::Dfa* Regex::host_dfa(DfaKind k, rb::Error* err) {
@@ -149,15 +149,16 @@ int Regex::check(int e, const char* what) {
   } while (0)
 
 int Regex::ensure(DfaKind k, DeviceDfa** out) {
-  if (!stream_) {
+  if (!pinned_) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
       return fail("no CUDA device available: regex_b200 has no CPU matching path");
     cudaStream_t s;
     RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    stream_ = s;
+    own_stream_ = s;
     RB_CUDA(cudaMallocHost(&pinned_, 4096));
   }
+  stream_ = use_ext_stream_ ? ext_stream_ : own_stream_;
   if (dev_[k]) { *out = dev_[k]; return 0; }
   rb::Error err;
   const rb::Dfa* h = host_dfa(k, &err);
@@ -220,26 +221,26 @@ static uint32_t pick_warm(const Regex& re) {
 }
 
 // ------------------------------------------------------------- start bitmap --
-int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
+int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io) {
   DeviceDfa* rev;
   if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  const uint64_t base = start ? ((start - 1) & ~255ull) : 0;  // bit i <-> position i+1
   const bool utf8_mask = only_utf8 && can_match_empty;
   const bool fast = rev->next256 && !utf8_mask && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
   // segment length: long enough to amortise the warm-up, short enough to fill the GPU
   uint32_t seg = tuning.seg;
   if (seg == 0) {
     const uint64_t lanes = (uint64_t)std::max(1, device_sm_count()) * 1024 * 2;
-    uint64_t want = ((n - base) / lanes + 63) / 64 * 64;
+    uint64_t want = ((limit - base) / lanes + 63) / 64 * 64;
     seg = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 256), fast ? 4096 : 1024);
   }
-  const uint64_t n_seg = std::max<uint64_t>(1, (n - base + seg - 1) / seg);
+  const uint64_t n_seg = std::max<uint64_t>(1, (limit - base + seg - 1) / seg);
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   ScanArgs a{};
   a.dfa = rev->view;
   a.text = d_text;
   a.n = n;
+  a.limit = limit;
   a.base = base;
   a.n_seg = n_seg;
   a.seg = seg;
@@ -247,7 +248,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
   if (fast) a.warm = (a.warm + 63) / 64 * 64;
   a.bitmap = (uint64_t*)bitmap_.ensure(((n >> 6) + 2) * 8);
   a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
-  a.fin = (uint16_t*)fin_.ensure(n_seg * 2);
+  a.fin = (uint16_t*)fin_.ensure((n_seg + 1) * 2);
   uint32_t* redo = (uint32_t*)redo_.ensure(n_seg * 4);
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
   if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
@@ -272,9 +273,41 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
     if (fast) scan_rev_fast<<<grid_for(work, block, fast_blocks), block, smem, st>>>(args);
     else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
   };
-  launch(a, n_seg);
-  RB_LAUNCH_CHECK("scan_rev");
+  const bool reuse = io && io->reuse_scan;
+  if (!reuse) {
+    launch(a, n_seg);
+    RB_LAUNCH_CHECK("scan_rev");
+  }
   stats.scan_redo_rounds = stats.scan_redo_segments = 0;
+  auto redo_round = [&](uint32_t n_redo) -> int {
+    stats.scan_redo_rounds++;
+    stats.scan_redo_segments += n_redo;
+    ScanArgs r = a;
+    r.redo_list = redo;
+    r.n_redo = counters;
+    launch(r, n_redo);
+    RB_LAUNCH_CHECK("scan_rev(redo)");
+    return 0;
+  };
+  // A shard may be told the exact state at its top edge by its right neighbour.
+  uint16_t* h16 = (uint16_t*)pinned_ + 512;
+  const bool shard = io && (!io->is_first || !io->is_last || io->rev_entry != kNoState);
+  if (shard) {
+    RB_CUDA(cudaMemcpyAsync(h16, a.guess + (n_seg - 1), 2, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    io->rev_guess = h16[0];
+    if (io->rev_entry != kNoState && io->rev_entry != io->rev_guess) {
+      h16[1] = (uint16_t)io->rev_entry;
+      uint32_t* h32 = (uint32_t*)pinned_ + 300;
+      h32[0] = (uint32_t)(n_seg - 1);
+      h32[1] = 1;
+      RB_CUDA(cudaMemcpyAsync(a.fin + n_seg, h16 + 1, 2, cudaMemcpyHostToDevice, st));
+      RB_CUDA(cudaMemcpyAsync(redo, h32, 4, cudaMemcpyHostToDevice, st));
+      RB_CUDA(cudaMemcpyAsync(counters, h32 + 1, 4, cudaMemcpyHostToDevice, st));
+      if (int rc = redo_round(1)) return rc;
+      io->rev_guess = io->rev_entry;
+    }
+  }
   for (;;) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
     verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 1, redo, counters);
@@ -283,23 +316,37 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start) {
     RB_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_redo = *(uint32_t*)pinned_;
     if (n_redo == 0) break;
-    stats.scan_redo_rounds++;
-    stats.scan_redo_segments += n_redo;
-    ScanArgs r = a;
-    r.redo_list = redo;
-    r.n_redo = counters;
-    launch(r, n_redo);
-    RB_LAUNCH_CHECK("scan_rev(redo)");
+    if (int rc = redo_round(n_redo)) return rc;
+  }
+  if (shard) {
+    RB_CUDA(cudaMemcpyAsync(h16, a.fin, 2, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    io->rev_left = h16[0];
   }
   return 0;
 }
 
 // ------------------------------------------------------------------ find_all --
 int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t* d_out, uint64_t cap, uint64_t* total) {
-  std::lock_guard<std::recursive_mutex> lock(mu_);
   *total = 0;
-  if (is_set_) return fail("find requires exactly one pattern (RegexSet cannot be used with find, exec.rs:510-512)");
   if (start > n) return 0;  // re_trait.rs:198-200
+  ShardIO io;
+  io.own_lo = start ? ((start - 1) & ~255ull) : 0;  // bit i <-> position i+1
+  io.own_hi = n;
+  io.chain_p = start;
+  io.chain_lm = kNone;
+  int rc = find_all_shard_device(d_text, n, &io, d_out, cap);
+  *total = io.n_matches;
+  return rc;
+}
+
+int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io, uint64_t* d_out, uint64_t cap) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  io->n_matches = 0;
+  io->halo_overflow = false;
+  if (is_set_) return fail("find requires exactly one pattern (RegexSet cannot be used with find, exec.rs:510-512)");
+  if (io->own_hi > n || io->own_lo > io->own_hi || (io->own_lo & 255) || (!io->is_last && ((io->own_hi & 255) || io->own_hi == n)))
+    return fail("bad shard geometry: own_lo/own_hi must be multiples of 256 inside the buffer (own_hi == n only for the last shard)");
   DeviceDfa *fwd, *rev = nullptr;
   if (int rc = ensure(kFwdAnchoredLF, &fwd)) return rc;
   const bool emulate = has_looks;
@@ -308,7 +355,7 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   cudaEvent_t ev[3];
   for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
   RB_CUDA(cudaEventRecord(ev[0], st));
-  if (int rc = scan_starts(d_text, n, start)) return rc;
+  if (int rc = scan_starts(d_text, n, io->own_lo, io->own_hi, io)) return rc;
   RB_CUDA(cudaEventRecord(ev[1], st));
 
   WalkArgs w{};
@@ -318,10 +365,12 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.n = n;
   w.bitmap = (const uint64_t*)bitmap_.ptr;
   w.flag0 = (const uint8_t*)((uint32_t*)counters_.ptr + 24);
-  w.base = start ? ((start - 1) & ~255ull) : 0;
+  w.base = io->own_lo;
+  w.limit = io->own_hi;
+  w.text_continues = !io->is_last;
   w.chunk = std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
   w.stage_cap = std::max<uint32_t>(4, w.chunk / 64);
-  w.n_chunks = std::max<uint64_t>(1, (n - std::min(n, w.base) + w.chunk - 1) / w.chunk);
+  w.n_chunks = std::max<uint64_t>(1, (w.limit - w.base + w.chunk - 1) / w.chunk);
   const uint64_t nc = w.n_chunks;
   w.in_p = (uint64_t*)in_p_.ensure(nc * 8);
   w.in_lm = (uint64_t*)in_lm_.ensure(nc * 8);
@@ -344,7 +393,9 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
   w.emulate_slice = emulate;
   w.can_match_empty = can_match_empty;
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
-  init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, start);
+  w.err_flag = counters + 28;
+  RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 4, st));
+  init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, io->chain_p, io->chain_lm);
   RB_LAUNCH_CHECK("init_walk_entries");
   // fast runner: byte-indexed shared-memory table, uniform start state, 8-byte aligned text
   const bool wfast = fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
@@ -398,14 +449,22 @@ int Regex::find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, ui
     else compact_spans<false><<<g, 256, wsmem, st>>>(w);
     RB_LAUNCH_CHECK("compact_spans");
   }
-  RB_CUDA(cudaMemcpyAsync(pinned_, grand, 8, cudaMemcpyDeviceToHost, st));
+  uint64_t* h = (uint64_t*)pinned_;
+  RB_CUDA(cudaMemcpyAsync(h, grand, 8, cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(h + 1, w.out_p + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(h + 2, w.out_lm + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(h + 3, w.err_flag, 4, cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaEventRecord(ev[2], st));
   RB_CUDA(cudaStreamSynchronize(st));
-  *total = *(uint64_t*)pinned_;
+  io->n_matches = h[0];
+  io->exit_p = h[1];
+  io->exit_lm = h[2];
+  io->halo_overflow = *(uint32_t*)(h + 3) != 0;
   cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
   cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
   cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);
   for (auto& e : ev) cudaEventDestroy(e);
+  if (io->halo_overflow) return fail("a match runs past the end of the shard halo; enlarge the halo");
   return 0;
 }
 

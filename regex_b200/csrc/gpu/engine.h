@@ -39,6 +39,25 @@ struct Stats {  // filled by the last single-haystack call (diagnostics, bench r
   float scan_ms = 0, walk_ms = 0, total_ms = 0;
 };
 
+constexpr uint32_t kNoState = 0xFFFFFFFFu;
+
+// One byte-range shard of a larger haystack (multi-GPU).  The buffer is
+// [left context | owned bytes | right halo]; positions are buffer-relative.
+struct ShardIO {
+  // in
+  uint64_t own_lo = 0, own_hi = 0;  // owns match starts at positions (own_lo, own_hi] (+ position 0 if own_lo == 0)
+  bool is_first = true, is_last = true;  // buffer begins / ends where the haystack does
+  uint32_t rev_entry = kNoState;    // exact reverse-scan state at own_hi from the right neighbour
+  uint64_t chain_p = 0, chain_lm = ~0ull;  // iterator state entering the shard (kSpec = speculate)
+  bool reuse_scan = false;          // keep the start bitmap of the previous call on this buffer
+  // out
+  uint32_t rev_guess = 0;           // state assumed at own_hi
+  uint32_t rev_left = 0;            // exact state at own_lo (what the left neighbour must assume)
+  uint64_t exit_p = 0, exit_lm = 0; // iterator state leaving the shard
+  uint64_t n_matches = 0;
+  bool halo_overflow = false;
+};
+
 class DeviceBuf {
  public:
   ~DeviceBuf();
@@ -60,6 +79,8 @@ class Regex {
   // find_iter (re_trait.rs:197-220): writes up to cap {start,end} pairs to d_out
   // (device memory, may be null to count only); *total = number of matches.
   int find_all_device(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t* d_out, uint64_t cap, uint64_t* total);
+  // the same over one shard of a sharded haystack; spans are buffer-relative
+  int find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io, uint64_t* d_out, uint64_t cap);
   // find_at (exec.rs:473-514)
   int find_at_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e);
   // shortest_match_at / is_match_at (exec.rs:382-468); for sets: any pattern.
@@ -81,6 +102,8 @@ class Regex {
   int find_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* spans, uint8_t* out_bits);
   int set_matches_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* masks);
 
+  // Run on a caller-owned CUDA stream (e.g. torch's current stream) instead of the private one.
+  void set_stream(void* cuda_stream) { ext_stream_ = cuda_stream; use_ext_stream_ = true; }
   const std::string& last_error() const { return error_; }
   Tuning tuning;
   Stats stats;
@@ -95,7 +118,7 @@ class Regex {
   int ensure(DfaKind k, DeviceDfa** out);
   int fail(const std::string& msg);
   int check(int cuda_err, const char* what);
-  int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t start);
+  int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io);
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
   const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
 
@@ -108,6 +131,9 @@ class Regex {
   std::string error_;
   std::recursive_mutex mu_;
   void* stream_ = nullptr;
+  void* own_stream_ = nullptr;
+  void* ext_stream_ = nullptr;
+  bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, stage_, block_sums_, out_, bits_, masks_;

@@ -31,8 +31,8 @@ __global__ void scan_rev_bitmap(ScanArgs a) {
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
-    const uint64_t lo = min(a.base + t * a.seg, a.n);
-    const uint64_t hi = min(lo + a.seg, a.n);  // bytes [lo, hi)
+    const uint64_t lo = min(a.base + t * a.seg, a.limit);
+    const uint64_t hi = min(lo + a.seg, a.limit);  // bytes [lo, hi); limit <= n (shards scan their own bytes only)
     uint32_t s;
     if (a.redo_list) {
       s = a.fin[t + 1];
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a) {
     uint32_t e = 0;
     if (live) {
       t = a.redo_list ? a.redo_list[idx] : idx;
-      lo = min(a.base + t * a.seg, a.n);  // multiple of 64 (or n)
-      hi = min(lo + a.seg, a.n);          // multiple of 64 (or n)
+      lo = min(a.base + t * a.seg, a.limit);  // multiple of 64 (or limit)
+      hi = min(lo + a.seg, a.limit);          // multiple of 64 (or limit == n)
       i = hi;
       if (a.redo_list) {
         e = fast_entry(tbase, a.fin[t + 1]);
@@ -343,10 +343,14 @@ __device__ __forceinline__ uint64_t next_bit(const uint64_t* bm, const uint8_t* 
 // End of the leftmost-first match anchored at s (src/dfa.rs:576-764 run on the
 // anchored program): last position at which a match state was entered, with the
 // one-byte delay and the EOF flush.
-__device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const Table& T, const uint8_t* text, uint64_t n, uint64_t s) {
+// halo_err: non-null when the buffer is a shard whose text continues past n (running
+// into n then means the halo was too short, not end-of-text).
+__device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const Table& T, const uint8_t* text, uint64_t n, uint64_t s,
+                                                 uint32_t* halo_err = nullptr) {
   uint32_t st = pick_start_fwd(d, text, n, s);
   uint64_t last = kNone;
   for (uint64_t q = s;; q++) {
+    if (q >= n && halo_err) { *halo_err = 1; return last; }
     st = q < n ? T.step(st, __ldg(text + q)) : T.step_eof(st);
     if (st >= d.match_lo) last = q;
     if (st == 0 || q >= n) break;
@@ -385,7 +389,7 @@ __device__ __forceinline__ uint64_t next_utf8(const uint8_t* text, uint64_t n, u
 struct GenericRunner {
   Table T;
   __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
-    return anchored_end(a.fwd, T, a.text, a.n, s);
+    return anchored_end(a.fwd, T, a.text, a.n, s, a.text_continues ? a.err_flag : nullptr);
   }
 };
 // Fast anchored runner: byte-indexed XOR-swizzled table in shared memory (one LDS per
@@ -410,6 +414,7 @@ struct FastRunner {
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         if ((uint64_t)j >= avail) {  // EOF step (dfa.rs:748-763)
+          if (a.text_continues) { *a.err_flag = 1; return last; }
           const uint32_t st = (e - tbase) >> 10;
           if (eof[st] >= match_lo) last = a.n;
           return last;
@@ -449,7 +454,7 @@ template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
                                                uint64_t* dst, uint64_t w_at, uint64_t limit) {
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
-  const uint64_t ce = min(cb + a.chunk, a.n);
+  const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
   uint64_t fc = kNone;
   uint64_t cached_w = kNone, word = 0;
@@ -586,10 +591,10 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
 template __global__ void compact_spans<false>(WalkArgs);
 template __global__ void compact_spans<true>(WalkArgs);
 
-__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start) {
+__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {
-    in_p[k] = k == 0 ? start : kSpec;
-    in_lm[k] = kNone;
+    in_p[k] = k == 0 ? p0 : kSpec;
+    in_lm[k] = k == 0 ? lm0 : kNone;
   }
 }
 

@@ -12,7 +12,8 @@ struct ScanArgs {
   DfaView dfa;
   int use_smem;
   const uint8_t* text;
-  uint64_t n;        // haystack length
+  uint64_t n;        // haystack (buffer) length
+  uint64_t limit;    // reverse scan: bytes [base, limit) are scanned (== n except for shards)
   uint64_t base;     // first position covered (64-aligned for bitmap scans)
   uint64_t n_seg;
   uint32_t seg;      // positions per segment (multiple of 64)
@@ -35,6 +36,9 @@ struct WalkArgs {
   DfaView rev;  // reverse, anchored, longest (reference dfa_reverse) -- slice emulation only
   const uint8_t* text;
   uint64_t n;
+  uint64_t limit;        // candidate bits [base, limit) (== n except for shards)
+  int text_continues;    // shard: the haystack goes on after n (no EOF there)
+  uint32_t* err_flag;    // set when a match runs past the end of a shard's halo
   const uint64_t* bitmap;
   const uint8_t* flag0;
   uint64_t base;  // first bitmap bit of chunk 0 (64-aligned); bit i <-> position i+1
@@ -84,7 +88,7 @@ template <bool FAST>
 __global__ void walk_chunks(WalkArgs a);
 template <bool FAST>
 __global__ void compact_spans(WalkArgs a);
-__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t start);
+__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
 __global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);
 __global__ void scan_block_sums(uint64_t* block_sums, uint64_t n_blocks, unsigned long long* grand_total);

@@ -1,0 +1,214 @@
+"""Byte-range sharding of one haystack across GPUs.
+
+One process per GPU.  Rank g keeps [left context | its bytes | right halo] of the
+haystack in its own HBM and runs the ordinary single-GPU kernels on it through
+rure_b200_find_all_shard_device.  The only data that crosses NVLink are three tiny
+per-shard values, exchanged with all_gather (NCCL on GPUs, gloo in the CPU tests):
+
+  1. the reverse-scan state at the shard's left edge -- the right-hand neighbour of a
+     shard boundary knows it exactly, the left-hand one guessed it from its halo;
+     a wrong guess triggers a redo of the affected segments only;
+  2. the find_iter iterator state (next search position, previous match end) leaving
+     each shard -- a shard that speculated "the iterator enters at my first byte" re-walks
+     (no re-scan) when a match of its left neighbour reaches into it;
+  3. the match counts, whose exclusive prefix sum gives every rank its global offset.
+
+The reference has nothing to mirror here (the crate is single-threaded per search,
+exec.rs:1066-1072); results equal find_iter over the concatenated haystack.
+"""
+from dataclasses import dataclass
+
+NO_STATE = 0xFFFFFFFF
+NONE = (1 << 64) - 1
+SPEC = NONE - 1
+ALIGN = 256
+
+
+@dataclass
+class ShardGeometry:
+    rank: int
+    world: int
+    total: int      # length of the whole haystack
+    a: int          # this rank owns match starts at global positions (a, b]  (+ 0 for rank 0)
+    b: int
+    buf_lo: int     # global index of buffer byte 0
+    buf_hi: int     # global index one past the last buffer byte
+
+    @property
+    def own_lo(self):
+        return self.a - self.buf_lo
+
+    @property
+    def own_hi(self):
+        return self.b - self.buf_lo
+
+    @property
+    def n_buf(self):
+        return self.buf_hi - self.buf_lo
+
+    @property
+    def is_first(self):
+        return self.rank == 0
+
+    @property
+    def is_last(self):
+        return self.rank == self.world - 1
+
+
+def plan(total, world, rank, halo=1 << 16, left_ctx=ALIGN):
+    """Boundaries at multiples of 256 bytes; `halo` bytes of the right neighbour and
+    `left_ctx` bytes of the left neighbour are replicated (look-behind / long matches)."""
+    assert halo % 16 == 0 and left_ctx % ALIGN == 0 and left_ctx >= ALIGN
+
+    def edge(g):
+        if g <= 0:
+            return 0
+        if g >= world:
+            return total
+        return min(total, (total * g // world) // ALIGN * ALIGN)
+
+    a, b = edge(rank), edge(rank + 1)
+    if rank < world - 1 and b >= total:  # tiny haystacks: trailing ranks own nothing
+        b = a if a >= total else b
+    buf_lo = a - left_ctx if rank > 0 and a > 0 else a
+    buf_hi = total if rank == world - 1 else min(total, b + halo)
+    return ShardGeometry(rank, world, total, a, b, buf_lo, buf_hi)
+
+
+class TorchDistComm:
+    """all_gather of small integer vectors over torch.distributed (nccl or gloo)."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_gather(self, values):
+        import torch
+        # 64-bit patterns travel as int64 (two's complement keeps NONE / SPEC intact)
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in values], dtype=torch.int64, device=self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [[int(x) & ((1 << 64) - 1) for x in o.tolist()] for o in out]
+
+
+class ThreadComm:
+    """In-process stand-in for the collectives: `world` threads, each owning one shard
+    (tests drive several shards through one GPU this way)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+
+    def view(self, rank):
+        parent = self
+
+        class _View:
+            world = parent.world
+
+            def __init__(self):
+                self.rank = rank
+
+            def all_gather(self, values):
+                parent._slots[rank] = list(values)
+                parent._barrier.wait()
+                out = [list(v) for v in parent._slots]
+                parent._barrier.wait()
+                return out
+
+        return _View()
+
+
+class SingleComm:
+    rank, world = 0, 1
+
+    def all_gather(self, values):
+        return [list(values)]
+
+
+def _spec_ok(tp, tl, c_first, can_match_empty, has_looks):
+    """Mirror of spec_ok() in csrc/gpu/kernels.cu at shard granularity."""
+    if tp == NONE:
+        return False
+    if can_match_empty or has_looks:
+        return tp < c_first or (tp == c_first and not has_looks and not (can_match_empty and tl == c_first))
+    return tp <= c_first
+
+
+def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
+    """Run the boundary protocol.  `engine.run(io: dict) -> dict` executes one shard search
+    (see GpuShardEngine) and returns rev_guess, rev_left, exit_p, exit_lm, n_matches with
+    positions relative to the shard buffer.
+
+    Returns (n_local, global_offset, global_total); the engine holds the local spans
+    (buffer-relative; add geom.buf_lo for global positions)."""
+    to_buf = lambda v: v if v in (NONE, SPEC) else v - geom.buf_lo
+    to_glob = lambda v: v if v in (NONE, SPEC) else v + geom.buf_lo
+    io = dict(own_lo=geom.own_lo, own_hi=geom.own_hi, is_first=geom.is_first, is_last=geom.is_last,
+              rev_entry=NO_STATE, reuse_scan=False,
+              chain_p=to_buf(start) if geom.is_first else SPEC, chain_lm=NONE)
+    owns_nothing = geom.a >= geom.b and not geom.is_first
+    res = engine.run(io) if not owns_nothing else None
+    rounds = 0
+    # ---- 1. reverse-scan states flow right-to-left ------------------------------
+    while True:
+        mine = [NO_STATE, NO_STATE] if res is None else [res["rev_left"], res["rev_guess"]]
+        states = comm.all_gather(mine + [0])
+        changed = 0
+        if res is not None and not geom.is_last:
+            # nearest right neighbour that owns bytes
+            want = next((states[g][0] for g in range(geom.rank + 1, geom.world) if states[g][0] != NO_STATE), NO_STATE)
+            if want != NO_STATE and want != res["rev_guess"]:
+                io.update(rev_entry=want, reuse_scan=True)
+                res = engine.run(io)
+                changed = 1
+        if not any(s[2] for s in comm.all_gather([0, 0, changed])):
+            break
+        rounds += 1
+    # ---- 2. iterator state flows left-to-right ----------------------------------
+    while True:
+        mine = [SPEC, SPEC] if res is None else [to_glob(res["exit_p"]), to_glob(res["exit_lm"])]
+        exits = comm.all_gather(mine + [0])
+        changed = 0
+        if res is not None and not geom.is_first:
+            tp, tl = next(((exits[g][0], exits[g][1]) for g in range(geom.rank - 1, -1, -1) if exits[g][0] != SPEC))
+            tp_b = to_buf(tp)
+            tl_b = NONE if (tl != NONE and tl < geom.buf_lo) else to_buf(tl)
+            if io["chain_p"] == SPEC:
+                # positions left of the buffer are "before my first byte" whatever their value
+                before = tp != NONE and tp < geom.buf_lo
+                ok = before or _spec_ok(tp_b, tl_b, geom.own_lo + 1, can_match_empty, has_looks)
+            else:
+                ok = (io["chain_p"], io["chain_lm"]) == (tp_b, tl_b)
+            if not ok:
+                if tp != NONE and tp < geom.buf_lo:
+                    tp_b, tl_b = 0, NONE
+                io.update(chain_p=tp_b, chain_lm=tl_b, reuse_scan=True)
+                res = engine.run(io)
+                changed = 1
+        if not any(s[2] for s in comm.all_gather([0, 0, changed])):
+            break
+        rounds += 1
+    # ---- 3. counts -> global offsets ----------------------------------------------
+    counts = [c[0] for c in comm.all_gather([0 if res is None else res["n_matches"], 0, 0])]
+    return counts[geom.rank], sum(counts[:geom.rank]), sum(counts), rounds
+
+
+class GpuShardEngine:
+    """Shard search through the C ABI on a CUDA buffer (torch uint8 tensor)."""
+
+    def __init__(self, regex, d_buffer, cap):
+        import torch
+        self.regex = regex
+        self.d_buffer = d_buffer
+        self.spans = torch.empty((max(cap, 1), 2), dtype=torch.int64, device=d_buffer.device)
+        self.last = None
+
+    def run(self, io):
+        self.last = self.regex.find_all_shard_device(self.d_buffer, io, self.spans)
+        return self.last

@@ -246,3 +246,46 @@ def test_large_haystack_properties():
         # count-only mode must agree with emit mode
         assert r.find_all_device(d) == total
         assert n == len(base) * reps
+
+
+# ------------------------------------------------------------------- shards ----
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_search_matches_whole_haystack(world):
+    """Several byte-range shards driven through one GPU (one thread per shard, in-process
+    collectives): results must equal find_iter over the whole haystack."""
+    import threading
+    import torch
+    from regex_b200 import sharded
+    text = tiled_corpus(3 << 20) + b"a" * 70000 + b"\n" + tiled_corpus(1 << 20, seed=5)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    for pat in [r"[a-zA-Z]+ing", r"Holmes|Watson", r"aaa", r"(?m)^\w+", r"a*", r"[^\n]{5,}"]:
+        exp = O.OracleRegex(pat).find_iter(text)
+        comm = sharded.ThreadComm(world)
+        out = [None] * world
+        errs = []
+
+        def work(rank):
+            try:
+                re_ = R.BytesRegex(pat)
+                info = re_.pattern_info()
+                geom = sharded.plan(len(text), world, rank, halo=1 << 17)
+                buf = d_text[geom.buf_lo:geom.buf_hi].clone()
+                eng = sharded.GpuShardEngine(re_, buf, cap=len(exp) + 16)
+                n_local, offset, total, rounds = sharded.find_all_sharded(eng, geom, comm.view(rank), info["can_match_empty"], info["has_looks"])
+                spans = (eng.spans[:n_local] + geom.buf_lo).cpu().numpy()
+                out[rank] = (offset, spans, total)
+            except Exception as e:  # surface failures instead of dead-locking the barrier
+                errs.append(e)
+                comm._barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errs, errs
+        merged = []
+        for off, sp, total in out:
+            assert off == len(merged) and total == len(exp)
+            merged += [tuple(int(v) for v in r) for r in sp.tolist()]
+        assert merged == exp, (pat, world)

@@ -1,0 +1,97 @@
+"""World-size-2 (and 3) gloo test of the byte-range sharding protocol (CPU only).
+
+The shard engine is the table-walking simulator; the collectives are real
+torch.distributed all_gathers.  Rank 0 checks the concatenated spans against the oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import regex_b200 as R
+from helpers import sherlock_text
+from oracle import oracle as O
+from regex_b200 import sharded
+
+CASES = [
+    (r"[a-zA-Z]+ing", None), (r"Holmes|Watson", None), (r"\w+", None), (r"aaa", b"a" * 1500 + b"b" + b"a" * 700),
+    (r"a*", b"aab" * 400), (r"", b"xyz" * 300), (r"(?m)^\w+$", None), (r"(?-u:\b)\w+(?-u:\b)", None),
+    (r"[^\n]*", None), (r"(?s-u)Holmes.{0,12}", None),
+]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, text, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_sim import SimShardEngine
+    comm = sharded.TorchDistComm(torch.device("cpu"))
+    results = []
+    for pat, special in CASES:
+        t = special if special is not None else text
+        re_ = R.BytesRegex(pat)
+        info = re_.pattern_info()
+        geom = sharded.plan(len(t), world, rank, halo=512, left_ctx=256)
+        eng = SimShardEngine(re_, t[geom.buf_lo:geom.buf_hi], warm=0)  # warm=0: the guess is often wrong
+        n_local, offset, total, rounds = sharded.find_all_sharded(eng, geom, comm, info["can_match_empty"], info["has_looks"])
+        spans = [(s + geom.buf_lo, e + geom.buf_lo) for s, e in eng.spans]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (offset, spans, rounds))
+        if rank == 0:
+            merged = []
+            for off, sp, _ in sorted(gathered):
+                assert off == len(merged)
+                merged += sp
+            results.append((pat, merged, total, max(g[2] for g in gathered)))
+    if rank == 0:
+        q.put(results)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_protocol_matches_oracle(world):
+    text = sherlock_text()[3000:9000]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, text, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    saw_fixup = False
+    for (pat, special), (pat2, merged, total, rounds) in zip(CASES, results):
+        t = special if special is not None else text
+        exp = O.OracleRegex(pat).find_iter(t)
+        assert merged == exp, (pat, world, merged[:5], exp[:5])
+        assert total == len(exp)
+        saw_fixup = saw_fixup or rounds > 0
+    assert saw_fixup, "no case exercised a boundary fix-up; the test lost its teeth"
+
+
+def test_plan_covers_haystack_exactly():
+    for total in [0, 1, 255, 256, 257, 1000, 4096, 100000]:
+        for world in [1, 2, 3, 8]:
+            owned = []
+            for r in range(world):
+                g = sharded.plan(total, world, r, halo=64, left_ctx=256)
+                assert g.own_lo % 256 == 0 and (g.is_last or g.own_hi % 256 == 0)
+                assert 0 <= g.buf_lo <= g.a <= g.b <= g.buf_hi <= total
+                owned.append((g.a, g.b))
+            assert owned[0][0] == 0 and owned[-1][1] == total
+            for (a0, b0), (a1, b1) in zip(owned, owned[1:]):
+                assert b0 == a1
