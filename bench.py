@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--pattern", default=PATTERN)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--seg", type=int, default=0, help="scan segment bytes (0 = automatic)")
+    ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--also", action="store_true", help="time the other C2 patterns once each (extra keys)")
     return ap.parse_args()
 
@@ -219,6 +221,10 @@ def run_ours(args):
 
     re_ = R.BytesRegex(args.pattern)
     re_.set_stream(torch.cuda.current_stream().cuda_stream)  # so torch events bracket the kernels
+    if args.seg:
+        re_.set_tuning(seg=args.seg)
+    if args.no_fuse:
+        re_.set_fuse(False)
     info = re_.pattern_info()
     # count pass sizes the span buffer
     probe = sharded.GpuShardEngine(re_, text, cap=0)
@@ -233,13 +239,12 @@ def run_ours(args):
     def step():
         return sharded.find_all_sharded(engine, geom, comm, info["can_match_empty"], info["has_looks"])
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = R.kernel_launches()
     scan_ms, walk_ms = [], []
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:  # samples cover the warm-up steps and the timed steps
+        for _ in range(max(args.warmup, 3)):
+            step()
         barrier()
+        launches0 = R.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()

@@ -86,6 +86,7 @@ def _load():
         "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
         "rure_b200_force_generic": (None, [vp, c_int]),
         "rure_b200_set_stream": (None, [vp, vp]),
+        "rure_b200_set_fuse": (None, [vp, c_int]),
         "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
         "rure_b200_pattern_info": (None, [vp, POINTER(c_uint64)]),
     }
@@ -312,6 +313,9 @@ class _Compiled:
     def set_stream(self, cuda_stream):
         """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         _lib.rure_b200_set_stream(self._h, cuda_stream)
+
+    def set_fuse(self, yes=True):
+        _lib.rure_b200_set_fuse(self._h, int(yes))
 
     def force_generic(self, yes=True):
         _lib.rure_b200_force_generic(self._h, int(yes))

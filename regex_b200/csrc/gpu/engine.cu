@@ -214,6 +214,10 @@ static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t block
   return (uint32_t)std::max<uint64_t>(1, std::min(blocks, cap));
 }
 
+static size_t fast_scan_smem(uint32_t table_states) {
+  return (size_t)table_states * 1024 + 1024 + (1024 / 32) * (2 * 32 * 80 + 16);
+}
+
 static uint32_t pick_warm(const Regex& re) {
   if (re.tuning.warm) return (re.tuning.warm + 15) / 16 * 16;
   if (re.max_len != rb::kUnbounded) return (uint32_t)std::min<uint64_t>((std::max<uint64_t>(re.max_len, 1) + 15) / 16 * 16, 4096);
@@ -221,20 +225,33 @@ static uint32_t pick_warm(const Regex& re) {
 }
 
 // ------------------------------------------------------------- start bitmap --
-int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io) {
-  DeviceDfa* rev;
-  if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
-  cudaStream_t st = (cudaStream_t)stream_;
+Regex::ScanPlan Regex::plan_scan(const uint8_t* d_text, uint64_t base, uint64_t limit, bool fast_table) {
+  ScanPlan p;
   const bool utf8_mask = only_utf8 && can_match_empty;
-  const bool fast = rev->next256 && !utf8_mask && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
+  p.fast = fast_table && !utf8_mask && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
   // segment length: long enough to amortise the warm-up, short enough to fill the GPU
   uint32_t seg = tuning.seg;
   if (seg == 0) {
     const uint64_t lanes = (uint64_t)std::max(1, device_sm_count()) * 1024 * 2;
-    uint64_t want = ((limit - base) / lanes + 63) / 64 * 64;
-    seg = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 256), fast ? 4096 : 1024);
+    uint64_t want = ((limit - base) / lanes + 255) / 256 * 256;
+    seg = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 256), p.fast ? 4096 : 1024);
   }
-  const uint64_t n_seg = std::max<uint64_t>(1, (limit - base + seg - 1) / seg);
+  p.seg = seg;
+  p.n_seg = std::max<uint64_t>(1, (limit - base + seg - 1) / seg);
+  p.warm = pick_warm(*this);
+  if (p.fast) p.warm = (p.warm + 63) / 64 * 64;
+  return p;
+}
+
+int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
+                       const void* fused_walk) {
+  DeviceDfa* rev;
+  if (int rc = ensure(kRevUnanchoredAll, &rev)) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const bool utf8_mask = only_utf8 && can_match_empty;
+  const bool fast = plan.fast;
+  const uint32_t seg = plan.seg;
+  const uint64_t n_seg = plan.n_seg;
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   ScanArgs a{};
   a.dfa = rev->view;
@@ -244,8 +261,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   a.base = base;
   a.n_seg = n_seg;
   a.seg = seg;
-  a.warm = pick_warm(*this);
-  if (fast) a.warm = (a.warm + 63) / 64 * 64;
+  a.warm = plan.warm;
   a.bitmap = (uint64_t*)bitmap_.ensure(((n >> 6) + 2) * 8);
   a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
   a.fin = (uint16_t*)fin_.ensure((n_seg + 1) * 2);
@@ -257,12 +273,14 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   a.next256 = (const uint16_t*)rev->next256;
   a.eof = (const uint16_t*)rev->eof;
   size_t smem;
-  uint32_t block, fast_blocks = 1;
+  uint32_t block;
+  const WalkArgs* fw = (const WalkArgs*)fused_walk;
+  WalkArgs no_walk{};
   if (fast) {
     block = 1024;
-    smem = (size_t)rev->view.n_states * 1024 + 1024 + (block / 32) * (2 * 32 * 80 + 16);
-    fast_blocks = 1;
-    RB_CUDA(cudaFuncSetAttribute(scan_rev_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem = fast_scan_smem(rev->view.n_states + (fw ? fw->fwd.n_states : 0));
+    if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   } else {
     smem = smem_for(rev->view);
     a.use_smem = smem != 0;
@@ -270,7 +288,8 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     RB_CUDA(allow_smem(scan_rev_bitmap, smem));
   }
   auto launch = [&](const ScanArgs& args, uint64_t work) {
-    if (fast) scan_rev_fast<<<grid_for(work, block, fast_blocks), block, smem, st>>>(args);
+    if (fast && fw) scan_rev_fast<true><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw);
+    else if (fast) scan_rev_fast<false><<<grid_for(work, block, 1), block, smem, st>>>(args, no_walk);
     else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
   };
   const bool reuse = io && io->reuse_scan;
@@ -351,24 +370,34 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   if (int rc = ensure(kFwdAnchoredLF, &fwd)) return rc;
   const bool emulate = has_looks;
   if (emulate) if (int rc = ensure(kRevAnchoredLongest, &rev)) return rc;
+  DeviceDfa* revall;
+  if (int rc = ensure(kRevUnanchoredAll, &revall)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
   cudaEvent_t ev[3];
   for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
   RB_CUDA(cudaEventRecord(ev[0], st));
-  if (int rc = scan_starts(d_text, n, io->own_lo, io->own_hi, io)) return rc;
-  RB_CUDA(cudaEventRecord(ev[1], st));
+  const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi, revall->next256 != nullptr);
+  // runner: 2 = fixed-length (no haystack access), 1 = byte-indexed shared-memory table
+  // (uniform start state, 8-byte aligned text), 0 = generic
+  const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;
+  const bool wfast = !wfixed && fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
+  const int wkind = wfixed ? 2 : wfast ? 1 : 0;
+  // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
+  const bool fused = plan.fast && wkind == 1 && tuning.fuse && !io->reuse_scan &&
+                     fast_scan_smem(revall->view.n_states + fwd->view.n_states) <= 227 * 1024;
 
   WalkArgs w{};
   w.fwd = fwd->view;
   if (rev) w.rev = rev->view;
   w.text = d_text;
   w.n = n;
+  if (!bitmap_.ensure(((n >> 6) + 2) * 8) || !counters_.ensure(128)) return fail("out of device memory (bitmap)");
   w.bitmap = (const uint64_t*)bitmap_.ptr;
   w.flag0 = (const uint8_t*)((uint32_t*)counters_.ptr + 24);
   w.base = io->own_lo;
   w.limit = io->own_hi;
   w.text_continues = !io->is_last;
-  w.chunk = std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
+  w.chunk = fused ? plan.seg : std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
   w.stage_cap = std::max<uint32_t>(4, w.chunk / 64);
   w.n_chunks = std::max<uint64_t>(1, (w.limit - w.base + w.chunk - 1) / w.chunk);
   const uint64_t nc = w.n_chunks;
@@ -397,28 +426,33 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 4, st));
   init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, io->chain_p, io->chain_lm);
   RB_LAUNCH_CHECK("init_walk_entries");
-  // fast runner: byte-indexed shared-memory table, uniform start state, 8-byte aligned text
-  const bool wfast = fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
-  size_t wsmem;
-  if (wfast) {
+  size_t wsmem = 0;
+  if (wfixed) {
+    w.fixed_len = min_len;
+  } else if (wfast) {
     wsmem = (size_t)fwd->view.n_states * 1024 + 1024;
     w.fwd_next256 = (const uint16_t*)fwd->next256;
     w.fwd_eof = (const uint16_t*)fwd->eof;
-    RB_CUDA(allow_smem(walk_chunks<true>, wsmem));
-    RB_CUDA(allow_smem(compact_spans<true>, wsmem));
+    RB_CUDA(allow_smem(walk_chunks<1>, wsmem));
+    RB_CUDA(allow_smem(compact_spans<1>, wsmem));
   } else {
     wsmem = smem_for(fwd->view);
     w.use_smem = wsmem != 0;
-    RB_CUDA(allow_smem(walk_chunks<false>, wsmem));
-    RB_CUDA(allow_smem(compact_spans<false>, wsmem));
+    RB_CUDA(allow_smem(walk_chunks<0>, wsmem));
+    RB_CUDA(allow_smem(compact_spans<0>, wsmem));
   }
   auto launch_walk = [&](const WalkArgs& args, uint64_t work) {
     const uint32_t g = grid_for(work, 256, 6);
-    if (wfast) walk_chunks<true><<<g, 256, wsmem, st>>>(args);
-    else walk_chunks<false><<<g, 256, wsmem, st>>>(args);
+    if (wkind == 2) walk_chunks<2><<<g, 256, 0, st>>>(args);
+    else if (wkind == 1) walk_chunks<1><<<g, 256, wsmem, st>>>(args);
+    else walk_chunks<0><<<g, 256, wsmem, st>>>(args);
   };
-  launch_walk(w, nc);
-  RB_LAUNCH_CHECK("walk_chunks");
+  if (int rc = scan_starts(d_text, n, io->own_lo, io->own_hi, io, plan, fused ? &w : nullptr)) return rc;
+  RB_CUDA(cudaEventRecord(ev[1], st));
+  if (!fused) {
+    launch_walk(w, nc);
+    RB_LAUNCH_CHECK("walk_chunks");
+  }
   stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
   for (;;) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
@@ -445,8 +479,9 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   RB_LAUNCH_CHECK("scan_add_block_offsets");
   if (w.cap > 0) {
     const uint32_t g = grid_for(nc, 256, 6);
-    if (wfast) compact_spans<true><<<g, 256, wsmem, st>>>(w);
-    else compact_spans<false><<<g, 256, wsmem, st>>>(w);
+    if (wkind == 2) compact_spans<2><<<g, 256, 0, st>>>(w);
+    else if (wkind == 1) compact_spans<1><<<g, 256, wsmem, st>>>(w);
+    else compact_spans<0><<<g, 256, wsmem, st>>>(w);
     RB_LAUNCH_CHECK("compact_spans");
   }
   uint64_t* h = (uint64_t*)pinned_;

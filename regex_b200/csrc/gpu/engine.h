@@ -27,6 +27,7 @@ enum DfaKind { kFwdAnchoredLF = 0, kRevUnanchoredAll, kFwdUnanchoredAll, kRevAnc
 struct Tuning {
   uint32_t seg = 0;        // bytes per scan segment (multiple of 64); 0 = automatic
   bool force_generic = false;  // tests: use the generic scan kernel even when the fast one applies
+  bool fuse = true;            // walk each segment's chain inside the fast scan kernel
   uint32_t chunk = 2048;   // bitmap bits per chain-walk chunk (one thread; multiple of 256)
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;
@@ -118,7 +119,10 @@ class Regex {
   int ensure(DfaKind k, DeviceDfa** out);
   int fail(const std::string& msg);
   int check(int cuda_err, const char* what);
-  int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io);
+  struct ScanPlan { bool fast = false; uint32_t seg = 0, warm = 0; uint64_t n_seg = 0; };
+  ScanPlan plan_scan(const uint8_t* d_text, uint64_t base, uint64_t limit, bool fast_table);
+  int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
+                  const void* fused_walk);
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
   const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
 

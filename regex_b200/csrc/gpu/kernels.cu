@@ -132,113 +132,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-__global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a) {
-  // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
-  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t ring = tbase + a.dfa.n_states * 1024u + wid * kRingWarpBytes;
-  const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
-  {
-    const uint32_t n_ent = a.dfa.n_states * 256u;
-    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
-      const uint32_t r = i >> 8, b = i & 255u;
-      const uint32_t nx = a.next256[i];
-      const uint32_t addr = tbase + (r << 10) + ((b ^ (r & 31u)) << 2);
-      const uint32_t val = fast_entry(tbase, nx);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
-    }
-    if (lane == 0) {
-      mbar_init(bar0, 32);
-      mbar_init(bar0 + 8, 32);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-  }
-  const uint32_t thr = tbase + a.dfa.match_lo * 1024u;
-  const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
-  const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t rounds = (total + stride - 1) / stride;  // uniform: every warp makes every round
-  uint32_t uses = 0;  // ring uses so far (same for the whole warp): stage = uses & 1, parity = (uses >> 1) & 1
-  for (uint64_t round = 0; round < rounds; round++) {
-    const uint64_t idx = first + round * stride;
-    const bool live = idx < total;
-    uint64_t t = 0, lo = 0, hi = 0, i = 0;
-    uint32_t e = 0;
-    if (live) {
-      t = a.redo_list ? a.redo_list[idx] : idx;
-      lo = min(a.base + t * a.seg, a.limit);  // multiple of 64 (or limit)
-      hi = min(lo + a.seg, a.limit);          // multiple of 64 (or limit == n)
-      i = hi;
-      if (a.redo_list) {
-        e = fast_entry(tbase, a.fin[t + 1]);
-      } else {
-        i = min(hi + a.warm, a.n);
-        e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, i));
-        // ragged top of the warm-up (only next to the end of the haystack)
-        while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
-      }
-      if (i == hi) {
-        a.guess[t] = (uint16_t)((e - tbase) >> 10);
-        if (i & 63) {  // ragged top of the segment itself (last segment only)
-          uint64_t word = 0;
-          while (i > lo && (i & 63)) {
-            i--;
-            e = fast_step(e, a.text[i]);
-            if (e >= thr) word |= 1ull << (i & 63);
-          }
-          a.bitmap[i >> 6] = word;
-        }
-      }
-    }
-    // bytes [lo, i) remain, i a multiple of 64: whole groups through the ring
-    const uint32_t my_groups = live ? (uint32_t)((i - lo) >> 6) : 0;
-    uint32_t max_groups = my_groups;
-    for (int o = 16; o; o >>= 1) max_groups = max(max_groups, __shfl_xor_sync(0xffffffffu, max_groups, o));
-    const uint8_t* top = a.text + i;  // group k covers [top - 64(k+1), top - 64k)
-    auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
-      const uint32_t u = uses + k;
-      const uint32_t bar = bar0 + (u & 1) * 8;
-      if (k < my_groups) {
-        mbar_arrive_tx(bar, 64);
-        bulk_g2s(my_slot + (u & 1) * kRingStageBytes, top - 64ull * (k + 1), 64, bar);
-      } else {
-        mbar_arrive_tx(bar, 0);
-      }
-    };
-    if (max_groups > 0) issue(0);
-    if (max_groups > 1) issue(1);
-    for (uint32_t k = 0; k < max_groups; k++) {
-      const uint32_t u = uses + k;
-      const uint32_t slot = my_slot + (u & 1) * kRingStageBytes;
-      mbar_wait(bar0 + (u & 1) * 8, (u >> 1) & 1);
-      uint4 c0, c1, c2, c3;
-      if (k < my_groups) { c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48); }
-      if (k < my_groups) {
-        const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
-        if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
-        const uint32_t th = g < hi ? thr : 0xFFFFFFFFu;
-        uint32_t bhi = 0, blo = 0;
-        rev_block16<16>(c3, e, bhi, th);
-        rev_block16<0>(c2, e, bhi, th);
-        rev_block16<16>(c1, e, blo, th);
-        rev_block16<0>(c0, e, blo, th);
-        if (g < hi) a.bitmap[g >> 6] = ((uint64_t)bhi << 32) | blo;
-      }
-      // the slot's bytes have been consumed: refill it for the group after next
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (k + 2 < max_groups) issue(k + 2);
-    }
-    uses += max_groups;
-    if (live) {
-      const uint32_t s_lo = (e - tbase) >> 10;
-      a.fin[t] = (uint16_t)s_lo;
-      if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
-    }
-  }
-}
-
 // ------------------------------------------------------------ scan_fwd_reduce --
 // Mirror image for forward all-match scans.  Position q is a match END iff the
 // automaton, standing at q, reports a match when it consumes text[q] (EOF at n).
@@ -428,6 +321,14 @@ struct FastRunner {
   }
 };
 
+// Fixed-length patterns (min == max match length, e.g. the regex-dna variants or
+// `Holmes|Watson`): a candidate start s is known to begin a match, and every match has
+// the same length, so the leftmost-first end is s + L without touching the haystack.
+struct FixedLenRunner {
+  uint64_t len;
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs&, uint64_t s) const { return s + len; }
+};
+
 // Chain state of the find_iter iterator (re_trait.rs:174-179).
 struct Chain {
   uint64_t p, lm;  // next search position, end of the previous match (kNone = none)
@@ -450,9 +351,11 @@ __device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t
 // run the anchored automaton, advance the iterator -- so that the lanes of a warp
 // stay in the same phase (the nested per-word version ran at 5.7 of 32 lanes active).
 // Spans are written to dst[w_at + i] while w_at + i < limit.  Returns the match count.
+// nz: bit j set iff bitmap word j of the chunk may be non-zero (all ones when unknown);
+// lets the fused scan kernel skip the words it already knows to be empty.
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
-                                               uint64_t* dst, uint64_t w_at, uint64_t limit) {
+                                               uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz = ~0ull) {
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
   const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
@@ -469,7 +372,14 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
       uint64_t bit = max(c.p, cb + 1) - 1;
       uint64_t m = 0;
       while (bit < ce) {
-        const uint64_t wi = bit >> 6;
+        uint64_t wi = bit >> 6;
+        const uint64_t rel = wi - (cb >> 6);  // word index inside the chunk
+        if (rel < 64) {                       // skip words known to be empty
+          const uint64_t ahead = nz >> rel;
+          if (ahead == 0) { bit = ce; break; }
+          const uint64_t skip = (uint64_t)(__ffsll((long long)ahead) - 1);
+          if (skip) { wi += skip; bit = wi << 6; if (bit >= ce) break; }
+        }
         if (wi != cached_w) { word = a.bitmap[wi]; cached_w = wi; }
         m = word & (~0ull << (bit & 63));
         if (m) break;
@@ -504,11 +414,20 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
   return total;
 }
 
-// Runner set-up shared by the walk kernels.
-template <bool FAST>
+// Runner set-up shared by the walk kernels: 0 = generic, 1 = fast table, 2 = fixed length.
+template <int FAST>
 struct RunnerSetup;
 template <>
-struct RunnerSetup<false> {
+struct RunnerSetup<2> {
+  using type = FixedLenRunner;
+  static __device__ __forceinline__ type make(const WalkArgs& a) {
+    FixedLenRunner r;
+    r.len = a.fixed_len;
+    return r;
+  }
+};
+template <>
+struct RunnerSetup<0> {
   using type = GenericRunner;
   static __device__ __forceinline__ type make(const WalkArgs& a) {
     GenericRunner r;
@@ -517,7 +436,7 @@ struct RunnerSetup<false> {
   }
 };
 template <>
-struct RunnerSetup<true> {
+struct RunnerSetup<1> {
   using type = FastRunner;
   static __device__ __forceinline__ type make(const WalkArgs& a) {
     FastRunner r;
@@ -541,7 +460,7 @@ struct RunnerSetup<true> {
 // One thread per chunk: walk the chain speculatively (or from a given entry state),
 // staging up to stage_cap spans per chunk.  With a dirty list (after stitch_check)
 // only the listed chunks are walked again, densely packed into warps.
-template <bool FAST>
+template <int FAST>
 __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
   const auto R = RunnerSetup<FAST>::make(a);
   const uint64_t work = a.dirty_list ? (uint64_t)*a.n_dirty : a.n_chunks;
@@ -561,12 +480,13 @@ __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
     a.first_cand[k] = fc;
   }
 }
-template __global__ void walk_chunks<false>(WalkArgs);
-template __global__ void walk_chunks<true>(WalkArgs);
+template __global__ void walk_chunks<0>(WalkArgs);
+template __global__ void walk_chunks<1>(WalkArgs);
+template __global__ void walk_chunks<2>(WalkArgs);
 
 // Staged spans -> final array at the prefix-summed offsets.  Chunks that overflowed
 // their staging slots are walked again, writing straight to the output.
-template <bool FAST>
+template <int FAST>
 __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
   const auto R = RunnerSetup<FAST>::make(a);
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
@@ -588,8 +508,161 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
     }
   }
 }
-template __global__ void compact_spans<false>(WalkArgs);
-template __global__ void compact_spans<true>(WalkArgs);
+template __global__ void compact_spans<0>(WalkArgs);
+template __global__ void compact_spans<1>(WalkArgs);
+template __global__ void compact_spans<2>(WalkArgs);
+
+// FUSED: each lane also walks the find_iter chain over its own segment right after
+// scanning it (chunk == segment), while the segment's haystack bytes are still in L2 and
+// without a second kernel's bitmap round trip.  The walk is speculative exactly like
+// walk_chunks; stitch_check / walk_chunks(dirty) / compact_spans finish the job.
+template <bool FUSED>
+__global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa) {
+  // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
+  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t ring = tbase + (a.dfa.n_states + (FUSED ? wa.fwd.n_states : 0u)) * 1024u + wid * kRingWarpBytes;
+  const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
+  {
+    const uint32_t n_ent = a.dfa.n_states * 256u;
+    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
+      const uint32_t r = i >> 8, b = i & 255u;
+      const uint32_t nx = a.next256[i];
+      const uint32_t addr = tbase + (r << 10) + ((b ^ (r & 31u)) << 2);
+      const uint32_t val = fast_entry(tbase, nx);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
+    }
+    if (FUSED) {
+      const uint32_t fbase = tbase + a.dfa.n_states * 1024u;
+      const uint32_t n_fwd = wa.fwd.n_states * 256u;
+      for (uint32_t i = threadIdx.x; i < n_fwd; i += blockDim.x) {
+        const uint32_t r = i >> 8, b = i & 255u;
+        const uint32_t addr = fbase + (r << 10) + ((b ^ (r & 31u)) << 2);
+        const uint32_t val = fast_entry(fbase, wa.fwd_next256[i]);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
+      }
+    }
+    if (lane == 0) {
+      mbar_init(bar0, 32);
+      mbar_init(bar0 + 8, 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = tbase + a.dfa.match_lo * 1024u;
+  const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
+  const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t rounds = (total + stride - 1) / stride;  // uniform: every warp makes every round
+  uint32_t uses = 0;  // ring uses so far (same for the whole warp): stage = uses & 1, parity = (uses >> 1) & 1
+  for (uint64_t round = 0; round < rounds; round++) {
+    const uint64_t idx = first + round * stride;
+    const bool live = idx < total;
+    uint64_t t = 0, lo = 0, hi = 0, i = 0;
+    uint32_t e = 0;
+    if (live) {
+      t = a.redo_list ? a.redo_list[idx] : idx;
+      lo = min(a.base + t * a.seg, a.limit);  // multiple of 64 (or limit)
+      hi = min(lo + a.seg, a.limit);          // multiple of 64 (or limit == n)
+      i = hi;
+      if (a.redo_list) {
+        e = fast_entry(tbase, a.fin[t + 1]);
+      } else {
+        i = min(hi + a.warm, a.n);
+        e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, i));
+        // ragged top of the warm-up (only next to the end of the haystack)
+        while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
+      }
+      if (i == hi) {
+        a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        if (i & 63) {  // ragged top of the segment itself (last segment only)
+          uint64_t word = 0;
+          while (i > lo && (i & 63)) {
+            i--;
+            e = fast_step(e, a.text[i]);
+            if (e >= thr) word |= 1ull << (i & 63);
+          }
+          a.bitmap[i >> 6] = word;
+        }
+      }
+    }
+    // bytes [lo, i) remain, i a multiple of 64: whole groups through the ring
+    const uint32_t my_groups = live ? (uint32_t)((i - lo) >> 6) : 0;
+    uint32_t max_groups = my_groups;
+    for (int o = 16; o; o >>= 1) max_groups = max(max_groups, __shfl_xor_sync(0xffffffffu, max_groups, o));
+    const uint8_t* top = a.text + i;  // group k covers [top - 64(k+1), top - 64k)
+    auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
+      const uint32_t u = uses + k;
+      const uint32_t bar = bar0 + (u & 1) * 8;
+      if (k < my_groups) {
+        mbar_arrive_tx(bar, 64);
+        bulk_g2s(my_slot + (u & 1) * kRingStageBytes, top - 64ull * (k + 1), 64, bar);
+      } else {
+        mbar_arrive_tx(bar, 0);
+      }
+    };
+    uint64_t nz = 0;  // FUSED: which bitmap words of this segment are non-zero
+    if (max_groups > 0) issue(0);
+    if (max_groups > 1) issue(1);
+    for (uint32_t k = 0; k < max_groups; k++) {
+      const uint32_t u = uses + k;
+      const uint32_t slot = my_slot + (u & 1) * kRingStageBytes;
+      mbar_wait(bar0 + (u & 1) * 8, (u >> 1) & 1);
+      uint4 c0, c1, c2, c3;
+      if (k < my_groups) { c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48); }
+      if (k < my_groups) {
+        const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
+        if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        const uint32_t th = g < hi ? thr : 0xFFFFFFFFu;
+        uint32_t bhi = 0, blo = 0;
+        rev_block16<16>(c3, e, bhi, th);
+        rev_block16<0>(c2, e, bhi, th);
+        rev_block16<16>(c1, e, blo, th);
+        rev_block16<0>(c0, e, blo, th);
+        if (g < hi) {
+          a.bitmap[g >> 6] = ((uint64_t)bhi << 32) | blo;
+          if (FUSED && (bhi | blo)) nz |= 1ull << (((g - lo) >> 6) & 63);
+        }
+      }
+      // the slot's bytes have been consumed: refill it for the group after next
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (k + 2 < max_groups) issue(k + 2);
+    }
+    uses += max_groups;
+    if (live) {
+      const uint32_t s_lo = (e - tbase) >> 10;
+      a.fin[t] = (uint16_t)s_lo;
+      if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
+      if (FUSED) {
+        FastRunner R;
+        R.tbase = tbase + a.dfa.n_states * 1024u;
+        R.thr = R.tbase + wa.fwd.match_lo * 1024u;
+        R.start_e = fast_entry(R.tbase, wa.fwd.start[32]);
+        R.eof = wa.fwd_eof;
+        R.match_lo = wa.fwd.match_lo;
+        Chain c;
+        c.p = wa.in_p[t];
+        c.lm = wa.in_lm[t];
+        c.chain = c.p != kSpec;
+        if (!c.chain) { c.p = wa.base + t * (uint64_t)wa.chunk + 1; c.lm = kNone; }
+        uint64_t fc = kNone, total = 0;
+        // segments longer than 64 words, the ragged last segment and position 0 fall back to "unknown"
+        const bool nz_ok = a.seg <= 4096 && !(hi & 63) && lo != 0;
+        if (c.p != kNone)
+          total = chunk_walk(wa, R, t, c, &fc, wa.stage, t * (uint64_t)wa.stage_cap, (t + 1) * (uint64_t)wa.stage_cap, nz_ok ? nz : ~0ull);
+        wa.out_p[t] = c.p;
+        wa.out_lm[t] = c.lm;
+        wa.count[t] = total;
+        wa.first_cand[t] = fc;
+      }
+    }
+  }
+}
+template __global__ void scan_rev_fast<false>(ScanArgs, WalkArgs);
+template __global__ void scan_rev_fast<true>(ScanArgs, WalkArgs);
+
+
 
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {

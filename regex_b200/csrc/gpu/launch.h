@@ -58,6 +58,7 @@ struct WalkArgs {
   const uint32_t* n_dirty;
   const uint16_t* fwd_next256;  // fast runner: byte-indexed forward anchored table
   const uint16_t* fwd_eof;
+  uint64_t fixed_len;           // fixed-length runner: every match has this many bytes
   uint64_t* out;  // spans: start, end pairs
   uint64_t cap;
   int utf8;
@@ -78,15 +79,16 @@ struct BatchArgs {
 };
 
 __global__ void scan_rev_bitmap(ScanArgs a);
-__global__ void scan_rev_fast(ScanArgs a);
+template <bool FUSED>
+__global__ void scan_rev_fast(ScanArgs a, WalkArgs wa);
 __global__ void scan_fwd_reduce(ScanArgs a);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
                                 uint32_t* redo_list, uint32_t* n_redo);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result);
-template <bool FAST>
+template <int FAST>
 __global__ void walk_chunks(WalkArgs a);
-template <bool FAST>
+template <int FAST>
 __global__ void compact_spans(WalkArgs a);
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
