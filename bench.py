@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seg", type=int, default=0, help="scan segment bytes (0 = automatic)")
     ap.add_argument("--no-fuse", action="store_true")
+    ap.add_argument("--no-tensor-tma", action="store_true")
     ap.add_argument("--also", action="store_true", help="time the other C2 patterns once each (extra keys)")
     return ap.parse_args()
 
@@ -225,6 +226,8 @@ def run_ours(args):
         re_.set_tuning(seg=args.seg)
     if args.no_fuse:
         re_.set_fuse(False)
+    if args.no_tensor_tma:
+        re_.set_tensor_tma(False)
     info = re_.pattern_info()
     # count pass sizes the span buffer
     probe = sharded.GpuShardEngine(re_, text, cap=0)

@@ -119,6 +119,8 @@ void rure_b200_set_stream(rure *re, void *cuda_stream);
 void rure_b200_force_generic(rure *re, int yes);
 /* Walk each segment's find_iter chain inside the fast scan kernel (default on). */
 void rure_b200_set_fuse(rure *re, int yes);
+/* Feed the fast scan kernel with 2-D tiled TMA box loads (default on; off = per-lane bulk copies). */
+void rure_b200_set_tensor_tma(rure *re, int yes);
 /* Dense tables, for tests and tooling.  kind: 0 forward anchored leftmost-first,
  * 1 reverse unanchored all-match, 2 forward unanchored all-match, 3 reverse
  * anchored longest, 4 forward unanchored leftmost-first.

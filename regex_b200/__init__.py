@@ -87,6 +87,7 @@ def _load():
         "rure_b200_force_generic": (None, [vp, c_int]),
         "rure_b200_set_stream": (None, [vp, vp]),
         "rure_b200_set_fuse": (None, [vp, c_int]),
+        "rure_b200_set_tensor_tma": (None, [vp, c_int]),
         "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
         "rure_b200_pattern_info": (None, [vp, POINTER(c_uint64)]),
     }
@@ -316,6 +317,9 @@ class _Compiled:
 
     def set_fuse(self, yes=True):
         _lib.rure_b200_set_fuse(self._h, int(yes))
+
+    def set_tensor_tma(self, yes=True):
+        _lib.rure_b200_set_tensor_tma(self._h, int(yes))
 
     def force_generic(self, yes=True):
         _lib.rure_b200_force_generic(self._h, int(yes))

@@ -329,6 +329,7 @@ void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm,
 void rure_b200_set_stream(rure* re, void* cuda_stream) { re->re->set_stream(cuda_stream); }
 void rure_b200_force_generic(rure* re, int yes) { re->re->tuning.force_generic = yes != 0; }
 void rure_b200_set_fuse(rure* re, int yes) { re->re->tuning.fuse = yes != 0; }
+void rure_b200_set_tensor_tma(rure* re, int yes) { re->re->tuning.tensor_tma = yes != 0; }
 bool rure_b200_dfa_export(rure* re, int kind, uint32_t* info6, uint16_t* trans, uint8_t* classes, uint16_t* start, uint64_t* masks) {
   if (kind < 0 || kind >= rbgpu::kNumDfaKinds) { g_last_error = "bad dfa kind"; return false; }
   rb::Error err;

@@ -10,6 +10,21 @@
 
 namespace rbgpu {
 
+// cuTensorMapEncodeTiled through the runtime (the library links cudart statically, not libcuda).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+
 static std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launches() { return g_launches.load(); }
 
@@ -215,7 +230,7 @@ static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t block
 }
 
 static size_t fast_scan_smem(uint32_t table_states) {
-  return (size_t)table_states * 1024 + 1024 + (1024 / 32) * (2 * 32 * 80 + 16);
+  return (size_t)table_states * 1024 + 1024 + (1024 / 32) * (2 * 32 * 80 + 128);
 }
 
 static uint32_t pick_warm(const Regex& re) {
@@ -287,9 +302,25 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     block = tuning.block;
     RB_CUDA(allow_smem(scan_rev_bitmap, smem));
   }
+  // 2-D view of the haystack for the tiled TMA loads: rows = full segments, cols = bytes
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof tmap);
+  if (fast && tuning.tensor_tma && encode_tiled() && seg >= 64 && seg % 16 == 0 && a.warm <= seg) {
+    const uint64_t rows = (n - base) / seg;  // only rows that lie entirely inside the buffer
+    if (rows >= 34) {
+      cuuint64_t dims[2] = {seg, rows};
+      cuuint64_t strides[1] = {seg};
+      cuuint32_t box[2] = {16, 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)(d_text + base), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) a.tmap_rows = rows;
+    }
+  }
   auto launch = [&](const ScanArgs& args, uint64_t work) {
-    if (fast && fw) scan_rev_fast<true><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw);
-    else if (fast) scan_rev_fast<false><<<grid_for(work, block, 1), block, smem, st>>>(args, no_walk);
+    if (fast && fw) scan_rev_fast<true><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw, tmap);
+    else if (fast) scan_rev_fast<false><<<grid_for(work, block, 1), block, smem, st>>>(args, no_walk, tmap);
     else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
   };
   const bool reuse = io && io->reuse_scan;

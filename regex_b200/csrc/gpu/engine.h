@@ -28,6 +28,7 @@ struct Tuning {
   uint32_t seg = 0;        // bytes per scan segment (multiple of 64); 0 = automatic
   bool force_generic = false;  // tests: use the generic scan kernel even when the fast one applies
   bool fuse = true;            // walk each segment's chain inside the fast scan kernel
+  bool tensor_tma = true;      // feed the fast scan kernel with 2-D tiled TMA loads
   uint32_t chunk = 2048;   // bitmap bits per chain-walk chunk (one thread; multiple of 256)
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;

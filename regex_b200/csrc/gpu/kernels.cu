@@ -1,4 +1,6 @@
 // Kernel definitions; see kernels.cuh for the inventory and engine.cu for launches.
+#include <cuda.h>
+
 #include "kernels.cuh"
 #include "launch.h"
 
@@ -108,7 +110,7 @@ __device__ __forceinline__ uint32_t fast_step(uint32_t e, uint32_t byte) { retur
 // reads its own 64 bytes with four conflict-free LDS.128 (lane stride 80 bytes).
 constexpr uint32_t kRingLaneStride = 80;                       // 64 data + 16 pad
 constexpr uint32_t kRingStageBytes = 32 * kRingLaneStride;     // per warp
-constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes + 16;  // two stages + two mbarriers
+constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes + 128; // two stages + two mbarriers; multiple of 128 (TMA tensor dst alignment)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -125,6 +127,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One 2-D tiled TMA load: a [16 B x 32 rows] box (one 16-byte piece of 32 consecutive
+// segments) lands as 512 contiguous bytes, so lane j finds its piece at +16*j.
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* map, uint32_t col, uint32_t row, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -484,27 +492,41 @@ template __global__ void walk_chunks<0>(WalkArgs);
 template __global__ void walk_chunks<1>(WalkArgs);
 template __global__ void walk_chunks<2>(WalkArgs);
 
-// Staged spans -> final array at the prefix-summed offsets.  Chunks that overflowed
-// their staging slots are walked again, writing straight to the output.
+// Staged spans -> final array at the prefix-summed offsets.  A warp takes 32 consecutive
+// chunks and copies them one after the other with all lanes (coalesced 16-byte spans);
+// a chunk that overflowed its staging slots is walked again by one lane, writing straight
+// to the output.
 template <int FAST>
 __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
   const auto R = RunnerSetup<FAST>::make(a);
-  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
-       k += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t cnt = a.count[k], at = a.offset[k];
-    if (cnt == 0) continue;
-    if (cnt <= a.stage_cap) {
-      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.out);
-      for (uint64_t i = 0; i < cnt && at + i < a.cap; i++) dst[at + i] = src[i];
-    } else {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const ulonglong2* stage = reinterpret_cast<const ulonglong2*>(a.stage);
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.out);
+  for (uint64_t g = warp0; g * 32 < a.n_chunks; g += n_warps) {
+    const uint64_t k = g * 32 + lane;
+    const uint64_t my_cnt = k < a.n_chunks ? a.count[k] : 0;
+    const uint64_t my_at = k < a.n_chunks ? a.offset[k] : 0;
+    if (my_cnt > a.stage_cap) {  // rare: dense chunk, redo it in place
       Chain c;
       c.p = a.in_p[k];
       c.lm = a.in_lm[k];
       c.chain = c.p != kSpec;
       if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
       uint64_t fc;
-      chunk_walk(a, R, k, c, &fc, a.out, at, a.cap);
+      chunk_walk(a, R, k, c, &fc, a.out, my_at, a.cap);
+    }
+    __syncwarp();
+    uint32_t todo = __ballot_sync(0xffffffffu, my_cnt != 0 && my_cnt <= a.stage_cap);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t cnt = __shfl_sync(0xffffffffu, my_cnt, j);
+      const uint64_t at = __shfl_sync(0xffffffffu, my_at, j);
+      const ulonglong2* src = stage + (g * 32 + j) * (uint64_t)a.stage_cap;
+      for (uint64_t i = lane; i < cnt; i += 32)
+        if (at + i < a.cap) dst[at + i] = src[i];
     }
   }
 }
@@ -516,8 +538,13 @@ template __global__ void compact_spans<2>(WalkArgs);
 // scanning it (chunk == segment), while the segment's haystack bytes are still in L2 and
 // without a second kernel's bitmap round trip.  The walk is speculative exactly like
 // walk_chunks; stitch_check / walk_chunks(dirty) / compact_spans finish the job.
+// Haystack bytes reach shared memory by TMA.  When a warp's 32 lanes own 32 consecutive
+// full segments, the haystack is addressed as a 2-D tensor [rows = segments][cols = bytes]
+// and ONE elected lane issues four [16 B x 32 rows] box loads per 64-byte group for the
+// whole warp (per-lane 64-byte bulk copies were TMA-issue bound: a third of all issued
+// instructions were mbarrier polls).  Ragged ends and redo lists use per-lane bulk copies.
 template <bool FUSED>
-__global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa) {
+__global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
   // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
   const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -592,10 +619,28 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     uint32_t max_groups = my_groups;
     for (int o = 16; o; o >>= 1) max_groups = max(max_groups, __shfl_xor_sync(0xffffffffu, max_groups, o));
     const uint8_t* top = a.text + i;  // group k covers [top - 64(k+1), top - 64k)
+    // 2-D path: whole warp live, no redo list, identical geometry in every lane
+    // (full segments, full warm-up), and all rows (incl. the warm-up row) inside the map.
+    const uint64_t t0 = __shfl_sync(0xffffffffu, t, 0);
+    const bool uniform = live && !a.redo_list && hi - lo == a.seg && i == hi + a.warm && t == t0 + lane;
+    const bool boxed = a.tmap_rows != 0 && __all_sync(0xffffffffu, uniform) && t0 + 33 <= a.tmap_rows && a.warm <= a.seg;
     auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
       const uint32_t u = uses + k;
       const uint32_t bar = bar0 + (u & 1) * 8;
-      if (k < my_groups) {
+      if (boxed) {
+        if (lane == 0) {
+          mbar_arrive_tx(bar, 2048);
+          // byte offset of the group inside row-space: segment bytes then the neighbour row's warm-up bytes
+          const uint32_t o = a.seg + a.warm - 64u * (k + 1);
+          const uint32_t row = (uint32_t)t0 + (o >= a.seg ? 1u : 0u);
+          const uint32_t col = o >= a.seg ? o - a.seg : o;
+          const uint32_t dst = ring + (u & 1) * kRingStageBytes;
+#pragma unroll
+          for (uint32_t sub = 0; sub < 4; sub++) tma_box(dst + sub * 512u, &tmap, col + sub * 16u, row, bar);
+        } else {
+          mbar_arrive_tx(bar, 0);
+        }
+      } else if (k < my_groups) {
         mbar_arrive_tx(bar, 64);
         bulk_g2s(my_slot + (u & 1) * kRingStageBytes, top - 64ull * (k + 1), 64, bar);
       } else {
@@ -610,7 +655,12 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       const uint32_t slot = my_slot + (u & 1) * kRingStageBytes;
       mbar_wait(bar0 + (u & 1) * 8, (u >> 1) & 1);
       uint4 c0, c1, c2, c3;
-      if (k < my_groups) { c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48); }
+      if (boxed) {
+        const uint32_t b = ring + (u & 1) * kRingStageBytes + lane * 16u;
+        c0 = lds128(b); c1 = lds128(b + 512); c2 = lds128(b + 1024); c3 = lds128(b + 1536);
+      } else if (k < my_groups) {
+        c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48);
+      }
       if (k < my_groups) {
         const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
         if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
@@ -659,8 +709,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     }
   }
 }
-template __global__ void scan_rev_fast<false>(ScanArgs, WalkArgs);
-template __global__ void scan_rev_fast<true>(ScanArgs, WalkArgs);
+template __global__ void scan_rev_fast<false>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
+template __global__ void scan_rev_fast<true>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
 
 
 

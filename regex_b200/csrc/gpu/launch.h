@@ -1,6 +1,7 @@
 // Kernel argument blocks + declarations shared by kernels.cu and engine.cu.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 
 #include "kernels.cuh"
 
@@ -22,6 +23,7 @@ struct ScanArgs {
   uint8_t* flag0;    // reverse scan: a match starts at position 0
   const uint16_t* next256;  // fast kernels: [n_states][256] byte-indexed successor ids
   const uint16_t* eof;      // fast kernels: [n_states] EOF successor ids
+  uint64_t tmap_rows;       // fast kernels: rows (full segments) covered by the 2-D tensor map, 0 = none
   uint64_t* seg_first;  // forward scan: first match end per segment
   uint64_t* seg_mask;   // forward scan: OR of masks per segment (nullable)
   uint16_t* guess;
@@ -80,7 +82,7 @@ struct BatchArgs {
 
 __global__ void scan_rev_bitmap(ScanArgs a);
 template <bool FUSED>
-__global__ void scan_rev_fast(ScanArgs a, WalkArgs wa);
+__global__ void scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap);
 __global__ void scan_fwd_reduce(ScanArgs a);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
                                 uint32_t* redo_list, uint32_t* n_redo);
