@@ -293,9 +293,11 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   WalkArgs no_walk{};
   if (fast) {
     block = 1024;
-    smem = fast_scan_smem(rev->view.n_states + (fw ? fw->fwd.n_states : 0));
-    if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool fw_fixed = fw && fw->fixed_len != 0;
+    smem = fast_scan_smem(rev->view.n_states + (fw && !fw_fixed ? fw->fwd.n_states : 0));
+    if (fw_fixed) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   } else {
     smem = smem_for(rev->view);
     a.use_smem = smem != 0;
@@ -319,8 +321,9 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     }
   }
   auto launch = [&](const ScanArgs& args, uint64_t work) {
-    if (fast && fw) scan_rev_fast<true><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw, tmap);
-    else if (fast) scan_rev_fast<false><<<grid_for(work, block, 1), block, smem, st>>>(args, no_walk, tmap);
+    if (fast && fw && fw->fixed_len) scan_rev_fast<2><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw, tmap);
+    else if (fast && fw) scan_rev_fast<1><<<grid_for(work, block, 1), block, smem, st>>>(args, *fw, tmap);
+    else if (fast) scan_rev_fast<0><<<grid_for(work, block, 1), block, smem, st>>>(args, no_walk, tmap);
     else scan_rev_bitmap<<<grid_for(work, block, tuning.blocks_per_sm), block, smem, st>>>(args);
   };
   const bool reuse = io && io->reuse_scan;
@@ -414,8 +417,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   const bool wfast = !wfixed && fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
   // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
-  const bool fused = plan.fast && wkind == 1 && tuning.fuse && !io->reuse_scan &&
-                     fast_scan_smem(revall->view.n_states + fwd->view.n_states) <= 227 * 1024;
+  const bool fused = plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
+                     fast_scan_smem(revall->view.n_states + (wkind == 1 ? fwd->view.n_states : 0)) <= 227 * 1024;
 
   WalkArgs w{};
   w.fwd = fwd->view;

@@ -369,6 +369,17 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
   uint64_t total = 0;
   uint64_t fc = kNone;
   uint64_t cached_w = kNone, word = 0;
+  uint64_t pf_w = kNone, pf_word = 0;  // next candidate word, load issued ahead of use
+  const uint64_t w0 = cb >> 6, w_end = (ce + 63) >> 6;
+  // first word at or after `wi` that may be non-zero (w_end if none)
+  auto next_word = [&](uint64_t wi) -> uint64_t {
+    if (wi >= w_end) return w_end;
+    const uint64_t rel = wi - w0;
+    if (rel >= 64) return wi;
+    const uint64_t ahead = nz >> rel;
+    if (ahead == 0) return rel + 64 >= w_end - w0 ? w_end : w0 + 64;
+    return wi + (uint64_t)(__ffsll((long long)ahead) - 1);
+  };
   bool at_zero = c.p == 0 && cb == 0 && *a.flag0;  // position 0 has no bitmap bit
   while (c.p != kNone) {
     uint64_t s;
@@ -381,21 +392,20 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
       uint64_t m = 0;
       while (bit < ce) {
         uint64_t wi = bit >> 6;
-        const uint64_t rel = wi - (cb >> 6);  // word index inside the chunk
-        if (rel < 64) {                       // skip words known to be empty
-          const uint64_t ahead = nz >> rel;
-          if (ahead == 0) { bit = ce; break; }
-          const uint64_t skip = (uint64_t)(__ffsll((long long)ahead) - 1);
-          if (skip) { wi += skip; bit = wi << 6; if (bit >= ce) break; }
+        const uint64_t nw = next_word(wi);
+        if (nw != wi) { wi = nw; bit = wi << 6; if (bit >= ce) break; }
+        if (wi != cached_w) {
+          word = wi == pf_w ? pf_word : a.bitmap[wi];
+          cached_w = wi;
+          pf_w = next_word(wi + 1);  // start fetching the following candidate word now
+          if (pf_w < w_end) pf_word = a.bitmap[pf_w];
         }
-        if (wi != cached_w) { word = a.bitmap[wi]; cached_w = wi; }
         m = word & (~0ull << (bit & 63));
         if (m) break;
         bit = (wi + 1) << 6;
       }
       if (bit >= ce) break;
       s = (bit & ~63ull) + (uint64_t)__ffsll((long long)m);
-      if (s > ce) break;  // candidate beyond the chunk (bits above ce are zero by construction)
     }
     if (fc == kNone) fc = s;
     const uint64_t e = T.end_from(a, s);
@@ -543,12 +553,12 @@ template __global__ void compact_spans<2>(WalkArgs);
 // and ONE elected lane issues four [16 B x 32 rows] box loads per 64-byte group for the
 // whole warp (per-lane 64-byte bulk copies were TMA-issue bound: a third of all issued
 // instructions were mbarrier polls).  Ragged ends and redo lists use per-lane bulk copies.
-template <bool FUSED>
+template <int FUSED>
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
   // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
   const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t ring = tbase + (a.dfa.n_states + (FUSED ? wa.fwd.n_states : 0u)) * 1024u + wid * kRingWarpBytes;
+  const uint32_t ring = tbase + (a.dfa.n_states + (FUSED == 1 ? wa.fwd.n_states : 0u)) * 1024u + wid * kRingWarpBytes;
   const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
   {
     const uint32_t n_ent = a.dfa.n_states * 256u;
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       const uint32_t val = fast_entry(tbase, nx);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
     }
-    if (FUSED) {
+    if (FUSED == 1) {
       const uint32_t fbase = tbase + a.dfa.n_states * 1024u;
       const uint32_t n_fwd = wa.fwd.n_states * 256u;
       for (uint32_t i = threadIdx.x; i < n_fwd; i += blockDim.x) {
@@ -685,12 +695,16 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       a.fin[t] = (uint16_t)s_lo;
       if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
       if (FUSED) {
-        FastRunner R;
-        R.tbase = tbase + a.dfa.n_states * 1024u;
-        R.thr = R.tbase + wa.fwd.match_lo * 1024u;
-        R.start_e = fast_entry(R.tbase, wa.fwd.start[32]);
-        R.eof = wa.fwd_eof;
-        R.match_lo = wa.fwd.match_lo;
+        typename RunnerSetup<FUSED == 2 ? 2 : 1>::type R;
+        if constexpr (FUSED == 2) {
+          R.len = wa.fixed_len;
+        } else {
+          R.tbase = tbase + a.dfa.n_states * 1024u;
+          R.thr = R.tbase + wa.fwd.match_lo * 1024u;
+          R.start_e = fast_entry(R.tbase, wa.fwd.start[32]);
+          R.eof = wa.fwd_eof;
+          R.match_lo = wa.fwd.match_lo;
+        }
         Chain c;
         c.p = wa.in_p[t];
         c.lm = wa.in_lm[t];
@@ -709,8 +723,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     }
   }
 }
-template __global__ void scan_rev_fast<false>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
-template __global__ void scan_rev_fast<true>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
+template __global__ void scan_rev_fast<0>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
+template __global__ void scan_rev_fast<1>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
+template __global__ void scan_rev_fast<2>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
 
 
 

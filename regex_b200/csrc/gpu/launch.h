@@ -81,7 +81,7 @@ struct BatchArgs {
 };
 
 __global__ void scan_rev_bitmap(ScanArgs a);
-template <bool FUSED>
+template <int FUSED>
 __global__ void scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap);
 __global__ void scan_fwd_reduce(ScanArgs a);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
