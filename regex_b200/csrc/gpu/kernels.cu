@@ -307,12 +307,40 @@ struct FastRunner {
     for (uint64_t q = s;; q += 16) {
       const uint64_t al = q & ~7ull;
       const uint64_t* wp = reinterpret_cast<const uint64_t*>(a.text + al);
-      const uint64_t w0 = al < a.n ? __ldg(wp) : 0, w1 = al + 8 < a.n ? __ldg(wp + 1) : 0, w2 = al + 16 < a.n ? __ldg(wp + 2) : 0;
       const uint32_t sh = (uint32_t)(q & 7) * 8;
+      if (al + 24 <= a.n) {
+        // common case: the whole 16-byte window lies inside the haystack -- 32-bit
+        // bookkeeping only (offset of the last match state inside the window)
+        const uint64_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        const uint32_t x0 = __funnelshift_r((uint32_t)w0, (uint32_t)(w0 >> 32), sh);
+        const uint32_t x1 = __funnelshift_r((uint32_t)(w0 >> 32), (uint32_t)w1, sh);
+        const uint32_t x2 = __funnelshift_r((uint32_t)w1, (uint32_t)(w1 >> 32), sh);
+        const uint32_t x3 = __funnelshift_r((uint32_t)(w1 >> 32), (uint32_t)w2, sh);
+        const uint32_t x4 = __funnelshift_r((uint32_t)w2, (uint32_t)(w2 >> 32), sh);
+        // sh in {0,8,..,56}: for sh >= 32 the window starts one word later
+        const bool up = sh >= 32;
+        const uint32_t v[4] = {up ? x1 : x0, up ? x2 : x1, up ? x3 : x2, up ? x4 : x3};
+        uint32_t lj = ~0u;
+        bool died = false;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t idx = j == 0 ? (v[g] << 2) : (v[g] >> (8 * j - 2));
+            e = lds32((idx & 0x3FCu) ^ e);
+            if (e >= thr) lj = 4 * g + j;
+          }
+          if (e == dead) { died = true; break; }
+        }
+        if (lj != ~0u) last = q + lj;
+        if (died) return last;
+        continue;
+      }
+      const uint64_t w0 = al < a.n ? __ldg(wp) : 0, w1 = al + 8 < a.n ? __ldg(wp + 1) : 0, w2 = al + 16 < a.n ? __ldg(wp + 2) : 0;
       const uint64_t lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
       const uint64_t hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
       const uint64_t avail = a.n - q;  // bytes before EOF (q <= n)
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 16; j++) {
         if ((uint64_t)j >= avail) {  // EOF step (dfa.rs:748-763)
           if (a.text_continues) { *a.err_flag = 1; return last; }
@@ -323,7 +351,7 @@ struct FastRunner {
         const uint32_t byte = (uint32_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))) & 0xFF);
         e = fast_step(e, byte);
         if (e >= thr) last = q + j;
-        if ((j & 3) == 3 && e == dead) return last;
+        if (e == dead) return last;
       }
     }
   }
@@ -354,6 +382,10 @@ __device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t
   return tp <= first_cand && tp <= region_next;
 }
 
+template <typename Runner>
+__device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz);
+
 // The chain over one chunk (bits [cb, ce) <-> positions [cb+1, ce], plus position 0
 // for the chunk that starts the haystack).  One flat loop -- find the next candidate,
 // run the anchored automaton, advance the iterator -- so that the lanes of a warp
@@ -364,6 +396,8 @@ __device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
                                                uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz = ~0ull) {
+  if (!a.emulate_slice && !a.can_match_empty && a.chunk <= 4096)
+    return chunk_walk_simple(a, T, k, c, first_cand, dst, w_at, limit, nz);
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
   const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
@@ -427,6 +461,79 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
     c.lm = e;
     if (w_at + total < limit) { dst[2 * (w_at + total)] = ms; dst[2 * (w_at + total) + 1] = e; }
     total++;
+  }
+  *first_cand = fc;
+  return total;
+}
+
+// chunk_walk for the common pattern class -- no empty matches, no slice emulation --
+// where every candidate yields a span and the iterator simply continues at the match
+// end.  Same contract as chunk_walk; bit positions are kept relative to the chunk in
+// 32 bits and the chunk's non-zero words are visited through the `nz` mask, which
+// roughly halves the instructions per match.  Requires chunks of at most 64 words.
+template <typename Runner>
+__device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz) {
+  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+  const uint64_t ce = min(cb + a.chunk, a.limit);
+  const uint32_t nbits = (uint32_t)(ce - cb);
+  const uint64_t* bm = a.bitmap + (cb >> 6);  // cb is a multiple of 64
+  uint64_t* o = dst + 2 * w_at;
+  uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
+  uint32_t total = 0;
+  uint64_t fc = kNone;
+  auto emit = [&](uint64_t ms, uint64_t e) {
+    if (total < room) {
+      if (((uintptr_t)o & 15) == 0) *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)total) = make_ulonglong2(ms, e);
+      else { o[2 * (uint64_t)total] = ms; o[2 * (uint64_t)total + 1] = e; }
+    }
+    total++;
+  };
+  if (c.p == kNone) { *first_cand = fc; return 0; }
+  if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
+    fc = 0;
+    const uint64_t e = T.end_from(a, 0);
+    if (e == kNone) { c.p = 1; c.chain = false; }
+    else { emit(0, e); c.p = c.lm = e; c.chain = true; }
+  }
+  // bit r of the chunk <-> position cb + r + 1
+  uint32_t r = c.p > cb + 1 ? (uint32_t)min(c.p - cb - 1, (uint64_t)nbits) : 0u;
+  if (nbits < 64 * 64) nz &= (1ull << ((nbits + 63) >> 6)) - 1;
+  uint64_t rem = r < nbits ? nz & (~0ull << (r >> 6)) : 0;  // words still to visit
+  uint32_t cw = 0;
+  uint64_t cur = 0;
+  for (;;) {
+    if (cur == 0) {
+      if (rem == 0) break;
+      cw = (uint32_t)__ffsll((long long)rem) - 1;
+      rem &= rem - 1;
+      cur = bm[cw];
+      if (cw == (r >> 6)) cur &= ~0ull << (r & 63);
+      continue;
+    }
+    const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
+    const uint64_t s = cb + sr + 1;
+    if (fc == kNone) fc = s;
+    const uint64_t e = T.end_from(a, s);
+    if (e == kNone) {  // unreachable for consistent tables
+      cur &= cur - 1;
+      c.p = s + 1;
+      c.chain = false;
+      continue;
+    }
+    emit(s, e);
+    c.p = c.lm = e;
+    c.chain = true;
+    const uint64_t er = e - 1 - cb;  // next candidate bit >= er
+    if (er >= nbits) break;
+    r = (uint32_t)er;
+    const uint32_t ew = r >> 6;
+    if (ew == cw) {
+      cur &= ~0ull << (r & 63);
+    } else {
+      cur = 0;
+      rem &= ~0ull << ew;
+    }
   }
   *first_cand = fc;
   return total;
