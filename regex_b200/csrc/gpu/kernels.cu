@@ -689,6 +689,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     if (lane == 0) {
       mbar_init(bar0, 32);
       mbar_init(bar0 + 8, 32);
+      mbar_init(bar0 + 16, 1);  // boxed (2-D TMA) mode: one elected lane arrives for the warp
+      mbar_init(bar0 + 24, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -700,6 +702,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
   const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t rounds = (total + stride - 1) / stride;  // uniform: every warp makes every round
   uint32_t uses = 0;  // ring uses so far (same for the whole warp): stage = uses & 1, parity = (uses >> 1) & 1
+  uint32_t uses_b = 0;  // same for the boxed-mode barriers
   for (uint64_t round = 0; round < rounds; round++) {
     const uint64_t idx = first + round * stride;
     const bool live = idx < total;
@@ -741,44 +744,72 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     const uint64_t t0 = __shfl_sync(0xffffffffu, t, 0);
     const bool uniform = live && !a.redo_list && hi - lo == a.seg && i == hi + a.warm && t == t0 + lane;
     const bool boxed = a.tmap_rows != 0 && __all_sync(0xffffffffu, uniform) && t0 + 33 <= a.tmap_rows && a.warm <= a.seg;
+    uint64_t nz = 0;  // FUSED: which bitmap words of this segment are non-zero
+    if (boxed) {
+      // Tight loop for the common geometry: every lane scans one full segment plus the
+      // warm-up, so group counts, the warm-up/record split and the ring slots are warp
+      // uniform and one lane drives the TMA for all 32.
+      const uint32_t n_groups = (a.seg + a.warm) >> 6, n_warm = a.warm >> 6;
+      const uint32_t barb = bar0 + 16;
+      auto issue_box = [&](uint32_t k) {  // lane 0 only
+        const uint32_t u = uses_b + k;
+        const uint32_t bar = barb + (u & 1) * 8;
+        mbar_arrive_tx(bar, 2048);
+        // byte offset of the group inside row-space: segment bytes then the neighbour row's warm-up bytes
+        const uint32_t o = a.seg + a.warm - 64u * (k + 1);
+        const uint32_t row = (uint32_t)t0 + (o >= a.seg ? 1u : 0u);
+        const uint32_t col = o >= a.seg ? o - a.seg : o;
+        const uint32_t dst = ring + (u & 1) * kRingStageBytes;
+#pragma unroll
+        for (uint32_t sub = 0; sub < 4; sub++) tma_box(dst + sub * 512u, &tmap, col + sub * 16u, row, bar);
+      };
+      if (lane == 0) {
+        issue_box(0);
+        if (n_groups > 1) issue_box(1);
+      }
+      uint64_t* bw = a.bitmap + (hi >> 6);  // one past the segment's last bitmap word
+      const uint32_t my_b = ring + lane * 16u;
+      for (uint32_t k = 0; k < n_groups; k++) {
+        const uint32_t u = uses_b + k;
+        mbar_wait(barb + (u & 1) * 8, (u >> 1) & 1);
+        const uint32_t b = my_b + (u & 1) * kRingStageBytes;
+        const uint4 c0 = lds128(b), c1 = lds128(b + 512), c2 = lds128(b + 1024), c3 = lds128(b + 1536);
+        if (k == n_warm) a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        const bool rec = k >= n_warm;
+        const uint32_t th = rec ? thr : 0xFFFFFFFFu;
+        uint32_t bhi = 0, blo = 0;
+        rev_block16<16>(c3, e, bhi, th);
+        rev_block16<0>(c2, e, bhi, th);
+        rev_block16<16>(c1, e, blo, th);
+        rev_block16<0>(c0, e, blo, th);
+        if (rec) {
+          *--bw = ((uint64_t)bhi << 32) | blo;
+          if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
+        }
+        // every lane has its 64 bytes in registers: lane 0 refills the slot for the group after next
+        __syncwarp();
+        if (lane == 0 && k + 2 < n_groups) issue_box(k + 2);
+      }
+      uses_b += n_groups;
+    } else {
     auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
       const uint32_t u = uses + k;
       const uint32_t bar = bar0 + (u & 1) * 8;
-      if (boxed) {
-        if (lane == 0) {
-          mbar_arrive_tx(bar, 2048);
-          // byte offset of the group inside row-space: segment bytes then the neighbour row's warm-up bytes
-          const uint32_t o = a.seg + a.warm - 64u * (k + 1);
-          const uint32_t row = (uint32_t)t0 + (o >= a.seg ? 1u : 0u);
-          const uint32_t col = o >= a.seg ? o - a.seg : o;
-          const uint32_t dst = ring + (u & 1) * kRingStageBytes;
-#pragma unroll
-          for (uint32_t sub = 0; sub < 4; sub++) tma_box(dst + sub * 512u, &tmap, col + sub * 16u, row, bar);
-        } else {
-          mbar_arrive_tx(bar, 0);
-        }
-      } else if (k < my_groups) {
+      if (k < my_groups) {
         mbar_arrive_tx(bar, 64);
         bulk_g2s(my_slot + (u & 1) * kRingStageBytes, top - 64ull * (k + 1), 64, bar);
       } else {
         mbar_arrive_tx(bar, 0);
       }
     };
-    uint64_t nz = 0;  // FUSED: which bitmap words of this segment are non-zero
     if (max_groups > 0) issue(0);
     if (max_groups > 1) issue(1);
     for (uint32_t k = 0; k < max_groups; k++) {
       const uint32_t u = uses + k;
       const uint32_t slot = my_slot + (u & 1) * kRingStageBytes;
       mbar_wait(bar0 + (u & 1) * 8, (u >> 1) & 1);
-      uint4 c0, c1, c2, c3;
-      if (boxed) {
-        const uint32_t b = ring + (u & 1) * kRingStageBytes + lane * 16u;
-        c0 = lds128(b); c1 = lds128(b + 512); c2 = lds128(b + 1024); c3 = lds128(b + 1536);
-      } else if (k < my_groups) {
-        c0 = lds128(slot); c1 = lds128(slot + 16); c2 = lds128(slot + 32); c3 = lds128(slot + 48);
-      }
       if (k < my_groups) {
+        const uint4 c0 = lds128(slot), c1 = lds128(slot + 16), c2 = lds128(slot + 32), c3 = lds128(slot + 48);
         const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
         if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
         const uint32_t th = g < hi ? thr : 0xFFFFFFFFu;
@@ -797,6 +828,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       if (k + 2 < max_groups) issue(k + 2);
     }
     uses += max_groups;
+    }
     if (live) {
       const uint32_t s_lo = (e - tbase) >> 10;
       a.fin[t] = (uint16_t)s_lo;
