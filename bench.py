@@ -30,6 +30,8 @@ PATTERN = r"[a-zA-Z]+ing"
 ALSO = [r"Holmes|Watson", r"Sherlock|Holmes", r"Sher[a-z]+|Hol[a-z]+", r"(?i)Sherlock|Holmes|Watson", r"the\s+\w+"]
 SEED = 0x5EED0001
 GIB = 1 << 30
+# ncu --set full, scan_rev_fast<1> on 1 GiB of this corpus: 1.834 GB read + 0.301 GB written (profiles/r01_ncu_fused_scan.md)
+TRAFFIC_PER_BYTE = (1.834245e9 + 0.3012736e9) / (1 << 30)
 
 
 def parse_args():
@@ -278,7 +280,12 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         scan = sum(scan_ms) / len(scan_ms)
-        alg_bytes = n + n / 8  # scan kernel: haystack read + start bitmap written (spans belong to the walk)
+        fused = bool(st["fused"])
+        # 1 byte read per haystack byte + 16 bytes written per emitted span; the start
+        # bitmap, staging and stitch traffic are this design's overhead and earn no credit.  The fused
+        # kernel (reverse scan + chain walk of each segment) emits the spans; without fusion the
+        # dominant kernel is the scan alone and the spans belong to walk_chunks.
+        alg_bytes = n + (16 * n_local if fused else 0)
         achieved = alg_bytes / (scan / 1e3) / 1e9
         result = {
             "metric": "haystack GB/s scanned (find_iter, bit-exact spans)", "value": round(value, 2), "unit": "GB/s",
@@ -293,7 +300,9 @@ def run_ours(args):
                        "boundary_fixup_rounds": rounds},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "scan_rev_fast", "peak_source": peak_src,
+                         "traffic": TRAFFIC_PER_BYTE * n if fused and args.pattern == PATTERN else None,
+                         "traffic_source": "ncu --set full dram__bytes_read+write of scan_rev_fast<1> on a 1 GiB haystack (profiles/r01_ncu_fused_scan.md), scaled per byte",
+                         "kernel": "scan_rev_fast<fused scan+walk>" if fused else "scan_rev_fast<scan only>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(scan, 4),
                          "other_kernels_ms": round(sum(walk_ms) / len(walk_ms), 4)},
             "clocks": clk.summary(),

@@ -105,9 +105,10 @@ const char *rure_b200_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */
 uint64_t rure_b200_kernel_launches(void);
 /* Timing (CUDA events on the library's stream) and fix-up counters of the last
- * rure_b200_find_all* call on this object.  out[0..6] = scan_ms, walk_ms,
- * total_ms, scan_redo_rounds, scan_redo_segments, stitch_rounds, stitch_dirty_chunks */
-void rure_b200_last_stats(rure *re, double *out7);
+ * rure_b200_find_all* call on this object.  out[0..7] = scan_ms, walk_ms,
+ * total_ms, scan_redo_rounds, scan_redo_segments, stitch_rounds, stitch_dirty_chunks,
+ * fused (1 when the scan kernel also walked the chains, so scan_ms covers both) */
+void rure_b200_last_stats(rure *re, double *out8);
 /* seg/chunk are positions per scan segment / walk chunk (multiples of 64);
  * warm = warm-up bytes (0 = automatic); 0 keeps the current value elsewhere. */
 void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block,

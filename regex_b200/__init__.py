@@ -303,9 +303,9 @@ class _Compiled:
 
     # ---- diagnostics ------------------------------------------------------------
     def last_stats(self):
-        out = (c_double * 7)()
+        out = (c_double * 8)()
         _lib.rure_b200_last_stats(self._h, out)
-        keys = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks"]
+        keys = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks", "fused"]
         return dict(zip(keys, list(out)))
 
     def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):

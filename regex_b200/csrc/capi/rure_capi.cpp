@@ -312,7 +312,9 @@ bool rure_b200_find_all_shard_device(rure* re, const uint8_t* d_buffer, size_t n
 
 const char* rure_b200_last_error(void) { return g_last_error.c_str(); }
 uint64_t rure_b200_kernel_launches(void) { return rbgpu::kernel_launches(); }
-void rure_b200_last_stats(rure* re, double* out7) {
+void rure_b200_last_stats(rure* re, double* out8) {
+  double* out7 = out8;
+  out8[7] = re->re->stats.fused ? 1.0 : 0.0;
   const rbgpu::Stats& s = re->re->stats;
   out7[0] = s.scan_ms; out7[1] = s.walk_ms; out7[2] = s.total_ms;
   out7[3] = (double)s.scan_redo_rounds; out7[4] = (double)s.scan_redo_segments;

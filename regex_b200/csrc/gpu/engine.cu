@@ -529,6 +529,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   io->exit_p = h[1];
   io->exit_lm = h[2];
   io->halo_overflow = *(uint32_t*)(h + 3) != 0;
+  stats.fused = fused;
   cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
   cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
   cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);

@@ -39,6 +39,7 @@ struct Stats {  // filled by the last single-haystack call (diagnostics, bench r
   uint64_t scan_redo_rounds = 0, scan_redo_segments = 0;
   uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0;
   float scan_ms = 0, walk_ms = 0, total_ms = 0;
+  bool fused = false;  // the scan kernel also walked the chains (scan_ms covers both)
 };
 
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
