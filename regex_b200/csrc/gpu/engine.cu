@@ -58,9 +58,17 @@ struct Regex::DeviceDfa {
   void* trans = nullptr;
   void* classes = nullptr;
   void* masks = nullptr;
-  void* next256 = nullptr;  // byte-indexed expansion for the fast kernels (<= kFastStates states)
+  // byte-indexed expansion over the hot states for the fast kernels (kernels.cuh HotView);
+  // hot.n == 0 when even the ASCII-reachable part has more than kFastStates states
+  void* next256 = nullptr;
   void* eof = nullptr;
-  ~DeviceDfa() { cudaFree(trans); cudaFree(classes); cudaFree(masks); cudaFree(next256); cudaFree(eof); }
+  void* hot2full = nullptr;
+  void* full2hot = nullptr;
+  HotView hot{};
+  ~DeviceDfa() {
+    cudaFree(trans); cudaFree(classes); cudaFree(masks); cudaFree(next256); cudaFree(eof);
+    cudaFree(hot2full); cudaFree(full2hot);
+  }
 };
 
 // ------------------------------------------------------------------ compile --
@@ -197,16 +205,62 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
   v.table_bytes = (uint32_t)tb;
   std::memcpy(v.start, h->start, sizeof v.start);
   v.uniform_start = h->uniform_start;
-  if (h->n_states <= kFastStates) {
-    std::vector<uint16_t> n256((size_t)h->n_states * 256), eof(h->n_states);
-    for (uint32_t r = 0; r < h->n_states; r++) {
-      for (int b = 0; b < 256; b++) n256[(size_t)r * 256 + b] = h->next((uint16_t)r, (uint8_t)b);
-      eof[r] = h->next_eof((uint16_t)r);
+  // Hot set: every state when they all fit, else the closure of the start states under
+  // ASCII bytes (what an ASCII haystack can reach).  Row 1 is the trap.
+  {
+    std::vector<uint8_t> is_hot(h->n_states, 0);
+    if (h->n_states + 1 <= kFastStates) {
+      std::fill(is_hot.begin(), is_hot.end(), 1);
+    } else {
+      std::vector<uint16_t> stack;
+      auto push = [&](uint16_t s) { if (!is_hot[s]) { is_hot[s] = 1; stack.push_back(s); } };
+      push(0);
+      for (uint16_t s : h->start) push(s);
+      while (!stack.empty()) {
+        const uint16_t s = stack.back();
+        stack.pop_back();
+        for (int b = 0; b < 128; b++) push(h->next(s, (uint8_t)b));
+      }
     }
-    RB_CUDA(cudaMalloc(&d->next256, n256.size() * 2));
-    RB_CUDA(cudaMalloc(&d->eof, eof.size() * 2));
-    RB_CUDA(cudaMemcpy(d->next256, n256.data(), n256.size() * 2, cudaMemcpyHostToDevice));
-    RB_CUDA(cudaMemcpy(d->eof, eof.data(), eof.size() * 2, cudaMemcpyHostToDevice));
+    const size_t n_hot = (size_t)std::count(is_hot.begin(), is_hot.end(), 1) + 1;
+    if (n_hot <= kFastStates) {
+      std::vector<uint16_t> full2hot(h->n_states, 0xFFFF), hot2full;
+      hot2full.push_back(0);       // dead
+      hot2full.push_back(0xFFFF);  // trap
+      full2hot[0] = 0;
+      for (uint32_t s = 1; s < h->n_states; s++)  // full ids are already ordered non-match < match
+        if (is_hot[s]) { full2hot[s] = (uint16_t)hot2full.size(); hot2full.push_back((uint16_t)s); }
+      uint32_t hot_match_lo = (uint32_t)hot2full.size();
+      for (uint32_t i = 2; i < hot2full.size(); i++)
+        if (hot2full[i] >= h->match_lo) { hot_match_lo = i; break; }
+      std::vector<uint16_t> n256(hot2full.size() * 256), eof(hot2full.size(), 0);
+      for (uint32_t r = 0; r < hot2full.size(); r++) {
+        for (int b = 0; b < 256; b++) {
+          uint16_t to = 1;  // trap row: absorbing
+          if (r != 1) {
+            const uint16_t t = full2hot[h->next(hot2full[r], (uint8_t)b)];
+            to = t == 0xFFFF ? 1 : t;
+          }
+          n256[(size_t)r * 256 + b] = to;
+        }
+        if (r != 1) eof[r] = h->next_eof(hot2full[r]);
+      }
+      RB_CUDA(cudaMalloc(&d->next256, n256.size() * 2));
+      RB_CUDA(cudaMalloc(&d->eof, eof.size() * 2));
+      RB_CUDA(cudaMalloc(&d->hot2full, hot2full.size() * 2));
+      RB_CUDA(cudaMalloc(&d->full2hot, full2hot.size() * 2));
+      RB_CUDA(cudaMemcpy(d->next256, n256.data(), n256.size() * 2, cudaMemcpyHostToDevice));
+      RB_CUDA(cudaMemcpy(d->eof, eof.data(), eof.size() * 2, cudaMemcpyHostToDevice));
+      RB_CUDA(cudaMemcpy(d->hot2full, hot2full.data(), hot2full.size() * 2, cudaMemcpyHostToDevice));
+      RB_CUDA(cudaMemcpy(d->full2hot, full2hot.data(), full2hot.size() * 2, cudaMemcpyHostToDevice));
+      d->hot.next256 = (const uint16_t*)d->next256;
+      d->hot.eof = (const uint16_t*)d->eof;
+      d->hot.hot2full = (const uint16_t*)d->hot2full;
+      d->hot.full2hot = (const uint16_t*)d->full2hot;
+      d->hot.n = (uint32_t)hot2full.size();
+      d->hot.match_lo = hot_match_lo;
+      d->hot.start = full2hot[h->start[32]];
+    }
   }
   dev_[k] = d.release();
   *out = dev_[k];
@@ -285,8 +339,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
   a.flag0 = (uint8_t*)(counters + 24);
   a.utf8_boundaries = utf8_mask;
-  a.next256 = (const uint16_t*)rev->next256;
-  a.eof = (const uint16_t*)rev->eof;
+  a.hot = rev->hot;
   size_t smem;
   uint32_t block;
   const WalkArgs* fw = (const WalkArgs*)fused_walk;
@@ -294,7 +347,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (fast) {
     block = 1024;
     const bool fw_fixed = fw && fw->fixed_len != 0;
-    smem = fast_scan_smem(rev->view.n_states + (fw && !fw_fixed ? fw->fwd.n_states : 0));
+    smem = fast_scan_smem(rev->hot.n + (fw && !fw_fixed ? fw->fwd_hot.n : 0));
     if (fw_fixed) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,15 +463,15 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   cudaEvent_t ev[3];
   for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
   RB_CUDA(cudaEventRecord(ev[0], st));
-  const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi, revall->next256 != nullptr);
+  const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi, revall->hot.n != 0);
   // runner: 2 = fixed-length (no haystack access), 1 = byte-indexed shared-memory table
   // (uniform start state, 8-byte aligned text), 0 = generic
   const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;
-  const bool wfast = !wfixed && fwd->next256 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
+  const bool wfast = !wfixed && fwd->hot.n != 0 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
   // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
   const bool fused = plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
-                     fast_scan_smem(revall->view.n_states + (wkind == 1 ? fwd->view.n_states : 0)) <= 227 * 1024;
+                     fast_scan_smem(revall->hot.n + (wkind == 1 ? fwd->hot.n : 0)) <= 227 * 1024;
 
   WalkArgs w{};
   w.fwd = fwd->view;
@@ -464,9 +517,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   if (wfixed) {
     w.fixed_len = min_len;
   } else if (wfast) {
-    wsmem = (size_t)fwd->view.n_states * 1024 + 1024;
-    w.fwd_next256 = (const uint16_t*)fwd->next256;
-    w.fwd_eof = (const uint16_t*)fwd->eof;
+    wsmem = (size_t)fwd->hot.n * 1024 + 1024;
+    w.fwd_hot = fwd->hot;
     RB_CUDA(allow_smem(walk_chunks<1>, wsmem));
     RB_CUDA(allow_smem(compact_spans<1>, wsmem));
   } else {

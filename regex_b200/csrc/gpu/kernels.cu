@@ -296,14 +296,34 @@ struct GenericRunner {
 // Fast anchored runner: byte-indexed XOR-swizzled table in shared memory (one LDS per
 // byte, see scan_rev_fast), uniform start state, text taken 16 bytes at a time from
 // three aligned 8-byte loads so a typical match costs one memory round trip.
+// The anchored run on the full class-indexed table in global memory: where a FastRunner
+// lane goes when the haystack leaves the hot set (e.g. a non-ASCII byte under \w).
+// (scalar arguments only: a reference to the kernel's parameter block would make every
+// thread copy it to its stack.)  FastRunner patterns have a uniform start state.
+__device__ __noinline__ uint64_t slow_anchored_end(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo,
+                                                   uint32_t start, const uint8_t* text, uint64_t n, uint64_t s, uint32_t* halo_err) {
+  uint32_t st = start;
+  uint64_t last = kNone;
+  for (uint64_t q = s;; q++) {
+    if (q >= n && halo_err) { *halo_err = 1; return last; }
+    st = q < n ? trans[st * stride + classes[__ldg(text + q)]] : trans[st * stride + stride - 1];
+    if (st >= match_lo) last = q;
+    if (st == 0 || q >= n) break;
+  }
+  return last;
+}
 struct FastRunner {
   uint32_t tbase, thr, start_e;
-  const uint16_t* eof;
-  uint32_t match_lo;
+  const uint16_t* eof;  // by hot id, value in full numbering
+  uint32_t match_lo;    // full numbering (for the EOF successor)
+  static __device__ __forceinline__ uint64_t slow(const WalkArgs& a, uint64_t s) {
+    return slow_anchored_end(a.fwd.trans, a.fwd.classes, a.fwd.stride, a.fwd.match_lo, a.fwd.start[32], a.text, a.n, s,
+                             a.text_continues ? a.err_flag : nullptr);
+  }
   __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
     uint32_t e = start_e;
     uint64_t last = kNone;
-    const uint32_t dead = tbase;  // row 0, key 0
+    const uint32_t live = tbase + 2048u;  // rows 0 (dead) and 1 (trap) end the run
     for (uint64_t q = s;; q += 16) {
       const uint64_t al = q & ~7ull;
       const uint64_t* wp = reinterpret_cast<const uint64_t*>(a.text + al);
@@ -330,8 +350,9 @@ struct FastRunner {
             e = lds32((idx & 0x3FCu) ^ e);
             if (e >= thr) lj = 4 * g + j;
           }
-          if (e == dead) { died = true; break; }
+          if (e < live) { died = true; break; }
         }
+        if (e - tbase >= 1024u && e < live) return slow(a, s);  // trap: left the hot set
         if (lj != ~0u) last = q + lj;
         if (died) return last;
         continue;
@@ -351,7 +372,7 @@ struct FastRunner {
         const uint32_t byte = (uint32_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))) & 0xFF);
         e = fast_step(e, byte);
         if (e >= thr) last = q + j;
-        if (e == dead) return last;
+        if (e < live) return e - tbase >= 1024u ? slow(a, s) : last;
       }
     }
   }
@@ -566,17 +587,17 @@ struct RunnerSetup<1> {
   static __device__ __forceinline__ type make(const WalkArgs& a) {
     FastRunner r;
     r.tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
-    const uint32_t n_ent = a.fwd.n_states * 256u;
+    const uint32_t n_ent = a.fwd_hot.n * 256u;
     for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
       const uint32_t row = i >> 8, b = i & 255u;
       const uint32_t addr = r.tbase + (row << 10) + ((b ^ (row & 31u)) << 2);
-      const uint32_t val = fast_entry(r.tbase, a.fwd_next256[i]);
+      const uint32_t val = fast_entry(r.tbase, a.fwd_hot.next256[i]);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
     }
     __syncthreads();
-    r.thr = r.tbase + a.fwd.match_lo * 1024u;
-    r.start_e = fast_entry(r.tbase, a.fwd.start[32]);
-    r.eof = a.fwd_eof;
+    r.thr = r.tbase + a.fwd_hot.match_lo * 1024u;
+    r.start_e = fast_entry(r.tbase, a.fwd_hot.start);
+    r.eof = a.fwd_hot.eof;
     r.match_lo = a.fwd.match_lo;
     return r;
   }
@@ -660,29 +681,44 @@ template __global__ void compact_spans<2>(WalkArgs);
 // and ONE elected lane issues four [16 B x 32 rows] box loads per 64-byte group for the
 // whole warp (per-lane 64-byte bulk copies were TMA-issue bound: a third of all issued
 // instructions were mbarrier polls).  Ragged ends and redo lists use per-lane bulk copies.
+// One 64-byte group on the full class-indexed table (global memory), highest address
+// first: the path a lane of scan_rev_fast takes while it is outside the hot set.
+__device__ __noinline__ uint32_t slow_group(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo, uint32_t s,
+                                            uint4 c0, uint4 c1, uint4 c2, uint4 c3, uint64_t* bits_out) {
+  const uint32_t w[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+  uint64_t bits = 0;
+  for (int j = 63; j >= 0; j--) {
+    const uint32_t byte = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+    s = trans[s * stride + classes[byte]];
+    if (s >= match_lo) bits |= 1ull << j;
+  }
+  *bits_out = bits;
+  return s;
+}
+
 template <int FUSED>
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
   // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
   const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t ring = tbase + (a.dfa.n_states + (FUSED == 1 ? wa.fwd.n_states : 0u)) * 1024u + wid * kRingWarpBytes;
+  const uint32_t ring = tbase + (a.hot.n + (FUSED == 1 ? wa.fwd_hot.n : 0u)) * 1024u + wid * kRingWarpBytes;
   const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
   {
-    const uint32_t n_ent = a.dfa.n_states * 256u;
+    const uint32_t n_ent = a.hot.n * 256u;
     for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
       const uint32_t r = i >> 8, b = i & 255u;
-      const uint32_t nx = a.next256[i];
+      const uint32_t nx = a.hot.next256[i];
       const uint32_t addr = tbase + (r << 10) + ((b ^ (r & 31u)) << 2);
       const uint32_t val = fast_entry(tbase, nx);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
     }
     if (FUSED == 1) {
-      const uint32_t fbase = tbase + a.dfa.n_states * 1024u;
-      const uint32_t n_fwd = wa.fwd.n_states * 256u;
+      const uint32_t fbase = tbase + a.hot.n * 1024u;
+      const uint32_t n_fwd = wa.fwd_hot.n * 256u;
       for (uint32_t i = threadIdx.x; i < n_fwd; i += blockDim.x) {
         const uint32_t r = i >> 8, b = i & 255u;
         const uint32_t addr = fbase + (r << 10) + ((b ^ (r & 31u)) << 2);
-        const uint32_t val = fast_entry(fbase, wa.fwd_next256[i]);
+        const uint32_t val = fast_entry(fbase, wa.fwd_hot.next256[i]);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
       }
     }
@@ -695,7 +731,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     }
     __syncthreads();
   }
-  const uint32_t thr = tbase + a.dfa.match_lo * 1024u;
+  const uint32_t thr = tbase + a.hot.match_lo * 1024u;
+  const uint32_t trap_e = fast_entry(tbase, 1);
   const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -708,29 +745,59 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     const bool live = idx < total;
     uint64_t t = 0, lo = 0, hi = 0, i = 0;
     uint32_t e = 0;
+    uint32_t cold = 0;  // != 0: the lane is outside the hot set, in this state of the full table (e sits in the trap row)
+    auto enter = [&](uint32_t full) {
+      const uint32_t h = a.hot.full2hot[full];
+      if (h != 0xFFFFu) { e = fast_entry(tbase, h); cold = 0; }
+      else { e = trap_e; cold = full; }
+    };
+    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[(e - tbase) >> 10]; };
+    auto full_step = [&](uint32_t s, uint32_t byte) -> uint32_t { return a.dfa.trans[s * a.dfa.stride + a.dfa.classes[byte]]; };
+    // one 64-byte group: table steps in shared memory; a lane that ends in the trap row
+    // (it met a byte outside the hot set, or was cold already) redoes the group on the full table
+    auto do_group = [&](const uint4& c0, const uint4& c1, const uint4& c2, const uint4& c3, bool rec, uint32_t& bhi, uint32_t& blo) {
+      const uint32_t e0 = e;
+      const uint32_t th = rec ? thr : 0xFFFFFFFFu;
+      bhi = blo = 0;
+      rev_block16<16>(c3, e, bhi, th);
+      rev_block16<0>(c2, e, bhi, th);
+      rev_block16<16>(c1, e, blo, th);
+      rev_block16<0>(c0, e, blo, th);
+      if (((e - tbase) >> 10) == 1u) {
+        uint64_t bits;
+        const uint32_t s1 = slow_group(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo,
+                                       cold ? cold : a.hot.hot2full[(e0 - tbase) >> 10], c0, c1, c2, c3, &bits);
+        bhi = rec ? (uint32_t)(bits >> 32) : 0u;
+        blo = rec ? (uint32_t)bits : 0u;
+        enter(s1);
+      }
+    };
     if (live) {
       t = a.redo_list ? a.redo_list[idx] : idx;
       lo = min(a.base + t * a.seg, a.limit);  // multiple of 64 (or limit)
       hi = min(lo + a.seg, a.limit);          // multiple of 64 (or limit == n)
       i = hi;
       if (a.redo_list) {
-        e = fast_entry(tbase, a.fin[t + 1]);
+        enter(a.fin[t + 1]);
       } else {
         i = min(hi + a.warm, a.n);
-        e = fast_entry(tbase, pick_start_rev(a.dfa, a.text, a.n, i));
-        // ragged top of the warm-up (only next to the end of the haystack)
-        while (i > hi && (i & 63)) { i--; e = fast_step(e, a.text[i]); }
+        uint32_t s = pick_start_rev(a.dfa, a.text, a.n, i);
+        // ragged top of the warm-up (only next to the end of the haystack): full table, byte by byte
+        while (i > hi && (i & 63)) { i--; s = full_step(s, a.text[i]); }
+        enter(s);
       }
       if (i == hi) {
-        a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        a.guess[t] = (uint16_t)full_state();
         if (i & 63) {  // ragged top of the segment itself (last segment only)
           uint64_t word = 0;
+          uint32_t s = full_state();
           while (i > lo && (i & 63)) {
             i--;
-            e = fast_step(e, a.text[i]);
-            if (e >= thr) word |= 1ull << (i & 63);
+            s = full_step(s, a.text[i]);
+            if (s >= a.dfa.match_lo) word |= 1ull << (i & 63);
           }
           a.bitmap[i >> 6] = word;
+          enter(s);
         }
       }
     }
@@ -774,14 +841,10 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         mbar_wait(barb + (u & 1) * 8, (u >> 1) & 1);
         const uint32_t b = my_b + (u & 1) * kRingStageBytes;
         const uint4 c0 = lds128(b), c1 = lds128(b + 512), c2 = lds128(b + 1024), c3 = lds128(b + 1536);
-        if (k == n_warm) a.guess[t] = (uint16_t)((e - tbase) >> 10);
+        if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
-        const uint32_t th = rec ? thr : 0xFFFFFFFFu;
-        uint32_t bhi = 0, blo = 0;
-        rev_block16<16>(c3, e, bhi, th);
-        rev_block16<0>(c2, e, bhi, th);
-        rev_block16<16>(c1, e, blo, th);
-        rev_block16<0>(c0, e, blo, th);
+        uint32_t bhi, blo;
+        do_group(c0, c1, c2, c3, rec, bhi, blo);
         if (rec) {
           *--bw = ((uint64_t)bhi << 32) | blo;
           if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
@@ -811,13 +874,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       if (k < my_groups) {
         const uint4 c0 = lds128(slot), c1 = lds128(slot + 16), c2 = lds128(slot + 32), c3 = lds128(slot + 48);
         const uint64_t g = i - 64ull * (k + 1);  // first byte of this group
-        if (g + 64 == hi) a.guess[t] = (uint16_t)((e - tbase) >> 10);
-        const uint32_t th = g < hi ? thr : 0xFFFFFFFFu;
-        uint32_t bhi = 0, blo = 0;
-        rev_block16<16>(c3, e, bhi, th);
-        rev_block16<0>(c2, e, bhi, th);
-        rev_block16<16>(c1, e, blo, th);
-        rev_block16<0>(c0, e, blo, th);
+        if (g + 64 == hi) a.guess[t] = (uint16_t)full_state();
+        uint32_t bhi, blo;
+        do_group(c0, c1, c2, c3, g < hi, bhi, blo);
         if (g < hi) {
           a.bitmap[g >> 6] = ((uint64_t)bhi << 32) | blo;
           if (FUSED && (bhi | blo)) nz |= 1ull << (((g - lo) >> 6) & 63);
@@ -830,18 +889,18 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     uses += max_groups;
     }
     if (live) {
-      const uint32_t s_lo = (e - tbase) >> 10;
+      const uint32_t s_lo = full_state();
       a.fin[t] = (uint16_t)s_lo;
-      if (lo == 0) *a.flag0 = a.eof[s_lo] >= a.dfa.match_lo;
+      if (lo == 0) *a.flag0 = a.dfa.trans[s_lo * a.dfa.stride + a.dfa.stride - 1] >= a.dfa.match_lo;
       if (FUSED) {
         typename RunnerSetup<FUSED == 2 ? 2 : 1>::type R;
         if constexpr (FUSED == 2) {
           R.len = wa.fixed_len;
         } else {
-          R.tbase = tbase + a.dfa.n_states * 1024u;
-          R.thr = R.tbase + wa.fwd.match_lo * 1024u;
-          R.start_e = fast_entry(R.tbase, wa.fwd.start[32]);
-          R.eof = wa.fwd_eof;
+          R.tbase = tbase + a.hot.n * 1024u;
+          R.thr = R.tbase + wa.fwd_hot.match_lo * 1024u;
+          R.start_e = fast_entry(R.tbase, wa.fwd_hot.start);
+          R.eof = wa.fwd_hot.eof;
           R.match_lo = wa.fwd.match_lo;
         }
         Chain c;

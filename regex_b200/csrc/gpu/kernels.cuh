@@ -33,6 +33,21 @@ struct DfaView {
   uint8_t uniform_start;
 };
 
+// Byte-indexed table over the HOT states of a DFA for the shared-memory fast kernels:
+// either every state (small automata) or the states reachable from the start states
+// through ASCII bytes only (Unicode-aware classes compile to hundreds of states of
+// which an ASCII haystack visits a handful).  Hot ids: 0 = dead, 1 = trap (the
+// transition left the hot set; absorbing), then non-match states, then match states.
+// A lane that lands in the trap row re-runs those bytes on the full class-indexed table.
+struct HotView {
+  const uint16_t* next256;   // [n][256] successor hot ids
+  const uint16_t* eof;       // [n] EOF successor in FULL numbering
+  const uint16_t* hot2full;  // [n]
+  const uint16_t* full2hot;  // [full n_states], 0xFFFF = cold
+  uint32_t n, match_lo;      // rows; hot ids >= match_lo are match states
+  uint32_t start;            // hot id of the uniform start state (forward runner)
+};
+
 __device__ __forceinline__ bool is_word_byte(uint32_t b) {
   return (b - 'a' < 26u) || (b - 'A' < 26u) || (b - '0' < 10u) || b == '_';
 }

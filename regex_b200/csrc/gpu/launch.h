@@ -21,8 +21,7 @@ struct ScanArgs {
   uint32_t warm;     // warm-up bytes for the speculative entry state
   uint64_t* bitmap;  // reverse scan: bit i <=> a match starts at position i+1
   uint8_t* flag0;    // reverse scan: a match starts at position 0
-  const uint16_t* next256;  // fast kernels: [n_states][256] byte-indexed successor ids
-  const uint16_t* eof;      // fast kernels: [n_states] EOF successor ids
+  HotView hot;              // fast kernels: byte-indexed table over the hot states
   uint64_t tmap_rows;       // fast kernels: rows (full segments) covered by the 2-D tensor map, 0 = none
   uint64_t* seg_first;  // forward scan: first match end per segment
   uint64_t* seg_mask;   // forward scan: OR of masks per segment (nullable)
@@ -58,8 +57,7 @@ struct WalkArgs {
   const uint64_t* offset;
   uint32_t* dirty_list;     // chunks to walk again (nullable: all chunks)
   const uint32_t* n_dirty;
-  const uint16_t* fwd_next256;  // fast runner: byte-indexed forward anchored table
-  const uint16_t* fwd_eof;
+  HotView fwd_hot;              // fast runner: byte-indexed forward anchored table (hot states)
   uint64_t fixed_len;           // fixed-length runner: every match has this many bytes
   uint64_t* out;  // spans: start, end pairs
   uint64_t cap;

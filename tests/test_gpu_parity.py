@@ -115,6 +115,36 @@ def test_small_segments_force_boundary_logic(seg, chunk, warm, generic):
                 assert _spans(r.find_all(text[:cut])) == O.OracleRegex(pat, only_utf8=utf8).find_iter(text[:cut]), (pat, cut)
 
 
+@pytest.mark.parametrize("seg", [0, 64, 256])
+def test_unicode_classes_hot_table_and_cold_fallback(seg):
+    """Unicode-aware classes compile to hundreds of DFA states of which ASCII text visits a
+    handful: the fast kernels keep those hot rows in shared memory and a lane that meets
+    a byte outside the hot set (multi-byte UTF-8, invalid bytes) redoes the group on the
+    full table.  Mixed text makes lanes leave and re-enter the hot set all the time."""
+    ascii_part = sherlock_text()[:6000]
+    mixed = ("naïve café über straße Ωμέγα привет мир 日本語のテキスト ２０１４ ٣٤ x²+y² ".encode("utf-8")) * 8
+    junk = bytes([0xFF, 0xC3, 0x28, 0xE2, 0x82, 0x41, 0xF0, 0x9F, 0x98, 0x80, 0x80, 0xBF]) * 5
+    rng = np.random.Generator(np.random.PCG64(0x4807))
+    parts = []
+    for _ in range(60):
+        o = int(rng.integers(0, len(ascii_part) - 400))
+        parts.append(ascii_part[o:o + int(rng.integers(1, 400))])
+        parts.append(mixed[int(rng.integers(0, 40)):][:int(rng.integers(1, 120))] if rng.random() < 0.7 else junk[:int(rng.integers(1, 30))])
+    text_bytes = b"".join(parts)
+    text_str = (ascii_part[:3000].decode("latin-1") + mixed.decode("utf-8") * 2 + ascii_part[3000:5000].decode("latin-1")).encode("utf-8")
+    pats = [r"\w+", r"the\s+\w+", r"\d+", r"(\d{4})-(\d{2})-(\d{2})", r"\pL+ing", r"[^\s]+\s", r"(?i)sher\w*", r"\w+\s*[,.]"]
+    for pat in pats:
+        for cls, utf8, text in ((R.BytesRegex, False, text_bytes), (R.Regex, True, text_str)):
+            r = cls(pat)
+            if seg:
+                r.set_tuning(seg=seg, chunk=max(seg, 256), warm=0)
+            exp = O.OracleRegex(pat, only_utf8=utf8).find_iter(text)
+            got = _spans(r.find_all(text))
+            assert got == exp, (pat, utf8, seg, got[:5], exp[:5])
+            r.force_generic(True)
+            assert _spans(r.find_all(text)) == exp, (pat, utf8, "generic")
+
+
 def test_random_patterns_vs_oracle():
     """Seeded fuzz over a small regex grammar on a 4-letter alphabet (dense matches)."""
     rng = np.random.Generator(np.random.PCG64(0xB200))
