@@ -64,10 +64,11 @@ struct Regex::DeviceDfa {
   void* eof = nullptr;
   void* hot2full = nullptr;
   void* full2hot = nullptr;
+  void* view_dev = nullptr;  // copy of `view` in global memory (cold fallbacks take a pointer)
   HotView hot{};
   ~DeviceDfa() {
     cudaFree(trans); cudaFree(classes); cudaFree(masks); cudaFree(next256); cudaFree(eof);
-    cudaFree(hot2full); cudaFree(full2hot);
+    cudaFree(hot2full); cudaFree(full2hot); cudaFree(view_dev);
   }
 };
 
@@ -262,6 +263,8 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
       d->hot.start = full2hot[h->start[32]];
     }
   }
+  RB_CUDA(cudaMalloc(&d->view_dev, sizeof(DfaView)));
+  RB_CUDA(cudaMemcpy(d->view_dev, &d->view, sizeof(DfaView), cudaMemcpyHostToDevice));
   dev_[k] = d.release();
   *out = dev_[k];
   return 0;
@@ -701,9 +704,19 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
   a.offsets = d_offsets;
   a.n_rec = n_rec;
   a.out_bits = d_bits;
-  RB_CUDA(allow_smem(is_match_batch, smem));
-  is_match_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
-  RB_LAUNCH_CHECK("is_match_batch");
+  if (fwd->hot.n && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic) {
+    a.fwd_hot = fwd->hot;
+    a.fwd_g = (const DfaView*)fwd->view_dev;
+    const size_t fsm = (size_t)fwd->hot.n * 1024 + 1024;
+    RB_CUDA(allow_smem(batch_fast<0>, fsm));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
+    batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+    RB_LAUNCH_CHECK("batch_fast<0>");
+  } else {
+    RB_CUDA(allow_smem(is_match_batch, smem));
+    is_match_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
+    RB_LAUNCH_CHECK("is_match_batch");
+  }
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   return 0;
 }
@@ -723,8 +736,20 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
   a.n_rec = n_rec;
   a.out_bits = d_bits;
   a.out_spans = d_spans;
-  find_batch<<<(uint32_t)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
-  RB_LAUNCH_CHECK("find_batch");
+  if (fwd->hot.n && rev->hot.n && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic) {
+    a.fwd_hot = fwd->hot;
+    a.rev_hot = rev->hot;
+    a.fwd_g = (const DfaView*)fwd->view_dev;
+    a.rev_g = (const DfaView*)rev->view_dev;
+    const size_t fsm = (size_t)(fwd->hot.n + rev->hot.n) * 1024 + 1024;
+    RB_CUDA(allow_smem(batch_fast<1>, fsm));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
+    batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+    RB_LAUNCH_CHECK("batch_fast<1>");
+  } else {
+    find_batch<<<(uint32_t)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
+    RB_LAUNCH_CHECK("find_batch");
+  }
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   return 0;
 }

@@ -1056,6 +1056,211 @@ __global__ void find_batch(BatchArgs a) {
   if ((threadIdx.x & 31) == 0 && r < a.n_rec) a.out_bits[r >> 5] = bits;
 }
 
+
+// ---- batch_fast: the same per-record algorithms on the shared-memory hot tables ----
+// One thread per record as above, but (a) one LDS per byte on the byte-indexed tables
+// instead of class + transition look-ups, (b) the record is read 16 bytes at a time from
+// three aligned 8-byte loads (a byte load per lane costs a full L1 wavefront per lane:
+// 32 per warp-step, against ~2 for the table), (c) persistent blocks, so the tables are
+// staged once per block.  A record that leaves the hot set is redone on the full tables.
+__device__ __forceinline__ void window16(const uint8_t* p, uint32_t (&v)[4]) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint64_t* wp = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(addr & 7) * 8;
+  const uint64_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+  const uint32_t x0 = __funnelshift_r((uint32_t)w0, (uint32_t)(w0 >> 32), sh);
+  const uint32_t x1 = __funnelshift_r((uint32_t)(w0 >> 32), (uint32_t)w1, sh);
+  const uint32_t x2 = __funnelshift_r((uint32_t)w1, (uint32_t)(w1 >> 32), sh);
+  const uint32_t x3 = __funnelshift_r((uint32_t)(w1 >> 32), (uint32_t)w2, sh);
+  const uint32_t x4 = __funnelshift_r((uint32_t)w2, (uint32_t)(w2 >> 32), sh);
+  const bool up = sh >= 32;
+  v[0] = up ? x1 : x0; v[1] = up ? x2 : x1; v[2] = up ? x3 : x2; v[3] = up ? x4 : x3;
+}
+__device__ __forceinline__ uint32_t window_byte_idx(const uint32_t (&v)[4], int i) {  // (byte i) << 2, i compile-time
+  return (i & 3) == 0 ? (v[i >> 2] << 2) & 0x3FCu : (v[i >> 2] >> (8 * (i & 3) - 2)) & 0x3FCu;
+}
+__device__ __forceinline__ void stage_hot(const HotView& h, uint32_t tbase) {
+  const uint32_t n_ent = h.n * 256u;
+  for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
+    const uint32_t row = i >> 8, b = i & 255u;
+    const uint32_t addr = tbase + (row << 10) + ((b ^ (row & 31u)) << 2);
+    const uint32_t val = fast_entry(tbase, h.next256[i]);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
+  }
+}
+__device__ __noinline__ bool slow_is_match_record(const DfaView* f, const uint8_t* p, uint64_t len) {
+  uint32_t s = f->uniform_start ? f->start[32] : f->start[flags_forward(p, len, 0)];
+  for (uint64_t q = 0; s != 0; q++) {
+    s = q < len ? f->trans[s * f->stride + f->classes[p[q]]] : f->trans[s * f->stride + f->stride - 1];
+    if (s >= f->match_lo) return true;
+    if (q >= len) break;
+  }
+  return false;
+}
+__device__ __noinline__ bool slow_find_record(const DfaView* f, const DfaView* rv, const uint8_t* p, uint64_t len, uint64_t* ms_out, uint64_t* e_out) {
+  uint32_t s = f->uniform_start ? f->start[32] : f->start[flags_forward(p, len, 0)];
+  uint64_t e = kNone;
+  for (uint64_t q = 0; s != 0; q++) {
+    s = q < len ? f->trans[s * f->stride + f->classes[p[q]]] : f->trans[s * f->stride + f->stride - 1];
+    if (s >= f->match_lo) e = q;
+    if (q >= len) break;
+  }
+  if (e == kNone) return false;
+  const uint64_t ms = e == 0 ? 0 : slice_start(*rv, p, len, 0, e);
+  if (ms == kNone) return false;
+  *ms_out = ms;
+  *e_out = e;
+  return true;
+}
+
+// MODE 0: is_match (forward all-match automaton, stop at the first match state);
+// MODE 1: find (forward leftmost-first end, then the reverse longest automaton for the start).
+template <int MODE>
+__global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
+  const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+  const uint32_t rbase = fbase + a.fwd_hot.n * 1024u;
+  stage_hot(a.fwd_hot, fbase);
+  if (MODE == 1) stage_hot(a.rev_hot, rbase);
+  __syncthreads();
+  const uint32_t fthr = fbase + a.fwd_hot.match_lo * 1024u, flive = fbase + 2048u;
+  const uint32_t rthr = rbase + a.rev_hot.match_lo * 1024u, rlive = rbase + 2048u;
+  const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // multiple of 32: warps stay on one ballot word
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r - lane < a.n_rec; r += stride) {
+    bool hit = false;
+    uint64_t ms = 0, me = 0;
+    if (r < a.n_rec) {
+      const uint64_t lo = a.offsets[r], len = a.offsets[r + 1] - lo;
+      const uint8_t* p = a.text + lo;
+      bool cold = false;
+      // ---- forward ----
+      const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
+      uint32_t e = fast_entry(fbase, h0 == 0xFFFFu ? 1u : h0);
+      uint64_t last = kNone;
+      uint32_t mx = 0;
+      uint64_t q = 0;
+      bool done = false;
+      while (!done) {
+        const uint64_t left = len - q;
+        if (left == 0) {  // EOF step
+          if (e >= flive && a.fwd_hot.eof[(e - fbase) >> 10] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
+          break;
+        }
+        const uint8_t* wp = p + q;
+        const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+        if (al + 24 <= buf_hi) {
+          uint32_t v[4];
+          window16(wp, v);
+          const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
+          uint32_t lj = ~0u;
+          if (nb == 16) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                e = lds32(window_byte_idx(v, 4 * g + j) ^ e);
+                if (MODE == 0) mx = max(mx, e);
+                else if (e >= fthr) lj = 4 * g + j;
+              }
+              if (e < flive || (MODE == 0 && mx >= fthr)) { done = true; break; }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+              if ((uint32_t)i < nb) {
+                e = lds32(window_byte_idx(v, i) ^ e);
+                if (MODE == 0) mx = max(mx, e);
+                else if (e >= fthr) lj = i;
+              }
+            }
+            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
+          }
+          if (MODE == 1 && lj != ~0u) last = q + lj;
+          q += nb;
+        } else {  // the last bytes of the whole buffer: byte loads
+          for (uint64_t i = 0; i < left && !done; i++) {
+            e = fast_step(e, p[q + i]);
+            if (MODE == 0) mx = max(mx, e);
+            else if (e >= fthr) last = q + i;
+            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
+          }
+          q += left;
+        }
+      }
+      if (e - fbase >= 1024u && e < flive && !(MODE == 0 && mx >= fthr)) cold = true;  // trap row
+      if (MODE == 0) {
+        hit = cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr;
+      } else if (cold) {
+        hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+      } else if (last != kNone) {
+        // ---- reverse from the match end (exec.rs:651-657; the record is its own slice) ----
+        me = last;
+        uint64_t start = kNone;
+        bool rcold = false;
+        if (me == 0) {
+          start = 0;
+        } else {
+          const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, me)];
+          const uint32_t hr = a.rev_hot.full2hot[sf];
+          if (sf == 0) {
+            start = kNone;
+          } else if (hr == 0xFFFFu) {
+            rcold = true;
+          } else {
+            uint32_t er = fast_entry(rbase, hr);
+            uint64_t at = me;
+            bool rdone = false;
+            while (at > 0 && !rdone) {
+              const uint8_t* wp = p + at - 16;  // window = bytes [at-16, at); only the last min(16, at) belong to the record
+              const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+              const uint32_t nb = at >= 16 ? 16u : (uint32_t)at;
+              if (al >= a.text && al + 24 <= buf_hi) {
+                uint32_t v[4];
+                window16(wp, v);
+                uint32_t lj = ~0u;
+#pragma unroll
+                for (int i = 15; i >= 0; i--) {
+                  if ((uint32_t)(15 - i) < nb && !rdone) {
+                    er = lds32(window_byte_idx(v, i) ^ er);
+                    if (er >= rthr) lj = i;
+                    if (er < rlive) rdone = true;
+                  }
+                }
+                if (lj != ~0u) start = at - 16 + lj + 1;
+                at -= nb;
+              } else {
+                for (uint32_t i = 0; i < nb && !rdone; i++) {
+                  at--;
+                  er = fast_step(er, p[at]);
+                  if (er >= rthr) start = at + 1;
+                  if (er < rlive) rdone = true;
+                }
+              }
+            }
+            if (er - rbase >= 1024u && er < rlive) rcold = true;
+            else if (!rdone && a.rev_hot.eof[(er - rbase) >> 10] >= a.rev.match_lo) start = 0;
+          }
+        }
+        if (rcold) {
+          hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+        } else if (start != kNone) {
+          hit = true;
+          ms = start;
+        }
+      }
+      if (MODE == 1) {
+        a.out_spans[2 * r] = hit ? ms : 0;
+        a.out_spans[2 * r + 1] = hit ? me : 0;
+      }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) a.out_bits[r >> 5] = bits;
+  }
+}
+template __global__ void batch_fast<0>(BatchArgs);
+template __global__ void batch_fast<1>(BatchArgs);
+
 // dfa.rs:525-570 per record: OR of the per-state pattern masks along the scan.
 __global__ void set_matches_batch(BatchArgs a) {
   const Table T = stage_table(a.fwd, g_smem, a.use_smem);

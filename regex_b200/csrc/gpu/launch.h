@@ -69,6 +69,9 @@ struct WalkArgs {
 struct BatchArgs {
   DfaView fwd;
   DfaView rev;
+  HotView fwd_hot, rev_hot;          // batch_fast: byte-indexed hot tables
+  const DfaView* fwd_g;              // the same views in global memory (cold fallback)
+  const DfaView* rev_g;
   int use_smem;
   const uint8_t* text;
   const uint64_t* offsets;  // n_rec + 1
@@ -78,6 +81,8 @@ struct BatchArgs {
   uint64_t* out_masks;  // mask_words per record
 };
 
+template <int MODE>
+__global__ void batch_fast(BatchArgs a);
 __global__ void scan_rev_bitmap(ScanArgs a);
 template <int FUSED>
 __global__ void scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap);

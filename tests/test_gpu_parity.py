@@ -211,18 +211,32 @@ def _log_lines(n, seed=0x5EED0003):
 def test_batched_lines_match_scalar_api():
     lines = _log_lines(3000)
     lines[17] = b""  # empty record
+    # records that leave the hot (ASCII-reachable) part of Unicode-class tables, short
+    # records, and records shorter / longer than the 16-byte window of batch_fast
+    lines[0] = b"2014-01-02"
+    lines[1] = "٢٠١٤-٠١-٠٢ arabic-indic digits are \\d too\n".encode()
+    lines[2] = "naïve 1999-12-31 café\n".encode()
+    lines[3] = b"\xff\xfe 2001-02-03 \xc3\n"
+    lines[4] = b"7"
+    lines[5] = b"x" * 15 + b"2020-10-10"
+    lines[6] = b"x" * 16 + b"2020-10-10" + b"y" * 33
+    lines[-1] = b"no newline at the very end 2030-01-01"
     text = b"".join(lines)
     off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.uint64)
-    for pat in [r"(\d{4})-(\d{2})-(\d{2})", r"(?-u)(\d{4})-(\d{2})-(\d{2})", r"^\d+ host", r"svc\[\d+\]:$", r"(?i)holmes", r"\n$"]:
-        r, o = R.BytesRegex(pat), O.OracleRegex(pat)
-        m = r.is_match_batch(text, off)
-        found, spans = r.find_batch(text, off)
-        for i, l in enumerate(lines):
-            exp = o.find_at(l)
-            assert bool(m[i]) == (exp is not None), (pat, i)
-            assert bool(found[i]) == (exp is not None), (pat, i)
-            if exp:
-                assert tuple(int(v) for v in spans[i]) == exp, (pat, i)
+    for pat in [r"(\d{4})-(\d{2})-(\d{2})", r"(?-u)(\d{4})-(\d{2})-(\d{2})", r"^\d+ host", r"svc\[\d+\]:$", r"(?i)holmes", r"\n$",
+                r"\w+\s\w+$", r"(?-u:\b)\d{2}(?-u:\b)", r"^$", r"[a-z]+ing"]:
+        o = O.OracleRegex(pat)
+        for generic in (False, True):
+            r = R.BytesRegex(pat)
+            r.force_generic(generic)
+            m = r.is_match_batch(text, off)
+            found, spans = r.find_batch(text, off)
+            for i, l in enumerate(lines):
+                exp = o.find_at(l)
+                assert bool(m[i]) == (exp is not None), (pat, i, generic)
+                assert bool(found[i]) == (exp is not None), (pat, i, generic)
+                if exp:
+                    assert tuple(int(v) for v in spans[i]) == exp, (pat, i, generic)
 
 
 SET_PATTERNS = [r"\w+", r"\d+", r"\s+", r"[A-Z][a-z]+", "Holmes", "Watson", "Sherlock", r"Holmes|Watson", r"^The", r"\.$",
