@@ -8,6 +8,11 @@ namespace rbgpu {
 
 extern __shared__ __align__(16) unsigned char g_smem[];
 
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p);
+__device__ __forceinline__ uint32_t word_byte(const uint4& v, int j) {  // byte j (0..15) of a 16-byte vector
+  const uint32_t w = (j >> 2) == 0 ? v.x : (j >> 2) == 1 ? v.y : (j >> 2) == 2 ? v.z : v.w;
+  return (w >> (8 * (j & 3))) & 0xFFu;
+}
 __device__ __forceinline__ uint32_t pick_start_rev(const DfaView& d, const uint8_t* t, uint64_t n, uint64_t at) {
   return d.uniform_start ? d.start[32] : d.start[flags_reverse(t, n, at)];
 }
@@ -25,9 +30,12 @@ __device__ __forceinline__ uint32_t pick_start_fwd(const DfaView& d, const uint8
 // against the neighbour's exact final state and lists the segments to redo.
 //
 // Generic version: any table size (shared memory when it fits, else L1/L2), any
-// alignment, optional UTF-8 boundary mask.  One byte load + two lookups per byte.
+// alignment, optional UTF-8 boundary mask.  Two lookups per byte; the haystack is read
+// with 16-byte loads when the buffer is 16-byte aligned (a byte load per lane costs the
+// warp 32 L1 wavefronts per byte-step, a 16-byte load 32 per sixteen).
 __global__ void scan_rev_bitmap(ScanArgs a) {
   const Table T = stage_table(a.dfa, g_smem, a.use_smem);
+  const bool vec = (reinterpret_cast<uintptr_t>(a.text) & 15) == 0;
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
   const uint32_t match_lo = a.dfa.match_lo;
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
@@ -41,20 +49,33 @@ __global__ void scan_rev_bitmap(ScanArgs a) {
     } else {
       const uint64_t w = min(hi + a.warm, a.n);
       s = pick_start_rev(a.dfa, a.text, a.n, w);
-      for (uint64_t i = w; i > hi; i--) s = T.step(s, a.text[i - 1]);
+      uint64_t i = w;
+      while (i > hi && (!vec || (i & 15) || i - hi < 16)) { i--; s = T.step(s, a.text[i]); }
+      while (i > hi) {  // vec: i and hi are 16-byte aligned here
+        const uint4 v = ldg128(a.text + i - 16);
+#pragma unroll
+        for (int j = 15; j >= 0; j--) s = T.step(s, word_byte(v, j));
+        i -= 16;
+      }
     }
     a.guess[t] = (uint16_t)s;
     uint64_t word = 0;
     uint32_t next_byte = hi < a.n ? a.text[hi] : 0;  // text[i+1], for the UTF-8 boundary mask
-    for (uint64_t i = hi; i > lo;) {
-      i--;
-      const uint32_t b = a.text[i];
+    auto consume = [&](uint32_t b, uint64_t pos) {
       s = T.step(s, b);
       bool hit = s >= match_lo;
       if (a.utf8_boundaries && (next_byte & 0xC0) == 0x80) hit = false;
-      if (hit) word |= 1ull << (i & 63);
+      if (hit) word |= 1ull << (pos & 63);
       next_byte = b;
-      if ((i & 63) == 0 || i == lo) { a.bitmap[i >> 6] = word; word = 0; }
+      if ((pos & 63) == 0 || pos == lo) { a.bitmap[pos >> 6] = word; word = 0; }
+    };
+    uint64_t i = hi;
+    while (i > lo && (!vec || (i & 15) || i - lo < 16)) { i--; consume(a.text[i], i); }
+    while (i > lo) {  // vec: 16-byte aligned, lo is a multiple of 64
+      const uint4 v = ldg128(a.text + i - 16);
+#pragma unroll
+      for (int j = 15; j >= 0; j--) consume(word_byte(v, j), i - 16 + j);
+      i -= 16;
     }
     a.fin[t] = (uint16_t)s;
     if (lo == 0) {
@@ -146,6 +167,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // Per segment: the first match end and the OR of the per-state pattern masks.
 __global__ void scan_fwd_reduce(ScanArgs a) {
   const Table T = stage_table(a.dfa, g_smem, a.use_smem);
+  const bool vec = (reinterpret_cast<uintptr_t>(a.text) & 15) == 0;
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
   const uint32_t match_lo = a.dfa.match_lo, mw = a.dfa.mask_words;
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
@@ -159,22 +181,42 @@ __global__ void scan_fwd_reduce(ScanArgs a) {
     } else {
       const uint64_t w = (lo - a.base > a.warm) ? lo - a.warm : a.base;
       s = pick_start_fwd(a.dfa, a.text, a.n, w);
-      for (uint64_t q = w; q < lo; q++) s = T.step(s, a.text[q]);
+      uint64_t q = w;
+      while (q < lo && (!vec || (q & 15) || lo - q < 16)) { s = T.step(s, a.text[q]); q++; }
+      while (q < lo) {
+        const uint4 v = ldg128(a.text + q);
+#pragma unroll
+        for (int j = 0; j < 16; j++) s = T.step(s, word_byte(v, j));
+        q += 16;
+      }
     }
     a.guess[t] = (uint16_t)s;
     uint64_t first = kNone;
     uint64_t acc[kMaxMaskWords] = {0, 0, 0, 0};
-    for (uint64_t q = lo; q < hi; q++) {
-      s = q < a.n ? T.step(s, a.text[q]) : T.step_eof(s);
+    uint32_t last_match = 0;  // masks of this state are already in acc
+    auto consume = [&](uint32_t ns, uint64_t pos) {
+      s = ns;
       if (s >= match_lo) {
-        if (first == kNone) first = q;
-        if (a.seg_mask) {
+        if (first == kNone) first = pos;
+        if (a.seg_mask && s != last_match) {
+          last_match = s;
 #pragma unroll
           for (uint32_t w = 0; w < kMaxMaskWords; w++)
             if (w < mw) acc[w] |= a.dfa.masks[(uint64_t)s * mw + w];
         }
       }
+    };
+    uint64_t q = lo;
+    const uint64_t text_hi = min(hi, a.n);  // bytes [lo, text_hi), then the EOF step if hi == n + 1
+    while (q < text_hi && (!vec || (q & 15) || text_hi - q < 16)) { consume(T.step(s, a.text[q]), q); q++; }
+    while (q + 16 <= text_hi) {
+      const uint4 v = ldg128(a.text + q);
+#pragma unroll
+      for (int j = 0; j < 16; j++) consume(T.step(s, word_byte(v, j)), q + j);
+      q += 16;
     }
+    while (q < text_hi) { consume(T.step(s, a.text[q]), q); q++; }
+    if (q < hi) consume(T.step_eof(s), q);  // q == n
     a.fin[t] = (uint16_t)s;
     a.seg_first[t] = first;
     if (a.seg_mask) {
@@ -1271,15 +1313,37 @@ __global__ void set_matches_batch(BatchArgs a) {
   const uint32_t mw = a.fwd.mask_words;
   uint64_t acc[kMaxMaskWords] = {0, 0, 0, 0};
   uint32_t s = pick_start_fwd(a.fwd, p, len, 0);
-  for (uint64_t q = 0; s != 0; q++) {
-    s = q < len ? T.step(s, p[q]) : T.step_eof(s);
-    if (s >= a.fwd.match_lo) {
+  uint32_t last_match = 0;  // masks of this state are already in acc
+  auto consume = [&](uint32_t ns) {
+    s = ns;
+    if (s >= a.fwd.match_lo && s != last_match) {
+      last_match = s;
 #pragma unroll
       for (uint32_t w = 0; w < kMaxMaskWords; w++)
         if (w < mw) acc[w] |= a.fwd.masks[(uint64_t)s * mw + w];
     }
-    if (q >= len) break;
+  };
+  // the record 16 bytes at a time (three aligned 8-byte loads) while that stays inside the buffer
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.text) & 7) == 0;
+  const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
+  uint64_t q = 0;
+  while (q < len && s != 0) {
+    const uint8_t* wp = p + q;
+    const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+    if (aligned && al + 24 <= buf_hi) {
+      uint32_t v[4];
+      window16(wp, v);
+      const uint32_t nb = len - q >= 16 ? 16u : (uint32_t)(len - q);
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        if ((uint32_t)i < nb && s != 0) consume(T.step(s, window_byte_idx(v, i) >> 2));
+      q += nb;
+    } else {
+      consume(T.step(s, p[q]));
+      q++;
+    }
   }
+  if (s != 0) consume(T.step_eof(s));
 #pragma unroll
   for (uint32_t w = 0; w < kMaxMaskWords; w++)
     if (w < mw) a.out_masks[r * mw + w] = acc[w];
