@@ -49,9 +49,10 @@ void* DeviceBuf::ensure(size_t bytes) {
   return ptr;
 }
 
-// Byte-indexed tables of up to this many states (1 KiB per state) are staged in
-// shared memory by the fast kernels.
-static constexpr uint32_t kFastStates = 56;
+// Hot tables of up to this many rows (288 bytes per row, one-byte successor ids) are
+// staged in shared memory by the fast kernels.
+static constexpr uint32_t kFastStates = 200;
+static size_t hot_bytes(uint32_t rows) { return ((size_t)rows * 288 + 255) / 256 * 256; }  // kernels.cu hot_table_bytes
 
 struct Regex::DeviceDfa {
   DfaView view;
@@ -286,8 +287,8 @@ static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t block
   return (uint32_t)std::max<uint64_t>(1, std::min(blocks, cap));
 }
 
-static size_t fast_scan_smem(uint32_t table_states) {
-  return (size_t)table_states * 1024 + 1024 + (1024 / 32) * (2 * 32 * 80 + 128);
+static size_t fast_scan_smem(size_t table_bytes) {
+  return table_bytes + 1024 + (1024 / 32) * (2 * 2048 + 32);  // kernels.cu: tables, 512-aligned rings, mbarriers
 }
 
 static uint32_t pick_warm(const Regex& re) {
@@ -350,7 +351,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (fast) {
     block = 1024;
     const bool fw_fixed = fw && fw->fixed_len != 0;
-    smem = fast_scan_smem(rev->hot.n + (fw && !fw_fixed ? fw->fwd_hot.n : 0));
+    smem = fast_scan_smem(hot_bytes(rev->hot.n) + (fw && !fw_fixed ? hot_bytes(fw->fwd_hot.n) : 0));
     if (fw_fixed) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -368,10 +369,10 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     if (rows >= 34) {
       cuuint64_t dims[2] = {seg, rows};
       cuuint64_t strides[1] = {seg};
-      cuuint32_t box[2] = {16, 32};
+      cuuint32_t box[2] = {64, 32};  // one box = the 64-byte group of all 32 lanes' segments
       cuuint32_t estr[2] = {1, 1};
       CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)(d_text + base), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) a.tmap_rows = rows;
     }
@@ -474,7 +475,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
   // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
   const bool fused = plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
-                     fast_scan_smem(revall->hot.n + (wkind == 1 ? fwd->hot.n : 0)) <= 227 * 1024;
+                     fast_scan_smem(hot_bytes(revall->hot.n) + (wkind == 1 ? hot_bytes(fwd->hot.n) : 0)) <= 227 * 1024;
 
   WalkArgs w{};
   w.fwd = fwd->view;
@@ -520,7 +521,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   if (wfixed) {
     w.fixed_len = min_len;
   } else if (wfast) {
-    wsmem = (size_t)fwd->hot.n * 1024 + 1024;
+    wsmem = hot_bytes(fwd->hot.n) + 256;
     w.fwd_hot = fwd->hot;
     RB_CUDA(allow_smem(walk_chunks<1>, wsmem));
     RB_CUDA(allow_smem(compact_spans<1>, wsmem));
@@ -707,7 +708,7 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
   if (fwd->hot.n && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic) {
     a.fwd_hot = fwd->hot;
     a.fwd_g = (const DfaView*)fwd->view_dev;
-    const size_t fsm = (size_t)fwd->hot.n * 1024 + 1024;
+    const size_t fsm = hot_bytes(fwd->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<0>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
     batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
@@ -741,7 +742,7 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
     a.rev_hot = rev->hot;
     a.fwd_g = (const DfaView*)fwd->view_dev;
     a.rev_g = (const DfaView*)rev->view_dev;
-    const size_t fsm = (size_t)(fwd->hot.n + rev->hot.n) * 1024 + 1024;
+    const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<1>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
     batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);

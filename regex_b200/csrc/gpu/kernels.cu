@@ -86,20 +86,43 @@ __global__ void scan_rev_bitmap(ScanArgs a) {
   }
 }
 
-// Fast version for byte-indexed tables that fit shared memory (<= ~200 states):
-//   - the table is expanded to [state][256] 32-bit entries; an entry IS the shared-
-//     memory address of the successor's row plus a per-row XOR key, so one LOP3
-//     ((w >> k) & 0x3FC) ^ entry forms the next address and one LDS fetches the
-//     next entry.  The key (row & 31) rotates the bank of a given byte from row
-//     to row, which removes the systematic conflicts of small alphabets (DNA).
-//   - match rows sit above non-match rows, so "entry >= thr" is the match test.
-//   - each lane streams its own segment with 16-byte loads, one 64-byte group
-//     prefetched ahead; bits are assembled in registers, one 64-bit store per
-//     64 bytes of text.
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+// Fast version for hot tables (kernels.cuh HotView) staged in shared memory:
+//   - ONE-BYTE entries: row r holds the 256 successor ids of hot state r, rows are
+//     kHotRow = 288 bytes apart.  With 4-byte entries a row covers all 32 banks, so lanes
+//     in different states collide at random (ncu: 2.1 wavefronts per look-up, the
+//     kernel's binding cost).  With one-byte entries the letters a-z of one row live in 7
+//     consecutive words, and the 32 spare bytes per row start consecutive rows 8 banks
+//     apart: the few states a text automaton spends its time in use disjoint banks, and
+//     lanes reading neighbouring bytes of one row share a word (broadcast).
+//   - a step is PRMT (haystack byte k merged into the 256-aligned table address) +
+//     IMAD (state * 288 + that) + LDS.U8; the state IS the row index, match rows sit
+//     above non-match rows ("e >= match_lo"), row 0 = dead, row 1 = trap.
+//   - bits are assembled in registers, one 64-bit store per 64 bytes of text.
+constexpr uint32_t kHotRow = 288;
+__device__ __forceinline__ uint32_t hot_table_bytes(uint32_t rows) { return (rows * kHotRow + 255u) & ~255u; }
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
+}
+// successor of state e on byte K (compile-time) of the little-endian word w; tb = 256-aligned table address
+template <int K>
+__device__ __forceinline__ uint32_t hot_next(uint32_t tb, uint32_t w, uint32_t e) {
+  const uint32_t x = __byte_perm(w, tb, 0x7650 + K);  // tb | byte K of w
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, 288, %2;" : "=r"(addr) : "r"(e), "r"(x));
+  return lds8(addr);
+}
+__device__ __forceinline__ uint32_t hot_next_b(uint32_t tb, uint32_t byte, uint32_t e) { return lds8(tb + e * kHotRow + byte); }
+// cooperative expansion of a hot table into shared memory (4 entries per store)
+__device__ __forceinline__ void hot_stage(const HotView& h, uint32_t tb) {
+  const uint32_t n4 = h.n * 64u;
+  const uint2* src = reinterpret_cast<const uint2*>(h.next256);  // 4 x u16
+  for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    const uint2 v = src[i];
+    const uint32_t packed = (v.x & 0xFFu) | ((v.x >> 8) & 0xFF00u) | ((v.y & 0xFFu) << 16) | ((v.y >> 16) << 24);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tb + (i >> 6) * kHotRow + (i & 63u) * 4u), "r"(packed));
+  }
 }
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
   uint4 v;
@@ -109,29 +132,28 @@ __device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
 }
 // Consume the 4 bytes of w from the highest address down; BIT0 = bit index of byte 0.
 template <int BIT0>
-__device__ __forceinline__ void rev_word(uint32_t w, uint32_t& e, uint32_t& bits, uint32_t thr) {
-  e = lds32(((w >> 22) & 0x3FCu) ^ e); if (e >= thr) bits |= 1u << (BIT0 + 3);
-  e = lds32(((w >> 14) & 0x3FCu) ^ e); if (e >= thr) bits |= 1u << (BIT0 + 2);
-  e = lds32(((w >> 6) & 0x3FCu) ^ e);  if (e >= thr) bits |= 1u << (BIT0 + 1);
-  e = lds32(((w << 2) & 0x3FCu) ^ e);  if (e >= thr) bits |= 1u << (BIT0 + 0);
+__device__ __forceinline__ void rev_word(uint32_t tb, uint32_t w, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  e = hot_next<3>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 3);
+  e = hot_next<2>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 2);
+  e = hot_next<1>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 1);
+  e = hot_next<0>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 0);
 }
 template <int BIT0>
-__device__ __forceinline__ void rev_block16(const uint4& v, uint32_t& e, uint32_t& bits, uint32_t thr) {
-  rev_word<BIT0 + 12>(v.w, e, bits, thr);
-  rev_word<BIT0 + 8>(v.z, e, bits, thr);
-  rev_word<BIT0 + 4>(v.y, e, bits, thr);
-  rev_word<BIT0 + 0>(v.x, e, bits, thr);
+__device__ __forceinline__ void rev_block16(uint32_t tb, const uint4& v, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  rev_word<BIT0 + 12>(tb, v.w, e, bits, thr);
+  rev_word<BIT0 + 8>(tb, v.z, e, bits, thr);
+  rev_word<BIT0 + 4>(tb, v.y, e, bits, thr);
+  rev_word<BIT0 + 0>(tb, v.x, e, bits, thr);
 }
-__device__ __forceinline__ uint32_t fast_entry(uint32_t tbase, uint32_t id) { return tbase + id * 1024u + (id & 31u) * 4u; }
-__device__ __forceinline__ uint32_t fast_step(uint32_t e, uint32_t byte) { return lds32((byte << 2) ^ e); }
 
 // ---- TMA ring: per-lane 64-byte groups land in shared memory through cp.async.bulk ----
 // Uncoalesced per-lane LDG.128 costs one L1TEX wavefront per lane (ncu: L1/TEX at 98 %
 // with half of it global loads).  Bulk copies bypass the LSU path; each lane then
-// reads its own 64 bytes with four conflict-free LDS.128 (lane stride 80 bytes).
-constexpr uint32_t kRingLaneStride = 80;                       // 64 data + 16 pad
+// reads its own 64 bytes with four LDS.128 (conflict-free in the 2-D TMA layout below).
+constexpr uint32_t kRingLaneStride = 64;                       // one 64-byte group per lane
 constexpr uint32_t kRingStageBytes = 32 * kRingLaneStride;     // per warp
-constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes + 128; // two stages + two mbarriers; multiple of 128 (TMA tensor dst alignment)
+constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes;       // two stages; 512-byte aligned (TMA 64B-swizzle pattern)
+constexpr uint32_t kRingBarBytes = 32;                         // four 8-byte mbarriers per warp, after all rings
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -355,7 +377,7 @@ __device__ __noinline__ uint64_t slow_anchored_end(const uint16_t* trans, const 
   return last;
 }
 struct FastRunner {
-  uint32_t tbase, thr, start_e;
+  uint32_t tb, thr, start_e;  // table address, first match row, start row
   const uint16_t* eof;  // by hot id, value in full numbering
   uint32_t match_lo;    // full numbering (for the EOF successor)
   static __device__ __forceinline__ uint64_t slow(const WalkArgs& a, uint64_t s) {
@@ -365,7 +387,7 @@ struct FastRunner {
   __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
     uint32_t e = start_e;
     uint64_t last = kNone;
-    const uint32_t live = tbase + 2048u;  // rows 0 (dead) and 1 (trap) end the run
+    const uint32_t live = 2;  // rows 0 (dead) and 1 (trap) end the run
     for (uint64_t q = s;; q += 16) {
       const uint64_t al = q & ~7ull;
       const uint64_t* wp = reinterpret_cast<const uint64_t*>(a.text + al);
@@ -386,15 +408,13 @@ struct FastRunner {
         bool died = false;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t idx = j == 0 ? (v[g] << 2) : (v[g] >> (8 * j - 2));
-            e = lds32((idx & 0x3FCu) ^ e);
-            if (e >= thr) lj = 4 * g + j;
-          }
+          e = hot_next<0>(tb, v[g], e); if (e >= thr) lj = 4 * g + 0;
+          e = hot_next<1>(tb, v[g], e); if (e >= thr) lj = 4 * g + 1;
+          e = hot_next<2>(tb, v[g], e); if (e >= thr) lj = 4 * g + 2;
+          e = hot_next<3>(tb, v[g], e); if (e >= thr) lj = 4 * g + 3;
           if (e < live) { died = true; break; }
         }
-        if (e - tbase >= 1024u && e < live) return slow(a, s);  // trap: left the hot set
+        if (e == 1) return slow(a, s);  // trap: left the hot set
         if (lj != ~0u) last = q + lj;
         if (died) return last;
         continue;
@@ -407,14 +427,13 @@ struct FastRunner {
       for (int j = 0; j < 16; j++) {
         if ((uint64_t)j >= avail) {  // EOF step (dfa.rs:748-763)
           if (a.text_continues) { *a.err_flag = 1; return last; }
-          const uint32_t st = (e - tbase) >> 10;
-          if (eof[st] >= match_lo) last = a.n;
+          if (eof[e] >= match_lo) last = a.n;
           return last;
         }
         const uint32_t byte = (uint32_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))) & 0xFF);
-        e = fast_step(e, byte);
+        e = hot_next_b(tb, byte, e);
         if (e >= thr) last = q + j;
-        if (e < live) return e - tbase >= 1024u ? slow(a, s) : last;
+        if (e < live) return e == 1 ? slow(a, s) : last;
       }
     }
   }
@@ -628,17 +647,11 @@ struct RunnerSetup<1> {
   using type = FastRunner;
   static __device__ __forceinline__ type make(const WalkArgs& a) {
     FastRunner r;
-    r.tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
-    const uint32_t n_ent = a.fwd_hot.n * 256u;
-    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
-      const uint32_t row = i >> 8, b = i & 255u;
-      const uint32_t addr = r.tbase + (row << 10) + ((b ^ (row & 31u)) << 2);
-      const uint32_t val = fast_entry(r.tbase, a.fwd_hot.next256[i]);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
-    }
+    r.tb = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+    hot_stage(a.fwd_hot, r.tb);
     __syncthreads();
-    r.thr = r.tbase + a.fwd_hot.match_lo * 1024u;
-    r.start_e = fast_entry(r.tbase, a.fwd_hot.start);
+    r.thr = a.fwd_hot.match_lo;
+    r.start_e = a.fwd_hot.start;
     r.eof = a.fwd_hot.eof;
     r.match_lo = a.fwd.match_lo;
     return r;
@@ -740,30 +753,17 @@ __device__ __noinline__ uint32_t slow_group(const uint16_t* trans, const uint8_t
 
 template <int FUSED>
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
-  // shared layout: [table: n_states KiB, 1 KiB aligned][per warp: 2 stages x 32 lanes x 80 B, 2 mbarriers]
-  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
+  // shared layout: [reverse hot table][forward hot table (FUSED == 1)], 256-byte aligned,
+  // then, 512-byte aligned, per warp 2 stages x 32 lanes x 64 B, then the mbarriers
+  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+  const uint32_t fbase = tbase + hot_table_bytes(a.hot.n);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t ring = tbase + (a.hot.n + (FUSED == 1 ? wa.fwd_hot.n : 0u)) * 1024u + wid * kRingWarpBytes;
-  const uint32_t bar0 = ring + 2 * kRingStageBytes;  // two 8-byte mbarriers
+  const uint32_t rings = (fbase + (FUSED == 1 ? hot_table_bytes(wa.fwd_hot.n) : 0u) + 511u) & ~511u;
+  const uint32_t ring = rings + wid * kRingWarpBytes;
+  const uint32_t bar0 = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
   {
-    const uint32_t n_ent = a.hot.n * 256u;
-    for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
-      const uint32_t r = i >> 8, b = i & 255u;
-      const uint32_t nx = a.hot.next256[i];
-      const uint32_t addr = tbase + (r << 10) + ((b ^ (r & 31u)) << 2);
-      const uint32_t val = fast_entry(tbase, nx);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
-    }
-    if (FUSED == 1) {
-      const uint32_t fbase = tbase + a.hot.n * 1024u;
-      const uint32_t n_fwd = wa.fwd_hot.n * 256u;
-      for (uint32_t i = threadIdx.x; i < n_fwd; i += blockDim.x) {
-        const uint32_t r = i >> 8, b = i & 255u;
-        const uint32_t addr = fbase + (r << 10) + ((b ^ (r & 31u)) << 2);
-        const uint32_t val = fast_entry(fbase, wa.fwd_hot.next256[i]);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
-      }
-    }
+    hot_stage(a.hot, tbase);
+    if (FUSED == 1) hot_stage(wa.fwd_hot, fbase);
     if (lane == 0) {
       mbar_init(bar0, 32);
       mbar_init(bar0 + 8, 32);
@@ -773,8 +773,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     }
     __syncthreads();
   }
-  const uint32_t thr = tbase + a.hot.match_lo * 1024u;
-  const uint32_t trap_e = fast_entry(tbase, 1);
+  const uint32_t thr = a.hot.match_lo;
   const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -790,10 +789,10 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     uint32_t cold = 0;  // != 0: the lane is outside the hot set, in this state of the full table (e sits in the trap row)
     auto enter = [&](uint32_t full) {
       const uint32_t h = a.hot.full2hot[full];
-      if (h != 0xFFFFu) { e = fast_entry(tbase, h); cold = 0; }
-      else { e = trap_e; cold = full; }
+      if (h != 0xFFFFu) { e = h; cold = 0; }
+      else { e = 1; cold = full; }
     };
-    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[(e - tbase) >> 10]; };
+    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[e]; };
     auto full_step = [&](uint32_t s, uint32_t byte) -> uint32_t { return a.dfa.trans[s * a.dfa.stride + a.dfa.classes[byte]]; };
     // one 64-byte group: table steps in shared memory; a lane that ends in the trap row
     // (it met a byte outside the hot set, or was cold already) redoes the group on the full table
@@ -801,14 +800,14 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       const uint32_t e0 = e;
       const uint32_t th = rec ? thr : 0xFFFFFFFFu;
       bhi = blo = 0;
-      rev_block16<16>(c3, e, bhi, th);
-      rev_block16<0>(c2, e, bhi, th);
-      rev_block16<16>(c1, e, blo, th);
-      rev_block16<0>(c0, e, blo, th);
-      if (((e - tbase) >> 10) == 1u) {
+      rev_block16<16>(tbase, c3, e, bhi, th);
+      rev_block16<0>(tbase, c2, e, bhi, th);
+      rev_block16<16>(tbase, c1, e, blo, th);
+      rev_block16<0>(tbase, c0, e, blo, th);
+      if (e == 1u) {
         uint64_t bits;
         const uint32_t s1 = slow_group(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo,
-                                       cold ? cold : a.hot.hot2full[(e0 - tbase) >> 10], c0, c1, c2, c3, &bits);
+                                       cold ? cold : a.hot.hot2full[e0], c0, c1, c2, c3, &bits);
         bhi = rec ? (uint32_t)(bits >> 32) : 0u;
         blo = rec ? (uint32_t)bits : 0u;
         enter(s1);
@@ -868,21 +867,22 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         const uint32_t o = a.seg + a.warm - 64u * (k + 1);
         const uint32_t row = (uint32_t)t0 + (o >= a.seg ? 1u : 0u);
         const uint32_t col = o >= a.seg ? o - a.seg : o;
-        const uint32_t dst = ring + (u & 1) * kRingStageBytes;
-#pragma unroll
-        for (uint32_t sub = 0; sub < 4; sub++) tma_box(dst + sub * 512u, &tmap, col + sub * 16u, row, bar);
+        tma_box(ring + (u & 1) * kRingStageBytes, &tmap, col, row, bar);
       };
       if (lane == 0) {
         issue_box(0);
         if (n_groups > 1) issue_box(1);
       }
       uint64_t* bw = a.bitmap + (hi >> 6);  // one past the segment's last bitmap word
-      const uint32_t my_b = ring + lane * 16u;
+      // the box lands row-major (row = lane, 64 bytes) with the 64B swizzle: 16-byte chunk j of
+      // row r sits at chunk j ^ ((r >> 1) & 3), which makes the four LDS.128 conflict-free
+      const uint32_t my_b = ring + lane * 64u;
+      const uint32_t sw = ((lane >> 1) & 3u) << 4;
       for (uint32_t k = 0; k < n_groups; k++) {
         const uint32_t u = uses_b + k;
         mbar_wait(barb + (u & 1) * 8, (u >> 1) & 1);
         const uint32_t b = my_b + (u & 1) * kRingStageBytes;
-        const uint4 c0 = lds128(b), c1 = lds128(b + 512), c2 = lds128(b + 1024), c3 = lds128(b + 1536);
+        const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
         if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
         uint32_t bhi, blo;
@@ -939,9 +939,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         if constexpr (FUSED == 2) {
           R.len = wa.fixed_len;
         } else {
-          R.tbase = tbase + a.hot.n * 1024u;
-          R.thr = R.tbase + wa.fwd_hot.match_lo * 1024u;
-          R.start_e = fast_entry(R.tbase, wa.fwd_hot.start);
+          R.tb = fbase;
+          R.thr = wa.fwd_hot.match_lo;
+          R.start_e = wa.fwd_hot.start;
           R.eof = wa.fwd_hot.eof;
           R.match_lo = wa.fwd.match_lo;
         }
@@ -1118,17 +1118,12 @@ __device__ __forceinline__ void window16(const uint8_t* p, uint32_t (&v)[4]) {
   const bool up = sh >= 32;
   v[0] = up ? x1 : x0; v[1] = up ? x2 : x1; v[2] = up ? x3 : x2; v[3] = up ? x4 : x3;
 }
-__device__ __forceinline__ uint32_t window_byte_idx(const uint32_t (&v)[4], int i) {  // (byte i) << 2, i compile-time
-  return (i & 3) == 0 ? (v[i >> 2] << 2) & 0x3FCu : (v[i >> 2] >> (8 * (i & 3) - 2)) & 0x3FCu;
+__device__ __forceinline__ uint32_t window_byte(const uint32_t (&v)[4], int i) {  // byte i, i compile-time
+  return (v[i >> 2] >> (8 * (i & 3))) & 0xFFu;
 }
-__device__ __forceinline__ void stage_hot(const HotView& h, uint32_t tbase) {
-  const uint32_t n_ent = h.n * 256u;
-  for (uint32_t i = threadIdx.x; i < n_ent; i += blockDim.x) {
-    const uint32_t row = i >> 8, b = i & 255u;
-    const uint32_t addr = tbase + (row << 10) + ((b ^ (row & 31u)) << 2);
-    const uint32_t val = fast_entry(tbase, h.next256[i]);
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(val));
-  }
+template <int I>
+__device__ __forceinline__ uint32_t window_next(uint32_t tb, const uint32_t (&v)[4], uint32_t e) {
+  return hot_next<(I & 3)>(tb, v[I >> 2], e);
 }
 __device__ __noinline__ bool slow_is_match_record(const DfaView* f, const uint8_t* p, uint64_t len) {
   uint32_t s = f->uniform_start ? f->start[32] : f->start[flags_forward(p, len, 0)];
@@ -1159,13 +1154,13 @@ __device__ __noinline__ bool slow_find_record(const DfaView* f, const DfaView* r
 // MODE 1: find (forward leftmost-first end, then the reverse longest automaton for the start).
 template <int MODE>
 __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
-  const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 1023u) & ~1023u;
-  const uint32_t rbase = fbase + a.fwd_hot.n * 1024u;
-  stage_hot(a.fwd_hot, fbase);
-  if (MODE == 1) stage_hot(a.rev_hot, rbase);
+  const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+  const uint32_t rbase = fbase + hot_table_bytes(a.fwd_hot.n);
+  hot_stage(a.fwd_hot, fbase);
+  if (MODE == 1) hot_stage(a.rev_hot, rbase);
   __syncthreads();
-  const uint32_t fthr = fbase + a.fwd_hot.match_lo * 1024u, flive = fbase + 2048u;
-  const uint32_t rthr = rbase + a.rev_hot.match_lo * 1024u, rlive = rbase + 2048u;
+  const uint32_t fthr = a.fwd_hot.match_lo, flive = 2;
+  const uint32_t rthr = a.rev_hot.match_lo, rlive = 2;
   const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // multiple of 32: warps stay on one ballot word
   const uint32_t lane = threadIdx.x & 31;
@@ -1178,7 +1173,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
       bool cold = false;
       // ---- forward ----
       const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
-      uint32_t e = fast_entry(fbase, h0 == 0xFFFFu ? 1u : h0);
+      uint32_t e = h0 == 0xFFFFu ? 1u : h0;
       uint64_t last = kNone;
       uint32_t mx = 0;
       uint64_t q = 0;
@@ -1186,7 +1181,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
       while (!done) {
         const uint64_t left = len - q;
         if (left == 0) {  // EOF step
-          if (e >= flive && a.fwd_hot.eof[(e - fbase) >> 10] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
+          if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
           break;
         }
         const uint8_t* wp = p + q;
@@ -1199,19 +1194,17 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           if (nb == 16) {
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                e = lds32(window_byte_idx(v, 4 * g + j) ^ e);
-                if (MODE == 0) mx = max(mx, e);
-                else if (e >= fthr) lj = 4 * g + j;
-              }
+              e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
+              e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
+              e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
+              e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
               if (e < flive || (MODE == 0 && mx >= fthr)) { done = true; break; }
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 15; i++) {
               if ((uint32_t)i < nb) {
-                e = lds32(window_byte_idx(v, i) ^ e);
+                e = hot_next_b(fbase, window_byte(v, i), e);
                 if (MODE == 0) mx = max(mx, e);
                 else if (e >= fthr) lj = i;
               }
@@ -1222,7 +1215,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           q += nb;
         } else {  // the last bytes of the whole buffer: byte loads
           for (uint64_t i = 0; i < left && !done; i++) {
-            e = fast_step(e, p[q + i]);
+            e = hot_next_b(fbase, p[q + i], e);
             if (MODE == 0) mx = max(mx, e);
             else if (e >= fthr) last = q + i;
             if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
@@ -1230,7 +1223,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           q += left;
         }
       }
-      if (e - fbase >= 1024u && e < flive && !(MODE == 0 && mx >= fthr)) cold = true;  // trap row
+      if (e == 1u && !(MODE == 0 && mx >= fthr)) cold = true;  // trap row
       if (MODE == 0) {
         hit = cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr;
       } else if (cold) {
@@ -1250,7 +1243,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           } else if (hr == 0xFFFFu) {
             rcold = true;
           } else {
-            uint32_t er = fast_entry(rbase, hr);
+            uint32_t er = hr;
             uint64_t at = me;
             bool rdone = false;
             while (at > 0 && !rdone) {
@@ -1264,7 +1257,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
 #pragma unroll
                 for (int i = 15; i >= 0; i--) {
                   if ((uint32_t)(15 - i) < nb && !rdone) {
-                    er = lds32(window_byte_idx(v, i) ^ er);
+                    er = hot_next_b(rbase, window_byte(v, i), er);
                     if (er >= rthr) lj = i;
                     if (er < rlive) rdone = true;
                   }
@@ -1274,14 +1267,14 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
               } else {
                 for (uint32_t i = 0; i < nb && !rdone; i++) {
                   at--;
-                  er = fast_step(er, p[at]);
+                  er = hot_next_b(rbase, p[at], er);
                   if (er >= rthr) start = at + 1;
                   if (er < rlive) rdone = true;
                 }
               }
             }
-            if (er - rbase >= 1024u && er < rlive) rcold = true;
-            else if (!rdone && a.rev_hot.eof[(er - rbase) >> 10] >= a.rev.match_lo) start = 0;
+            if (er == 1u) rcold = true;
+            else if (!rdone && a.rev_hot.eof[er] >= a.rev.match_lo) start = 0;
           }
         }
         if (rcold) {
@@ -1336,7 +1329,7 @@ __global__ void set_matches_batch(BatchArgs a) {
       const uint32_t nb = len - q >= 16 ? 16u : (uint32_t)(len - q);
 #pragma unroll
       for (int i = 0; i < 16; i++)
-        if ((uint32_t)i < nb && s != 0) consume(T.step(s, window_byte_idx(v, i) >> 2));
+        if ((uint32_t)i < nb && s != 0) consume(T.step(s, window_byte(v, i)));
       q += nb;
     } else {
       consume(T.step(s, p[q]));
