@@ -288,7 +288,7 @@ static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t block
 }
 
 static size_t fast_scan_smem(size_t table_bytes) {
-  return table_bytes + 1024 + (1024 / 32) * (2 * 2048 + 32);  // kernels.cu: tables, 512-aligned rings, mbarriers
+  return table_bytes + 1024 + (1024 / 32) * (2 * 2048 + 64);  // kernels.cu kBoxStages, kRingBarBytes  // kernels.cu: tables, 512-aligned rings, mbarriers
 }
 
 static uint32_t pick_warm(const Regex& re) {
@@ -467,7 +467,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   cudaEvent_t ev[3];
   for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
   RB_CUDA(cudaEventRecord(ev[0], st));
-  const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi, revall->hot.n != 0);
+  const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi,
+                                   revall->hot.n != 0 && fast_scan_smem(hot_bytes(revall->hot.n)) <= 227 * 1024);
   // runner: 2 = fixed-length (no haystack access), 1 = byte-indexed shared-memory table
   // (uniform start state, 8-byte aligned text), 0 = generic
   const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;

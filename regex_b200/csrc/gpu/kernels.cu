@@ -152,8 +152,9 @@ __device__ __forceinline__ void rev_block16(uint32_t tb, const uint4& v, uint32_
 // reads its own 64 bytes with four LDS.128 (conflict-free in the 2-D TMA layout below).
 constexpr uint32_t kRingLaneStride = 64;                       // one 64-byte group per lane
 constexpr uint32_t kRingStageBytes = 32 * kRingLaneStride;     // per warp
-constexpr uint32_t kRingWarpBytes = 2 * kRingStageBytes;       // two stages; 512-byte aligned (TMA 64B-swizzle pattern)
-constexpr uint32_t kRingBarBytes = 32;                         // four 8-byte mbarriers per warp, after all rings
+constexpr uint32_t kBoxStages = 2;                             // ring depth (3 measured slower: 2.15 -> 2.59 ms on 4 GiB, less L1 left)
+constexpr uint32_t kRingWarpBytes = kBoxStages * kRingStageBytes;  // 512-byte aligned (TMA 64B-swizzle pattern)
+constexpr uint32_t kRingBarBytes = 64;                         // 2 + kBoxStages 8-byte mbarriers per warp, after all rings
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -767,8 +768,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     if (lane == 0) {
       mbar_init(bar0, 32);
       mbar_init(bar0 + 8, 32);
-      mbar_init(bar0 + 16, 1);  // boxed (2-D TMA) mode: one elected lane arrives for the warp
-      mbar_init(bar0 + 24, 1);
+      for (uint32_t sidx = 0; sidx < kBoxStages; sidx++) mbar_init(bar0 + 16 + 8 * sidx, 1);  // boxed (2-D TMA) mode: one elected lane arrives for the warp
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
   const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t rounds = (total + stride - 1) / stride;  // uniform: every warp makes every round
   uint32_t uses = 0;  // ring uses so far (same for the whole warp): stage = uses & 1, parity = (uses >> 1) & 1
-  uint32_t uses_b = 0;  // same for the boxed-mode barriers
+  uint32_t slot_b = 0, par_b = 0;  // boxed mode: ring slot and barrier parity of the next group to consume
   for (uint64_t round = 0; round < rounds; round++) {
     const uint64_t idx = first + round * stride;
     const bool live = idx < total;
@@ -859,19 +859,19 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       // uniform and one lane drives the TMA for all 32.
       const uint32_t n_groups = (a.seg + a.warm) >> 6, n_warm = a.warm >> 6;
       const uint32_t barb = bar0 + 16;
-      auto issue_box = [&](uint32_t k) {  // lane 0 only
-        const uint32_t u = uses_b + k;
-        const uint32_t bar = barb + (u & 1) * 8;
+      auto issue_box = [&](uint32_t k, uint32_t slot) {  // lane 0 only
+        const uint32_t bar = barb + slot * 8;
         mbar_arrive_tx(bar, 2048);
         // byte offset of the group inside row-space: segment bytes then the neighbour row's warm-up bytes
         const uint32_t o = a.seg + a.warm - 64u * (k + 1);
         const uint32_t row = (uint32_t)t0 + (o >= a.seg ? 1u : 0u);
         const uint32_t col = o >= a.seg ? o - a.seg : o;
-        tma_box(ring + (u & 1) * kRingStageBytes, &tmap, col, row, bar);
+        tma_box(ring + slot * kRingStageBytes, &tmap, col, row, bar);
       };
       if (lane == 0) {
-        issue_box(0);
-        if (n_groups > 1) issue_box(1);
+#pragma unroll
+        for (uint32_t j = 0; j < kBoxStages; j++)
+          if (j < n_groups) issue_box(j, (slot_b + j) % kBoxStages);
       }
       uint64_t* bw = a.bitmap + (hi >> 6);  // one past the segment's last bitmap word
       // the box lands row-major (row = lane, 64 bytes) with the 64B swizzle: 16-byte chunk j of
@@ -879,9 +879,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       const uint32_t my_b = ring + lane * 64u;
       const uint32_t sw = ((lane >> 1) & 3u) << 4;
       for (uint32_t k = 0; k < n_groups; k++) {
-        const uint32_t u = uses_b + k;
-        mbar_wait(barb + (u & 1) * 8, (u >> 1) & 1);
-        const uint32_t b = my_b + (u & 1) * kRingStageBytes;
+        mbar_wait(barb + slot_b * 8, par_b);
+        const uint32_t b = my_b + slot_b * kRingStageBytes;
         const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
         if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
@@ -891,11 +890,11 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
           *--bw = ((uint64_t)bhi << 32) | blo;
           if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
         }
-        // every lane has its 64 bytes in registers: lane 0 refills the slot for the group after next
+        // every lane has its 64 bytes in registers: lane 0 refills the slot kBoxStages groups ahead
         __syncwarp();
-        if (lane == 0 && k + 2 < n_groups) issue_box(k + 2);
+        if (lane == 0 && k + kBoxStages < n_groups) issue_box(k + kBoxStages, slot_b);
+        if (++slot_b == kBoxStages) { slot_b = 0; par_b ^= 1; }
       }
-      uses_b += n_groups;
     } else {
     auto issue = [&](uint32_t k) {    // every lane arrives; lanes with data also copy
       const uint32_t u = uses + k;
