@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "launch.h"
 
@@ -343,6 +344,8 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
   a.flag0 = (uint8_t*)(counters + 24);
   a.utf8_boundaries = utf8_mask;
+  if (const char* pr = getenv("RB200_PROBE_SKIP_TABLE")) a.probe_skip_table = atoi(pr);
+  if (const char* pr = getenv("RB200_RING_CP_ASYNC")) a.ring_cp_async = atoi(pr);
   a.hot = rev->hot;
   size_t smem;
   uint32_t block;

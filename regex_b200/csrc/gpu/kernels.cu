@@ -737,6 +737,10 @@ template __global__ void compact_spans<2>(WalkArgs);
 // and ONE elected lane issues four [16 B x 32 rows] box loads per 64-byte group for the
 // whole warp (per-lane 64-byte bulk copies were TMA-issue bound: a third of all issued
 // instructions were mbarrier polls).  Ragged ends and redo lists use per-lane bulk copies.
+// one whole 32-byte sector of bitmap words {w0 (lowest address), w1, w2, w3}; p is 32-byte aligned
+__device__ __forceinline__ void st_sector(uint64_t* p, uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3) {
+  asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(w0), "l"(w1), "l"(w2), "l"(w3) : "memory");
+}
 // One 64-byte group on the full class-indexed table (global memory), highest address
 // first: the path a lane of scan_rev_fast takes while it is outside the hot set.
 __device__ __noinline__ uint32_t slow_group(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo, uint32_t s,
@@ -851,9 +855,65 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     // (full segments, full warm-up), and all rows (incl. the warm-up row) inside the map.
     const uint64_t t0 = __shfl_sync(0xffffffffu, t, 0);
     const bool uniform = live && !a.redo_list && hi - lo == a.seg && i == hi + a.warm && t == t0 + lane;
-    const bool boxed = a.tmap_rows != 0 && __all_sync(0xffffffffu, uniform) && t0 + 33 <= a.tmap_rows && a.warm <= a.seg;
+    const bool all_uniform = __all_sync(0xffffffffu, uniform) && a.warm <= a.seg;
+    const bool boxed = !a.ring_cp_async && a.tmap_rows != 0 && all_uniform && t0 + 33 <= a.tmap_rows;
+    const bool cp_ring = a.ring_cp_async && all_uniform;
     uint64_t nz = 0;  // FUSED: which bitmap words of this segment are non-zero
-    if (boxed) {
+    if (cp_ring) {
+      // Same geometry as the boxed path below, but the ring is filled by the warp itself:
+      // four cp.async (LDGSTS) warp instructions per 64-byte group, lane j copying 16-byte
+      // chunk (j & 3) of rows (j >> 2) + 8 i -- eight 64-byte pieces per instruction.
+      const uint32_t n_groups = (a.seg + a.warm) >> 6, n_warm = a.warm >> 6;
+      const uint32_t r0 = lane >> 2, ch = lane & 3u;
+      // row r of the warp starts at text + base + (t0 + r) * seg; offsets past seg run into the next row (the warm-up bytes)
+      const uint8_t* src0 = a.text + a.base + (t0 + r0) * (uint64_t)a.seg + ch * 16u;
+      auto issue_cp = [&](uint32_t k, uint32_t slot) {
+        const uint32_t o = a.seg + a.warm - 64u * (k + 1);
+#pragma unroll
+        for (uint32_t i4 = 0; i4 < 4; i4++) {
+          const uint32_t r = r0 + 8u * i4;
+          const uint32_t dst = ring + slot * kRingStageBytes + r * 64u + ((ch ^ ((r >> 1) & 3u)) << 4);
+          const uint8_t* src = src0 + (uint64_t)(8u * i4) * a.seg + o;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+      };
+      issue_cp(0, 0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (n_groups > 1) issue_cp(1, 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      uint64_t* bw = a.bitmap + (hi >> 6);
+      uint64_t pw1 = 0, pw2 = 0, pw3 = 0;  // the previous three words (higher addresses) of the current sector
+      const bool sector_stores = (a.seg & 255u) == 0;
+      const uint32_t my_b = ring + lane * 64u;
+      const uint32_t sw = ((lane >> 1) & 3u) << 4;
+      for (uint32_t k = 0; k < n_groups; k++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t b = my_b + (k & 1) * kRingStageBytes;
+        const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
+        if (k == n_warm) a.guess[t] = (uint16_t)full_state();
+        const bool rec = k >= n_warm;
+        uint32_t bhi, blo;
+        if (a.probe_skip_table) { bhi = c0.x ^ c1.y ^ c2.z; blo = c3.w ^ c0.y; }
+        else do_group(c0, c1, c2, c3, rec, bhi, blo);
+        if (a.probe_skip_table == 2) { if ((bhi | blo) == 0x12345u) *bw = 1; }  // probe: no bitmap stores either
+        else if (rec) {
+          // Bitmap words leave as whole 32-byte sectors (four words, every fourth group):
+          // an 8-byte store per group is a partial-sector write from each lane, and those
+          // capped the whole kernel at 3.0 TB/s (5.0 TB/s with the stores removed).
+          const uint64_t wv = ((uint64_t)bhi << 32) | blo;
+          --bw;
+          if (!sector_stores) *bw = wv;
+          else if (((k - n_warm) & 3u) == 3u) st_sector(bw, wv, pw1, pw2, pw3);
+          pw3 = pw2; pw2 = pw1; pw1 = wv;
+          if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
+        }
+        __syncwarp();  // every lane has its 64 bytes in registers: the slot can be refilled
+        if (k + 2 < n_groups) issue_cp(k + 2, k & 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (boxed) {
       // Tight loop for the common geometry: every lane scans one full segment plus the
       // warm-up, so group counts, the warm-up/record split and the ring slots are warp
       // uniform and one lane drives the TMA for all 32.
@@ -873,7 +933,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         for (uint32_t j = 0; j < kBoxStages; j++)
           if (j < n_groups) issue_box(j, (slot_b + j) % kBoxStages);
       }
-      uint64_t* bw = a.bitmap + (hi >> 6);  // one past the segment's last bitmap word
+      uint64_t* bw = a.bitmap + (hi >> 6);
+      uint64_t pw1 = 0, pw2 = 0, pw3 = 0;  // the previous three words (higher addresses) of the current sector
+      const bool sector_stores = (a.seg & 255u) == 0;  // one past the segment's last bitmap word
       // the box lands row-major (row = lane, 64 bytes) with the 64B swizzle: 16-byte chunk j of
       // row r sits at chunk j ^ ((r >> 1) & 3), which makes the four LDS.128 conflict-free
       const uint32_t my_b = ring + lane * 64u;
@@ -885,9 +947,18 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
         uint32_t bhi, blo;
-        do_group(c0, c1, c2, c3, rec, bhi, blo);
-        if (rec) {
-          *--bw = ((uint64_t)bhi << 32) | blo;
+        if (a.probe_skip_table) { bhi = c0.x ^ c1.y ^ c2.z; blo = c3.w ^ c0.y; }
+        else do_group(c0, c1, c2, c3, rec, bhi, blo);
+        if (a.probe_skip_table == 2) { if ((bhi | blo) == 0x12345u) *bw = 1; }  // probe: no bitmap stores either
+        else if (rec) {
+          // Bitmap words leave as whole 32-byte sectors (four words, every fourth group):
+          // an 8-byte store per group is a partial-sector write from each lane, and those
+          // capped the whole kernel at 3.0 TB/s (5.0 TB/s with the stores removed).
+          const uint64_t wv = ((uint64_t)bhi << 32) | blo;
+          --bw;
+          if (!sector_stores) *bw = wv;
+          else if (((k - n_warm) & 3u) == 3u) st_sector(bw, wv, pw1, pw2, pw3);
+          pw3 = pw2; pw2 = pw1; pw1 = wv;
           if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
         }
         // every lane has its 64 bytes in registers: lane 0 refills the slot kBoxStages groups ahead

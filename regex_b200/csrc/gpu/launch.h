@@ -30,6 +30,8 @@ struct ScanArgs {
   const uint32_t* redo_list;  // nullable: only these segments, entry = neighbour's fin
   const uint32_t* n_redo;
   int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
+  int ring_cp_async;    // feed the ring with per-warp cp.async (LDGSTS) instead of TMA boxes
+  int probe_skip_table; // measurement probe (RB200_PROBE_SKIP_TABLE=1): move the bytes, skip the automaton
 };
 
 struct WalkArgs {
