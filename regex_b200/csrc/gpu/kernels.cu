@@ -13,6 +13,10 @@ __device__ __forceinline__ uint32_t word_byte(const uint4& v, int j) {  // byte 
   const uint32_t w = (j >> 2) == 0 ? v.x : (j >> 2) == 1 ? v.y : (j >> 2) == 2 ? v.z : v.w;
   return (w >> (8 * (j & 3))) & 0xFFu;
 }
+// one whole 32-byte sector {w0 (lowest address), w1, w2, w3}; p is 32-byte aligned
+__device__ __forceinline__ void st_sector(uint64_t* p, uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3) {
+  asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(w0), "l"(w1), "l"(w2), "l"(w3) : "memory");
+}
 __device__ __forceinline__ uint32_t pick_start_rev(const DfaView& d, const uint8_t* t, uint64_t n, uint64_t at) {
   return d.uniform_start ? d.start[32] : d.start[flags_reverse(t, n, at)];
 }
@@ -565,12 +569,28 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
   uint32_t total = 0;
   uint64_t fc = kNone;
+  // Spans leave two at a time as whole 32-byte sectors when the destination allows it
+  // (staging areas do): the even span of a pair waits in registers for the odd one.
+  const bool pair_stores = ((uintptr_t)o & 31) == 0;
+  uint64_t held_s = 0, held_e = 0;
   auto emit = [&](uint64_t ms, uint64_t e) {
-    if (total < room) {
-      if (((uintptr_t)o & 15) == 0) *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)total) = make_ulonglong2(ms, e);
-      else { o[2 * (uint64_t)total] = ms; o[2 * (uint64_t)total + 1] = e; }
+    if (pair_stores) {
+      if (!(total & 1u)) { held_s = ms; held_e = e; }
+      else if (total < room) st_sector(o + 2 * (uint64_t)(total - 1), held_s, held_e, ms, e);
+      else if (total - 1 < room) *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)(total - 1)) = make_ulonglong2(held_s, held_e);
+    } else if (total < room) {
+      if (((uintptr_t)o & 15) == 0) {
+        *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)total) = make_ulonglong2(ms, e);
+      } else {
+        o[2 * (uint64_t)total] = ms;
+        o[2 * (uint64_t)total + 1] = e;
+      }
     }
     total++;
+  };
+  auto flush = [&]() {  // the unpaired last span
+    if (pair_stores && (total & 1u) && total - 1 < room)
+      *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)(total - 1)) = make_ulonglong2(held_s, held_e);
   };
   if (c.p == kNone) { *first_cand = fc; return 0; }
   if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
@@ -618,6 +638,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
       rem &= ~0ull << ew;
     }
   }
+  flush();
   *first_cand = fc;
   return total;
 }
@@ -714,13 +735,28 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
     __syncwarp();
     uint32_t todo = __ballot_sync(0xffffffffu, my_cnt != 0 && my_cnt <= a.stage_cap);
     while (todo) {
-      const int j = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint64_t cnt = __shfl_sync(0xffffffffu, my_cnt, j);
-      const uint64_t at = __shfl_sync(0xffffffffu, my_at, j);
-      const ulonglong2* src = stage + (g * 32 + j) * (uint64_t)a.stage_cap;
-      for (uint64_t i = lane; i < cnt; i += 32)
-        if (at + i < a.cap) dst[at + i] = src[i];
+      // four chunks per trip: their loads are in flight together (one chunk at a time was
+      // a dependent load -> store chain per lane)
+      int j[4];
+      uint64_t cnt[4], at[4];
+      ulonglong2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        j[u] = todo ? __ffs(todo) - 1 : -1;
+        if (todo) todo &= todo - 1;
+        cnt[u] = j[u] >= 0 ? __shfl_sync(0xffffffffu, my_cnt, j[u] & 31) : 0;
+        at[u] = __shfl_sync(0xffffffffu, my_at, j[u] & 31);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (lane < cnt[u]) v[u] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + lane];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (lane < cnt[u] && at[u] + lane < a.cap) dst[at[u] + lane] = v[u];
+#pragma unroll
+      for (int u = 0; u < 4; u++)  // chunks with more than 32 staged spans
+        for (uint64_t i = lane + 32; i < cnt[u]; i += 32)
+          if (at[u] + i < a.cap) dst[at[u] + i] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + i];
     }
   }
 }
@@ -737,10 +773,6 @@ template __global__ void compact_spans<2>(WalkArgs);
 // and ONE elected lane issues four [16 B x 32 rows] box loads per 64-byte group for the
 // whole warp (per-lane 64-byte bulk copies were TMA-issue bound: a third of all issued
 // instructions were mbarrier polls).  Ragged ends and redo lists use per-lane bulk copies.
-// one whole 32-byte sector of bitmap words {w0 (lowest address), w1, w2, w3}; p is 32-byte aligned
-__device__ __forceinline__ void st_sector(uint64_t* p, uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3) {
-  asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(w0), "l"(w1), "l"(w2), "l"(w3) : "memory");
-}
 // One 64-byte group on the full class-indexed table (global memory), highest address
 // first: the path a lane of scan_rev_fast takes while it is outside the hot set.
 __device__ __noinline__ uint32_t slow_group(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo, uint32_t s,
