@@ -188,7 +188,7 @@ class _Compiled:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:  # module globals are gone at interpreter shutdown
             _lib.rure_free(h)
             self._h = None
 
@@ -377,7 +377,7 @@ class _SetBase:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:
             _lib.rure_set_free(h)
             self._h = None
 

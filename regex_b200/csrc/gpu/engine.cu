@@ -620,7 +620,11 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  const uint32_t seg = tuning.seg ? tuning.seg : 1024;
+  // fast path (scan_fwd_fast): single pattern, hot table, 16-byte aligned haystack and start
+  const bool fast_ok = !want_masks && fwd->hot.n != 0 && !tuning.force_generic && tuning.tensor_tma && encode_tiled() &&
+                       ((uintptr_t)d_text & 15) == 0 && (start & 63) == 0 &&
+                       fast_scan_smem(hot_bytes(fwd->hot.n)) <= 227 * 1024;
+  const uint32_t seg = tuning.seg ? tuning.seg : (fast_ok ? 4096 : 1024);
   const uint64_t n_seg = (n + 1 - start + seg - 1) / seg;
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   const uint32_t mw = fwd->view.mask_words;
@@ -634,6 +638,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   a.n_seg = n_seg;
   a.seg = seg;
   a.warm = pick_warm(*this);
+  if (fast_ok) a.warm = (a.warm + 63) / 64 * 64;
   a.seg_first = (uint64_t*)seg_first_.ensure(n_seg * 8);
   a.seg_mask = want_masks ? (uint64_t*)seg_mask_.ensure(n_seg * 8 * mw) : nullptr;
   a.guess = (uint16_t*)guess_.ensure(n_seg * 2);
@@ -643,6 +648,29 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   if (!a.seg_first || (want_masks && !a.seg_mask) || !a.guess || !a.fin || !redo || !counters)
     return fail("out of device memory (scan scratch)");
   RB_CUDA(allow_smem(scan_fwd_reduce, smem));
+  // whole warps of full segments go to the fast kernel; segment 0, the ragged end and the EOF step stay generic
+  const uint64_t n_full = (n - start) / seg;
+  if (fast_ok && seg % 64 == 0 && a.warm <= seg && n_full >= 34) {
+    const uint64_t skip_lo = 1, skip_hi = 1 + (n_full - 1) / 32 * 32;
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof tmap);
+    cuuint64_t dims[2] = {seg, skip_hi - skip_lo + 1};  // row 0 = segment skip_lo - 1 (warm-up source of the first warp)
+    cuuint64_t strides[1] = {seg};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)(d_text + start + (skip_lo - 1) * (uint64_t)seg), dims, strides,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      a.hot = fwd->hot;
+      a.skip_lo = skip_lo;
+      a.skip_hi = skip_hi;
+      const size_t fsm = fast_scan_smem(hot_bytes(fwd->hot.n));
+      RB_CUDA(cudaFuncSetAttribute(scan_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      scan_fwd_fast<<<grid_for(skip_hi - skip_lo, 1024, 1), 1024, fsm, st>>>(a, tmap);
+      RB_LAUNCH_CHECK("scan_fwd_fast");
+    }
+  }
   scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
   RB_LAUNCH_CHECK("scan_fwd_reduce");
   for (;;) {

@@ -200,6 +200,7 @@ __global__ void scan_fwd_reduce(ScanArgs a) {
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
+    if (!a.redo_list && t >= a.skip_lo && t < a.skip_hi) continue;  // scan_fwd_fast's share
     const uint64_t lo = a.base + t * a.seg;
     const uint64_t hi = min(lo + a.seg, a.n + 1);
     uint32_t s;
@@ -612,7 +613,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
       rem &= rem - 1;
       cur = bm[cw];
       if (cw == (r >> 6)) cur &= ~0ull << (r & 63);
-      continue;
+      if (cur == 0) continue;  // rare; otherwise fall through: one trip per match keeps the lanes of a warp in phase
     }
     const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
     const uint64_t s = cb + sr + 1;
@@ -1070,6 +1071,121 @@ template __global__ void scan_rev_fast<1>(ScanArgs, WalkArgs, const __grid_const
 template __global__ void scan_rev_fast<2>(ScanArgs, WalkArgs, const __grid_constant__ CUtensorMap);
 
 
+
+
+// ------------------------------------------------------------- scan_fwd_fast --
+// Forward counterpart of scan_rev_fast for whole-haystack is_match / shortest_match:
+// hot table in shared memory, the haystack through the 2-D TMA ring, per segment the first
+// match END (positions as in scan_fwd_reduce), the state assumed at the segment's first
+// byte (guess) and the exact state after its last (fin).  It takes the warps of 32
+// consecutive full segments [skip_lo, skip_hi); scan_fwd_reduce does the ragged edges, the
+// EOF step and the redo rounds.
+template <int BIT0>
+__device__ __forceinline__ void fwd_word(uint32_t tb, uint32_t w, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  e = hot_next<0>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 0);
+  e = hot_next<1>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 1);
+  e = hot_next<2>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 2);
+  e = hot_next<3>(tb, w, e); if (e >= thr) bits |= 1u << (BIT0 + 3);
+}
+template <int BIT0>
+__device__ __forceinline__ void fwd_block16(uint32_t tb, const uint4& v, uint32_t& e, uint32_t& bits, uint32_t thr) {
+  fwd_word<BIT0 + 0>(tb, v.x, e, bits, thr);
+  fwd_word<BIT0 + 4>(tb, v.y, e, bits, thr);
+  fwd_word<BIT0 + 8>(tb, v.z, e, bits, thr);
+  fwd_word<BIT0 + 12>(tb, v.w, e, bits, thr);
+}
+__device__ __noinline__ uint32_t slow_group_fwd(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo, uint32_t s,
+                                                uint4 c0, uint4 c1, uint4 c2, uint4 c3, uint64_t* bits_out) {
+  const uint32_t w[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+  uint64_t bits = 0;
+  for (int j = 0; j < 64; j++) {
+    const uint32_t byte = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+    s = trans[s * stride + classes[byte]];
+    if (s >= match_lo) bits |= 1ull << j;
+  }
+  *bits_out = bits;
+  return s;
+}
+__global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
+  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t rings = (tbase + hot_table_bytes(a.hot.n) + 511u) & ~511u;
+  const uint32_t ring = rings + wid * kRingWarpBytes;
+  const uint32_t barb = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
+  hot_stage(a.hot, tbase);
+  if (lane == 0) {
+    for (uint32_t sidx = 0; sidx < kBoxStages; sidx++) mbar_init(barb + 8 * sidx, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t thr = a.hot.match_lo;
+  const uint32_t n_groups = (a.seg + a.warm) >> 6, n_warm = a.warm >> 6;
+  const uint64_t n_warps = (a.skip_hi - a.skip_lo) >> 5;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t warp_stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t slot_b = 0, par_b = 0;
+  const uint32_t my_b = ring + lane * 64u;
+  const uint32_t sw = ((lane >> 1) & 3u) << 4;
+  for (uint64_t wq = warp0; wq < n_warps; wq += warp_stride) {
+    const uint64_t t0 = a.skip_lo + wq * 32, t = t0 + lane;
+    const uint64_t lo = a.base + t * a.seg;  // this lane scans [lo - warm, lo) unrecorded, then [lo, lo + seg)
+    uint32_t e, cold = 0;
+    auto enter = [&](uint32_t full) {
+      const uint32_t h = a.hot.full2hot[full];
+      if (h != 0xFFFFu) { e = h; cold = 0; }
+      else { e = 1; cold = full; }
+    };
+    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[e]; };
+    enter(pick_start_fwd(a.dfa, a.text, a.n, lo - a.warm));
+    auto issue_box = [&](uint32_t k, uint32_t slot) {  // lane 0 only
+      const uint32_t bar = barb + slot * 8;
+      mbar_arrive_tx(bar, 2048);
+      // row-space offset of group k relative to row t0: the warm-up groups lie at the end of the previous row
+      const uint32_t o = 64u * k;
+      const bool prev = o < a.warm;
+      const uint32_t row = (uint32_t)(t0 - a.skip_lo) + (prev ? 0u : 1u);  // tensor row 0 = segment skip_lo - 1
+      const uint32_t col = prev ? a.seg - a.warm + o : o - a.warm;
+      tma_box(ring + slot * kRingStageBytes, &tmap, col, row, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+      for (uint32_t j = 0; j < kBoxStages; j++)
+        if (j < n_groups) issue_box(j, (slot_b + j) % kBoxStages);
+    }
+    uint64_t first = kNone;
+    for (uint32_t k = 0; k < n_groups; k++) {
+      mbar_wait(barb + slot_b * 8, par_b);
+      const uint32_t b = my_b + slot_b * kRingStageBytes;
+      const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
+      if (k == n_warm) a.guess[t] = (uint16_t)full_state();
+      const bool rec = k >= n_warm;
+      const uint32_t e0 = e;
+      const uint32_t th = rec ? thr : 0xFFFFFFFFu;
+      uint32_t blo = 0, bhi = 0;
+      fwd_block16<0>(tbase, c0, e, blo, th);
+      fwd_block16<16>(tbase, c1, e, blo, th);
+      fwd_block16<0>(tbase, c2, e, bhi, th);
+      fwd_block16<16>(tbase, c3, e, bhi, th);
+      if (e == 1u) {  // left the hot set (or was cold): redo the group on the full table
+        uint64_t bits;
+        const uint32_t s1 = slow_group_fwd(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo, cold ? cold : a.hot.hot2full[e0],
+                                           c0, c1, c2, c3, &bits);
+        bhi = rec ? (uint32_t)(bits >> 32) : 0u;
+        blo = rec ? (uint32_t)bits : 0u;
+        enter(s1);
+      }
+      if (first == kNone && (bhi | blo)) {
+        const uint64_t bits = ((uint64_t)bhi << 32) | blo;
+        first = lo + 64ull * (k - n_warm) + (uint64_t)(__ffsll((long long)bits) - 1);
+      }
+      __syncwarp();
+      if (lane == 0 && k + kBoxStages < n_groups) issue_box(k + kBoxStages, slot_b);
+      if (++slot_b == kBoxStages) { slot_b = 0; par_b ^= 1; }
+    }
+    a.fin[t] = (uint16_t)full_state();
+    a.seg_first[t] = first;
+  }
+}
 
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {

@@ -30,6 +30,7 @@ struct ScanArgs {
   const uint32_t* redo_list;  // nullable: only these segments, entry = neighbour's fin
   const uint32_t* n_redo;
   int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
+  uint64_t skip_lo, skip_hi;  // scan_fwd_reduce: segments [skip_lo, skip_hi) belong to scan_fwd_fast
   int ring_cp_async;    // feed the ring with per-warp cp.async (LDGSTS) instead of TMA boxes
   int probe_skip_table; // measurement probe (RB200_PROBE_SKIP_TABLE=1): move the bytes, skip the automaton
 };
@@ -89,6 +90,7 @@ __global__ void scan_rev_bitmap(ScanArgs a);
 template <int FUSED>
 __global__ void scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap);
 __global__ void scan_fwd_reduce(ScanArgs a);
+__global__ void scan_fwd_fast(ScanArgs a, const __grid_constant__ CUtensorMap tmap);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
                                 uint32_t* redo_list, uint32_t* n_redo);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,

@@ -145,6 +145,59 @@ def test_unicode_classes_hot_table_and_cold_fallback(seg):
             assert _spans(r.find_all(text)) == exp, (pat, utf8, "generic")
 
 
+@pytest.mark.parametrize("k", [25, 40, 60])
+def test_word_alternations_mid_size_tables(k):
+    """Alternations of k frequent words: 86 / 126 / 188 reverse-DFA states.  These sit on the
+    shared-memory hot path with one-byte state ids above 127 (k = 60) and, from k = 40 on,
+    with tables too large to share the CTA with a fused walk (separate walk kernel)."""
+    from collections import Counter
+    text = sherlock_text()[:300000]
+    words = [w.decode() for w in sherlock_text().split() if w.isalpha() and len(w) >= 4]
+    top = [w for w, _ in Counter(words).most_common(400)]
+    pat = "|".join(top[10:10 + k])
+    exp = O.OracleRegex(pat).find_iter(text)
+    r = R.BytesRegex(pat)
+    assert _spans(r.find_all(text)) == exp
+    lines = text.split(b"\n")[:2000]
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.uint64)
+    found, spans = r.find_batch(b"".join(lines), off)
+    o = O.OracleRegex(pat)
+    for i, l in enumerate(lines):
+        m = o.find_at(l)
+        assert bool(found[i]) == (m is not None), i
+        if m:
+            assert tuple(int(v) for v in spans[i]) == m, i
+    r.force_generic(True)
+    assert _spans(r.find_all(text)) == exp
+
+
+def test_forward_scan_fast_path_shortest_match():
+    """Whole-haystack is_match / shortest_match: scan_fwd_fast (hot table + TMA ring) for the
+    full segments, scan_fwd_reduce for the edges and the EOF step; match placed early, late,
+    across segment boundaries, only at EOF, and after non-ASCII bytes (cold fallback)."""
+    base = sherlock_text()[:400000].replace(b"Watson", b"W4tson").replace(b"ing", b"1ng")
+    cases = []
+    for pos in (0, 63, 4095, 4096, 4097, 131072 - 3, 250000, len(base) - 6):
+        t = bytearray(base)
+        t[pos:pos + 6] = b"Watson"
+        cases.append(bytes(t))
+    cases.append(base)                                   # no match at all
+    cases.append(base + b"Watson")                       # match ends exactly at EOF
+    cases.append(base[:200000] + "ünï 日本 ".encode() * 50 + base[200000:300000] + b"xx Watson yy")
+    pats = ["Watson", r"Wat\w+", r"[a-zA-Z]+ing", r"Watson$", r"(?m)^Watson", r"\w+son\s", r"W.{2,5}n"]
+    for text in cases:
+        for pat in pats:
+            o = O.OracleRegex(pat)
+            for cls in (R.BytesRegex,):
+                r = cls(pat)
+                for start in (0, 64, 4096, 199936):
+                    exp = o.shortest_match_at(text, start)
+                    assert r.shortest_match_at(text, start) == exp, (pat, start, exp)
+                    assert r.is_match_at(text, start) == (exp is not None), (pat, start)
+                r.force_generic(True)
+                assert r.shortest_match(text) == o.shortest_match_at(text, 0), (pat, "generic")
+
+
 def test_random_patterns_vs_oracle():
     """Seeded fuzz over a small regex grammar on a 4-letter alphabet (dense matches)."""
     rng = np.random.Generator(np.random.PCG64(0xB200))
