@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace("/", "_") + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("RB200_EXTRA_NVCC_FLAGS", "").split(), "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -53,7 +53,7 @@ void* DeviceBuf::ensure(size_t bytes) {
 // Hot tables of up to this many rows (288 bytes per row, one-byte successor ids) are
 // staged in shared memory by the fast kernels.
 static constexpr uint32_t kFastStates = 200;
-static size_t hot_bytes(uint32_t rows) { return ((size_t)rows * 288 + 255) / 256 * 256; }  // kernels.cu hot_table_bytes
+static size_t hot_bytes(uint32_t rows) { return ((size_t)rows * RB_HOT_ROW + 255) / 256 * 256; }  // kernels.cu hot_table_bytes
 
 struct Regex::DeviceDfa {
   DfaView view;

@@ -102,7 +102,7 @@ __global__ void scan_rev_bitmap(ScanArgs a) {
 //     IMAD (state * 288 + that) + LDS.U8; the state IS the row index, match rows sit
 //     above non-match rows ("e >= match_lo"), row 0 = dead, row 1 = trap.
 //   - bits are assembled in registers, one 64-bit store per 64 bytes of text.
-constexpr uint32_t kHotRow = 288;
+constexpr uint32_t kHotRow = RB_HOT_ROW;
 __device__ __forceinline__ uint32_t hot_table_bytes(uint32_t rows) { return (rows * kHotRow + 255u) & ~255u; }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
   uint32_t v;
@@ -114,7 +114,7 @@ template <int K>
 __device__ __forceinline__ uint32_t hot_next(uint32_t tb, uint32_t w, uint32_t e) {
   const uint32_t x = __byte_perm(w, tb, 0x7650 + K);  // tb | byte K of w
   uint32_t addr;
-  asm("mad.lo.u32 %0, %1, 288, %2;" : "=r"(addr) : "r"(e), "r"(x));
+  asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(e), "r"(x), "n"(RB_HOT_ROW));
   return lds8(addr);
 }
 __device__ __forceinline__ uint32_t hot_next_b(uint32_t tb, uint32_t byte, uint32_t e) { return lds8(tb + e * kHotRow + byte); }

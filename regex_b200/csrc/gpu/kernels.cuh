@@ -39,6 +39,9 @@ struct DfaView {
 // which an ASCII haystack visits a handful).  Hot ids: 0 = dead, 1 = trap (the
 // transition left the hot set; absorbing), then non-match states, then match states.
 // A lane that lands in the trap row re-runs those bytes on the full class-indexed table.
+#ifndef RB_HOT_ROW
+#define RB_HOT_ROW 288  // bytes between hot-table rows in shared memory: 256 entries + 32 (rows start 8 banks apart)
+#endif
 struct HotView {
   const uint16_t* next256;   // [n][256] successor hot ids
   const uint16_t* eof;       // [n] EOF successor in FULL numbering

@@ -3,7 +3,8 @@
 One process per GPU.  Rank g keeps [left context | its bytes | right halo] of the
 haystack in its own HBM and runs the ordinary single-GPU kernels on it through
 rure_b200_find_all_shard_device.  The only data that crosses NVLink are three tiny
-per-shard values, exchanged with all_gather (NCCL on GPUs, gloo in the CPU tests):
+per-shard values, exchanged in ONE all_gather per round (NCCL on GPUs, gloo in the CPU
+tests; a single round when every boundary guess was right):
 
   1. the reverse-scan state at the shard's left edge -- the right-hand neighbour of a
      shard boundary knows it exactly, the left-hand one guessed it from its halo;
@@ -145,58 +146,69 @@ def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
     (see GpuShardEngine) and returns rev_guess, rev_left, exit_p, exit_lm, n_matches with
     positions relative to the shard buffer.
 
-    Returns (n_local, global_offset, global_total); the engine holds the local spans
+    Every round is ONE all_gather of ten integers per rank: the gathered vectors let every
+    rank evaluate every rank's boundary conditions, so all ranks agree on who has to redo
+    what without a second exchange.  In the common case (every guess right) the whole
+    protocol is a single collective.
+
+    Returns (n_local, global_offset, global_total, rounds); the engine holds the local spans
     (buffer-relative; add geom.buf_lo for global positions)."""
+    world, me = geom.world, geom.rank
     to_buf = lambda v: v if v in (NONE, SPEC) else v - geom.buf_lo
     to_glob = lambda v: v if v in (NONE, SPEC) else v + geom.buf_lo
+    owns_bytes = not (geom.a >= geom.b and not geom.is_first)
     io = dict(own_lo=geom.own_lo, own_hi=geom.own_hi, is_first=geom.is_first, is_last=geom.is_last,
               rev_entry=NO_STATE, reuse_scan=False,
               chain_p=to_buf(start) if geom.is_first else SPEC, chain_lm=NONE)
-    owns_nothing = geom.a >= geom.b and not geom.is_first
-    res = engine.run(io) if not owns_nothing else None
+    res = engine.run(io) if owns_bytes else None
     rounds = 0
-    # ---- 1. reverse-scan states flow right-to-left ------------------------------
     while True:
-        mine = [NO_STATE, NO_STATE] if res is None else [res["rev_left"], res["rev_guess"]]
-        states = comm.all_gather(mine + [0])
-        changed = 0
-        if res is not None and not geom.is_last:
-            # nearest right neighbour that owns bytes
-            want = next((states[g][0] for g in range(geom.rank + 1, geom.world) if states[g][0] != NO_STATE), NO_STATE)
-            if want != NO_STATE and want != res["rev_guess"]:
-                io.update(rev_entry=want, reuse_scan=True)
+        if res is None:
+            mine = [NO_STATE, NO_STATE, SPEC, SPEC, 0, SPEC, NONE, 0]
+        else:
+            mine = [res["rev_left"], res["rev_guess"], to_glob(res["exit_p"]), to_glob(res["exit_lm"]), res["n_matches"],
+                    to_glob(io["chain_p"]), to_glob(io["chain_lm"]), 1]
+        allv = comm.all_gather(mine + [geom.buf_lo, geom.a])  # [8] = first buffer byte, [9] = first owned byte (global)
+        # ---- 1. reverse-scan states flow right-to-left: who guessed its right edge wrong? ----
+        redo_rev = {}
+        for g in range(world):
+            if not allv[g][7] or g == world - 1:
+                continue
+            want = next((allv[h][0] for h in range(g + 1, world) if allv[h][7] and allv[h][0] != NO_STATE), NO_STATE)
+            if want != NO_STATE and want != allv[g][1]:
+                redo_rev[g] = want
+        if redo_rev:
+            if me in redo_rev:
+                io.update(rev_entry=redo_rev[me], reuse_scan=True)
                 res = engine.run(io)
-                changed = 1
-        if not any(s[2] for s in comm.all_gather([0, 0, changed])):
-            break
-        rounds += 1
-    # ---- 2. iterator state flows left-to-right ----------------------------------
-    while True:
-        mine = [SPEC, SPEC] if res is None else [to_glob(res["exit_p"]), to_glob(res["exit_lm"])]
-        exits = comm.all_gather(mine + [0])
-        changed = 0
-        if res is not None and not geom.is_first:
-            tp, tl = next(((exits[g][0], exits[g][1]) for g in range(geom.rank - 1, -1, -1) if exits[g][0] != SPEC))
-            tp_b = to_buf(tp)
-            tl_b = NONE if (tl != NONE and tl < geom.buf_lo) else to_buf(tl)
-            if io["chain_p"] == SPEC:
-                # positions left of the buffer are "before my first byte" whatever their value
-                before = tp != NONE and tp < geom.buf_lo
-                ok = before or _spec_ok(tp_b, tl_b, geom.own_lo + 1, can_match_empty, has_looks)
+            rounds += 1
+            continue
+        # ---- 2. iterator state flows left-to-right: whose entry assumption was wrong? -------
+        redo_chain = {}
+        for g in range(1, world):
+            if not allv[g][7]:
+                continue
+            buf_lo_g, a_g = allv[g][8], allv[g][9]
+            tp, tl = next(((allv[h][2], allv[h][3]) for h in range(g - 1, -1, -1) if allv[h][2] != SPEC))
+            cp, cl = allv[g][5], allv[g][6]
+            # an entry left of the buffer is "before my first byte" whatever its value
+            entry = (buf_lo_g, NONE) if (tp != NONE and tp < buf_lo_g) else (tp, NONE if (tl != NONE and tl < buf_lo_g) else tl)
+            if cp == SPEC:
+                ok = (tp != NONE and tp < buf_lo_g) or _spec_ok(entry[0], entry[1], a_g + 1, can_match_empty, has_looks)
             else:
-                ok = (io["chain_p"], io["chain_lm"]) == (tp_b, tl_b)
+                ok = (cp, cl) == entry
             if not ok:
-                if tp != NONE and tp < geom.buf_lo:
-                    tp_b, tl_b = 0, NONE
-                io.update(chain_p=tp_b, chain_lm=tl_b, reuse_scan=True)
+                redo_chain[g] = entry
+        if redo_chain:
+            if me in redo_chain:
+                p_g, l_g = redo_chain[me]
+                io.update(chain_p=to_buf(p_g), chain_lm=to_buf(l_g), reuse_scan=True)
                 res = engine.run(io)
-                changed = 1
-        if not any(s[2] for s in comm.all_gather([0, 0, changed])):
-            break
-        rounds += 1
-    # ---- 3. counts -> global offsets ----------------------------------------------
-    counts = [c[0] for c in comm.all_gather([0 if res is None else res["n_matches"], 0, 0])]
-    return counts[geom.rank], sum(counts[:geom.rank]), sum(counts), rounds
+            rounds += 1
+            continue
+        # ---- 3. counts -> global offsets ------------------------------------------------
+        counts = [v[4] for v in allv]
+        return counts[me], sum(counts[:me]), sum(counts), rounds
 
 
 class GpuShardEngine:
