@@ -170,8 +170,9 @@ def run_reference(args):
         "impl": "reference", "metric": "haystack GB/s scanned (find_iter, bit-exact spans)", "value": round(gbs, 4),
         "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}`", "haystack": "bounded sample of the 16 GiB corpus",
-                   "sample_bytes": sample_bytes},
+        "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}` over {args.gib:g} GiB/GPU synthetic English text "
+                               f"(reference arm: each step scans a bounded {sample_bytes >> 20} MiB sample of that corpus on the host cores)",
+                   "haystack_bytes_per_gpu": int(args.gib * GIB), "sample_bytes": sample_bytes},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_bytes >> 20} MiB of the C2 corpus, {threads} threads, byte ranges cut at newlines; matches={count}"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
