@@ -345,7 +345,6 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   a.flag0 = (uint8_t*)(counters + 24);
   a.utf8_boundaries = utf8_mask;
   if (const char* pr = getenv("RB200_PROBE_SKIP_TABLE")) a.probe_skip_table = atoi(pr);
-  if (const char* pr = getenv("RB200_RING_CP_ASYNC")) a.ring_cp_async = atoi(pr);
   a.hot = rev->hot;
   size_t smem;
   uint32_t block;

@@ -889,64 +889,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     const uint64_t t0 = __shfl_sync(0xffffffffu, t, 0);
     const bool uniform = live && !a.redo_list && hi - lo == a.seg && i == hi + a.warm && t == t0 + lane;
     const bool all_uniform = __all_sync(0xffffffffu, uniform) && a.warm <= a.seg;
-    const bool boxed = !a.ring_cp_async && a.tmap_rows != 0 && all_uniform && t0 + 33 <= a.tmap_rows;
-    const bool cp_ring = a.ring_cp_async && all_uniform;
+    const bool boxed = a.tmap_rows != 0 && all_uniform && t0 + 33 <= a.tmap_rows;
     uint64_t nz = 0;  // FUSED: which bitmap words of this segment are non-zero
-    if (cp_ring) {
-      // Same geometry as the boxed path below, but the ring is filled by the warp itself:
-      // four cp.async (LDGSTS) warp instructions per 64-byte group, lane j copying 16-byte
-      // chunk (j & 3) of rows (j >> 2) + 8 i -- eight 64-byte pieces per instruction.
-      const uint32_t n_groups = (a.seg + a.warm) >> 6, n_warm = a.warm >> 6;
-      const uint32_t r0 = lane >> 2, ch = lane & 3u;
-      // row r of the warp starts at text + base + (t0 + r) * seg; offsets past seg run into the next row (the warm-up bytes)
-      const uint8_t* src0 = a.text + a.base + (t0 + r0) * (uint64_t)a.seg + ch * 16u;
-      auto issue_cp = [&](uint32_t k, uint32_t slot) {
-        const uint32_t o = a.seg + a.warm - 64u * (k + 1);
-#pragma unroll
-        for (uint32_t i4 = 0; i4 < 4; i4++) {
-          const uint32_t r = r0 + 8u * i4;
-          const uint32_t dst = ring + slot * kRingStageBytes + r * 64u + ((ch ^ ((r >> 1) & 3u)) << 4);
-          const uint8_t* src = src0 + (uint64_t)(8u * i4) * a.seg + o;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        }
-      };
-      issue_cp(0, 0);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (n_groups > 1) issue_cp(1, 1);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      uint64_t* bw = a.bitmap + (hi >> 6);
-      uint64_t pw1 = 0, pw2 = 0, pw3 = 0;  // the previous three words (higher addresses) of the current sector
-      const bool sector_stores = (a.seg & 255u) == 0;
-      const uint32_t my_b = ring + lane * 64u;
-      const uint32_t sw = ((lane >> 1) & 3u) << 4;
-      for (uint32_t k = 0; k < n_groups; k++) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        const uint32_t b = my_b + (k & 1) * kRingStageBytes;
-        const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
-        if (k == n_warm) a.guess[t] = (uint16_t)full_state();
-        const bool rec = k >= n_warm;
-        uint32_t bhi, blo;
-        if (a.probe_skip_table) { bhi = c0.x ^ c1.y ^ c2.z; blo = c3.w ^ c0.y; }
-        else do_group(c0, c1, c2, c3, rec, bhi, blo);
-        if (a.probe_skip_table == 2) { if ((bhi | blo) == 0x12345u) *bw = 1; }  // probe: no bitmap stores either
-        else if (rec) {
-          // Bitmap words leave as whole 32-byte sectors (four words, every fourth group):
-          // an 8-byte store per group is a partial-sector write from each lane, and those
-          // capped the whole kernel at 3.0 TB/s (5.0 TB/s with the stores removed).
-          const uint64_t wv = ((uint64_t)bhi << 32) | blo;
-          --bw;
-          if (!sector_stores) *bw = wv;
-          else if (((k - n_warm) & 3u) == 3u) st_sector(bw, wv, pw1, pw2, pw3);
-          pw3 = pw2; pw2 = pw1; pw1 = wv;
-          if (FUSED) nz = (nz << 1) | ((bhi | blo) ? 1ull : 0ull);
-        }
-        __syncwarp();  // every lane has its 64 bytes in registers: the slot can be refilled
-        if (k + 2 < n_groups) issue_cp(k + 2, k & 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (boxed) {
+    if (boxed) {
       // Tight loop for the common geometry: every lane scans one full segment plus the
       // warm-up, so group counts, the warm-up/record split and the ring slots are warp
       // uniform and one lane drives the TMA for all 32.

@@ -31,7 +31,6 @@ struct ScanArgs {
   const uint32_t* n_redo;
   int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
   uint64_t skip_lo, skip_hi;  // scan_fwd_reduce: segments [skip_lo, skip_hi) belong to scan_fwd_fast
-  int ring_cp_async;    // feed the ring with per-warp cp.async (LDGSTS) instead of TMA boxes
   int probe_skip_table; // measurement probe (RB200_PROBE_SKIP_TABLE=1): move the bytes, skip the automaton
 };
 
