@@ -1284,10 +1284,6 @@ __device__ __forceinline__ void window16(const uint8_t* p, uint32_t (&v)[4]) {
 __device__ __forceinline__ uint32_t window_byte(const uint32_t (&v)[4], int i) {  // byte i, i compile-time
   return (v[i >> 2] >> (8 * (i & 3))) & 0xFFu;
 }
-template <int I>
-__device__ __forceinline__ uint32_t window_next(uint32_t tb, const uint32_t (&v)[4], uint32_t e) {
-  return hot_next<(I & 3)>(tb, v[I >> 2], e);
-}
 __device__ __noinline__ bool slow_is_match_record(const DfaView* f, const uint8_t* p, uint64_t len) {
   uint32_t s = f->uniform_start ? f->start[32] : f->start[flags_forward(p, len, 0)];
   for (uint64_t q = 0; s != 0; q++) {

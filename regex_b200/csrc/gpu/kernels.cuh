@@ -4,16 +4,19 @@
 // so no tensor cores (BASELINE.json north_star).
 //
 // Kernel inventory (reference function each replaces):
-//   scan_rev_bitmap   all match STARTS of the haystack as a bitmap -- the
-//                     chunk-parallel form of running exec_at_reverse
-//                     (src/dfa.rs:768-866) from every match end
-//   scan_fwd_reduce   first match END / any match / RegexSet mask over one big
-//                     haystack -- exec_at with quit_after_match
-//                     (src/dfa.rs:576-764) and forward_many (:525-570)
-//   walk_chunks       the find_iter chain (src/re_trait.rs:197-220) over the
-//                     start bitmap + anchored leftmost-first runs (exec_at)
-//   *_batch           one thread per record: is_match / find / set matches,
-//                     the reference algorithm verbatim per record
+//   scan_rev_fast     all match STARTS of the haystack as a bitmap -- the chunk-parallel
+//                     form of running exec_at_reverse (src/dfa.rs:768-866) from every
+//                     match end -- on the shared-memory hot table, fed by 2-D tiled TMA;
+//                     FUSED: each lane also walks the find_iter chain of its segment
+//   scan_rev_bitmap   the same for tables that do not fit / special cases (generic)
+//   scan_fwd_fast,    first match END / any match / RegexSet mask over one big
+//   scan_fwd_reduce   haystack -- exec_at with quit_after_match (src/dfa.rs:576-764)
+//                     and forward_many (:525-570)
+//   walk_chunks,      the find_iter chain (src/re_trait.rs:197-220) over the start
+//   stitch_check,     bitmap + anchored leftmost-first runs (exec_at); speculative per
+//   compact_spans     chunk, validated against the left neighbour, ordered compaction
+//   batch_fast,       one thread per record: is_match / find / set matches, the
+//   *_batch           reference algorithm verbatim per record (exec.rs:632-662)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
