@@ -503,11 +503,12 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   uint64_t* offset = (uint64_t*)offset_.ensure(nc * 8);
   uint32_t* dirty_list = (uint32_t*)dirty_.ensure(nc * 4);
   w.first_cand = (uint64_t*)first_cand_.ensure(nc * 8);
+  w.skip = (uint32_t*)skip_.ensure(nc * 4);
   w.stage = (uint64_t*)stage_.ensure(nc * (uint64_t)w.stage_cap * 16);
   const uint64_t n_blocks = (nc + 1023) / 1024;
   uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
-  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !dirty_list || !w.first_cand || !w.stage || !block_sums || !counters)
+  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !dirty_list || !w.first_cand || !w.skip || !w.stage || !block_sums || !counters)
     return fail("out of device memory (walk scratch)");
   w.offset = offset;
   w.out = d_out;
@@ -518,7 +519,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
   w.err_flag = counters + 28;
   RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 4, st));
-  init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, nc, io->chain_p, io->chain_lm);
+  init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, w.skip, nc, io->chain_p, io->chain_lm);
   RB_LAUNCH_CHECK("init_walk_entries");
   size_t wsmem = 0;
   if (wfixed) {
@@ -548,20 +549,22 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   }
   stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
   for (;;) {
-    RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
+    RB_CUDA(cudaMemsetAsync(counters, 0, 8, st));  // [0] chunks to walk again, [1] chunks whose exit state changed by trimming
     WalkArgs wd = w;
     wd.dirty_list = dirty_list;
     wd.n_dirty = counters;
     stitch_check<<<grid_for(nc, 256, 8), 256, 0, st>>>(wd, counters);
     RB_LAUNCH_CHECK("stitch_check");
-    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 4, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 8, cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
-    const uint32_t n_dirty = *(uint32_t*)pinned_;
-    if (n_dirty == 0) break;
+    const uint32_t n_dirty = ((uint32_t*)pinned_)[0], n_changed = ((uint32_t*)pinned_)[1];
+    if (n_dirty == 0 && n_changed == 0) break;
     stats.stitch_rounds++;
     stats.stitch_dirty_chunks += n_dirty;
-    launch_walk(wd, n_dirty);
-    RB_LAUNCH_CHECK("walk_chunks(dirty)");
+    if (n_dirty) {
+      launch_walk(wd, n_dirty);
+      RB_LAUNCH_CHECK("walk_chunks(dirty)");
+    }
   }
   unsigned long long* grand = (unsigned long long*)(counters + 4);
   scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w.count, offset, block_sums, nc);

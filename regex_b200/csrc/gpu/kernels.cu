@@ -702,6 +702,7 @@ __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
     a.out_lm[k] = c.lm;
     a.count[k] = total;
     a.first_cand[k] = fc;
+    if (a.dirty_list) a.skip[k] = 0;  // the staged list is a fresh chain from in_p[k]
   }
 }
 template __global__ void walk_chunks<0>(WalkArgs);
@@ -724,6 +725,7 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
     const uint64_t k = g * 32 + lane;
     const uint64_t my_cnt = k < a.n_chunks ? a.count[k] : 0;
     const uint64_t my_at = k < a.n_chunks ? a.offset[k] : 0;
+    const uint32_t my_skip = k < a.n_chunks ? a.skip[k] : 0;
     if (my_cnt > a.stage_cap) {  // rare: dense chunk, redo it in place
       Chain c;
       c.p = a.in_p[k];
@@ -740,6 +742,7 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
       // a dependent load -> store chain per lane)
       int j[4];
       uint64_t cnt[4], at[4];
+      uint32_t sk[4];
       ulonglong2 v[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -747,17 +750,18 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
         if (todo) todo &= todo - 1;
         cnt[u] = j[u] >= 0 ? __shfl_sync(0xffffffffu, my_cnt, j[u] & 31) : 0;
         at[u] = __shfl_sync(0xffffffffu, my_at, j[u] & 31);
+        sk[u] = __shfl_sync(0xffffffffu, my_skip, j[u] & 31);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (lane < cnt[u]) v[u] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + lane];
+        if (lane < cnt[u]) v[u] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + sk[u] + lane];
 #pragma unroll
       for (int u = 0; u < 4; u++)
         if (lane < cnt[u] && at[u] + lane < a.cap) dst[at[u] + lane] = v[u];
 #pragma unroll
       for (int u = 0; u < 4; u++)  // chunks with more than 32 staged spans
         for (uint64_t i = lane + 32; i < cnt[u]; i += 32)
-          if (at[u] + i < a.cap) dst[at[u] + i] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + i];
+          if (at[u] + i < a.cap) dst[at[u] + i] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + sk[u] + i];
     }
   }
 }
@@ -1132,10 +1136,11 @@ __global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __gri
   }
 }
 
-__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0) {
+__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint32_t* skip, uint64_t n_chunks, uint64_t p0, uint64_t lm0) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {
     in_p[k] = k == 0 ? p0 : kSpec;
     in_lm[k] = k == 0 ? lm0 : kNone;
+    skip[k] = 0;
   }
 }
 
@@ -1151,9 +1156,36 @@ __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty) {
     if (cp == kSpec) ok = spec_ok(a, tp, tl, c_first, a.first_cand[k], c_first + a.chunk);
     else ok = cp == tp && cl == tl;
     if (!ok) {
+      // Most wrong speculations are one match of the left neighbour reaching into this chunk.
+      // Without empty matches or look-arounds the speculative chain and the real one meet
+      // again at the first staged span that starts at or after tp, provided the span before
+      // it ended by tp (no candidate lies between a span's end and the next span's start):
+      // drop the spans before it instead of walking the chunk again.
+      bool trimmed = false;
+      if (cp == kSpec && tp != kNone && !a.emulate_slice && !a.can_match_empty) {
+        const uint64_t cnt = a.count[k];
+        if (cnt <= a.stage_cap) {
+          const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
+          uint32_t lo = 0, hi = (uint32_t)cnt;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sp[mid].x < tp) lo = mid + 1; else hi = mid;
+          }
+          if (lo == 0 || sp[lo - 1].y <= tp) {
+            trimmed = true;
+            a.skip[k] = lo;
+            a.count[k] = cnt - lo;
+            if (lo == cnt) {  // nothing left: the chain passes through unchanged; the right neighbour must be looked at again
+              a.out_p[k] = tp;
+              a.out_lm[k] = tl;
+              atomicAdd(n_dirty + 1, 1u);
+            }
+          }
+        }
+      }
       a.in_p[k] = tp;
       a.in_lm[k] = tl;
-      a.dirty_list[atomicAdd(n_dirty, 1u)] = (uint32_t)k;
+      if (!trimmed) a.dirty_list[atomicAdd(n_dirty, 1u)] = (uint32_t)k;
     }
   }
 }

@@ -57,6 +57,7 @@ struct WalkArgs {
   uint64_t* out_lm;
   uint64_t* count;
   const uint64_t* offset;
+  uint32_t* skip;           // per chunk: staged spans dropped from the front by stitch_check (trimmed speculation)
   uint32_t* dirty_list;     // chunks to walk again (nullable: all chunks)
   const uint32_t* n_dirty;
   HotView fwd_hot;              // fast runner: byte-indexed forward anchored table (hot states)
@@ -98,7 +99,7 @@ template <int FAST>
 __global__ void walk_chunks(WalkArgs a);
 template <int FAST>
 __global__ void compact_spans(WalkArgs a);
-__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
+__global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint32_t* skip, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
 __global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
 __global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);
 __global__ void scan_block_sums(uint64_t* block_sums, uint64_t n_blocks, unsigned long long* grand_total);
