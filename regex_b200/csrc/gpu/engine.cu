@@ -403,7 +403,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   };
   // A shard may be told the exact state at its top edge by its right neighbour.
   uint16_t* h16 = (uint16_t*)pinned_ + 512;
-  const bool shard = io && (!io->is_first || !io->is_last || io->rev_entry != kNoState);
+  const bool shard = io && (!io->is_first || !io->is_last || io->rev_entry != kNoState || io->own_hi < n);
   if (shard) {
     RB_CUDA(cudaMemcpyAsync(h16, a.guess + (n_seg - 1), 2, cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));

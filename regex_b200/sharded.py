@@ -53,7 +53,10 @@ class ShardGeometry:
 
     @property
     def is_last(self):
-        return self.rank == self.world - 1
+        """The buffer ends where the haystack does (end-of-text semantics apply at its end).
+        True for the last rank, and for an earlier rank whose halo reaches the end of a short
+        haystack; the protocol itself goes by rank order."""
+        return self.buf_hi >= self.total
 
 
 def plan(total, world, rank, halo=1 << 16, left_ctx=ALIGN):
@@ -212,7 +215,10 @@ def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
 
 
 class GpuShardEngine:
-    """Shard search through the C ABI on a CUDA buffer (torch uint8 tensor)."""
+    """Shard search through the C ABI on a CUDA buffer (torch uint8 tensor).
+
+    Give every shard its own compiled regex object: a redo round (`reuse_scan`) relies on the
+    start bitmap the object kept from this shard's previous call."""
 
     def __init__(self, regex, d_buffer, cap):
         import torch

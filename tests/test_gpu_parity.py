@@ -409,3 +409,44 @@ def test_reference_ctest_binary():
     # the iterator example (group 0 path) must run to completion over sherlock.txt
     it = subprocess.run([os.path.join(os.path.dirname(exe), "iter_example")], capture_output=True, text=True, timeout=120, cwd=GOLDEN)
     assert it.returncode == 0, it.stderr[-500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_search_short_haystacks(world):
+    """Haystacks so short that an early rank's halo reaches the end of the text (its buffer
+    then ends where the haystack does: end-of-text semantics, no halo overflow) and trailing
+    ranks own nothing."""
+    import threading
+    import torch
+    from regex_b200 import sharded
+    base = sherlock_text()[5000:9000]
+    for pat in (r"[a-zA-Z]+ing", r"\w+", r"a*", r"(?m)^\w+$", r"[a-z]+\s*$"):
+        re_ = R.BytesRegex(pat)
+        info = re_.pattern_info()
+        exp_all = O.OracleRegex(pat)
+        for n in (0, 1, 255, 256, 257, 600, 1100, 4000):
+            t = base[:n]
+            comm = sharded.ThreadComm(world)
+            out = [None] * world
+
+            def work(rank):
+                geom = sharded.plan(len(t), world, rank, halo=512)
+                buf = torch.frombuffer(bytearray(t[geom.buf_lo:geom.buf_hi] or b"\0"), dtype=torch.uint8).cuda()[:geom.n_buf]
+                # one compiled regex per rank: reuse_scan keeps the start bitmap inside the object
+                eng = sharded.GpuShardEngine(R.BytesRegex(pat), buf, cap=len(t) + 8)
+                n_local, offset, total, _ = sharded.find_all_sharded(eng, geom, comm.view(rank), info["can_match_empty"], info["has_looks"])
+                spans = eng.spans[:n_local].cpu().numpy().astype(np.int64) + geom.buf_lo if n_local else np.zeros((0, 2), dtype=np.int64)
+                out[rank] = (offset, [tuple(int(v) for v in r) for r in spans], total)
+
+            threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join(timeout=60)
+                assert not th.is_alive(), (pat, n, world, "a rank failed or hung")
+            merged = []
+            for off, sp, _ in sorted(out):
+                assert off == len(merged), (pat, n, world)
+                merged += sp
+            assert merged == exp_all.find_iter(t), (pat, n, world)

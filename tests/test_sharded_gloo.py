@@ -95,3 +95,42 @@ def test_plan_covers_haystack_exactly():
             assert owned[0][0] == 0 and owned[-1][1] == total
             for (a0, b0), (a1, b1) in zip(owned, owned[1:]):
                 assert b0 == a1
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_protocol_tiny_haystacks(world):
+    """Haystacks shorter than a shard: trailing ranks own nothing and must still take part in
+    every collective (in-process ThreadComm, same protocol code)."""
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_sim import SimShardEngine
+    base = sherlock_text()[5000:7000]
+    for pat in (r"[a-zA-Z]+ing", r"\w+", r"a*", r"(?m)^\w+"):
+        re_ = R.BytesRegex(pat)
+        info = re_.pattern_info()
+        for n in (0, 1, 255, 256, 257, 600, 1100):
+            t = base[:n]
+            comm = sharded.ThreadComm(world)
+            out = [None] * world
+
+            def work(rank):
+                geom = sharded.plan(len(t), world, rank, halo=512)
+                eng = SimShardEngine(re_, t[geom.buf_lo:geom.buf_hi], warm=0)
+                n_local, offset, total, _ = sharded.find_all_sharded(eng, geom, comm.view(rank), info["can_match_empty"], info["has_looks"])
+                spans = [(s + geom.buf_lo, e + geom.buf_lo) for s, e in (eng.spans if n_local else [])]
+                out[rank] = (offset, spans, total)
+
+            threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join(timeout=30)
+                assert not th.is_alive(), (pat, n, world, "a rank failed or hung")
+            merged = []
+            for off, sp, _ in sorted(o for o in out):
+                assert off == len(merged), (pat, n, world)
+                merged += sp
+            exp = O.OracleRegex(pat).find_iter(t)
+            assert merged == exp, (pat, n, world, merged[:4], exp[:4])
+            assert all(o[2] == len(exp) for o in out)
