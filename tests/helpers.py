@@ -23,6 +23,25 @@ def sherlock_counts():
         return [x for x in json.load(f) if "feature = \"re-" not in x["cfg"] or "not(" in x["cfg"]]
 
 
+def misc_is_match():
+    """bench/src/misc.rs known answers: (name, pattern, expected, haystack bytes)."""
+    with open(os.path.join(GOLDEN, "misc_is_match.json")) as f:
+        cases = json.load(f)
+    out = []
+    for c in cases:
+        parts = []
+        for part in c["haystack"]:
+            if "s" in part:
+                parts.append(part["s"].encode("utf-8"))
+            elif "rep" in part:
+                parts.append(part["rep"][0].encode("utf-8") * part["rep"][1])
+            else:
+                with open(os.path.join(GOLDEN, part["file"]), "rb") as g:
+                    parts.append(g.read())
+        out.append((c["name"], c["re"], c["is_match"], b"".join(parts)))
+    return out
+
+
 def xorshift_bytes(seed, n, alphabet):
     """Deterministic pseudo-random bytes over `alphabet` (xorshift64*)."""
     out = np.empty(n, dtype=np.uint8)

@@ -56,6 +56,24 @@ def test_reference_vectors_through_c_abi():
     assert not bad, bad[:10]
 
 
+def test_misc_is_match_known_answers():
+    """bench/src/misc.rs is_match expectations through the C ABI (str Regex); a pattern whose
+    DFA exceeds the budget must say so instead of answering."""
+    from helpers import misc_is_match
+    answered = 0
+    for name, pat, expected, hay in misc_is_match():
+        try:
+            r = R.Regex(pat)
+        except R.Error as e:
+            assert "exceeds size limit" in str(e), (name, e)
+            continue
+        assert r.is_match(hay) == expected, name
+        assert (r.shortest_match(hay) is not None) == expected, name
+        assert (r.find(hay) is not None) == expected, name
+        answered += 1
+    assert answered >= 30
+
+
 def test_sherlock_counts_and_spans():
     """bench/src/sherlock.rs counts + full span parity with the oracle."""
     text = sherlock_text()

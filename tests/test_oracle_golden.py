@@ -10,7 +10,7 @@ import re as pyre
 
 import pytest
 
-from helpers import GOLDEN, sherlock_counts, sherlock_text, vectors
+from helpers import GOLDEN, misc_is_match, sherlock_counts, sherlock_text, vectors
 from oracle import oracle as O
 
 
@@ -57,6 +57,14 @@ def test_sherlock_counts():
     for x in sherlock_counts():
         r = O.OracleRegex(x["re"], only_utf8=True)
         assert r.count(text) == x["count"], x
+
+
+def test_misc_is_match_known_answers():
+    """bench/src/misc.rs bench_match!/bench_not_match! outcomes (str Regex), both oracle engines."""
+    for name, pat, expected, hay in misc_is_match():
+        o = O.OracleRegex(pat, only_utf8=True)
+        for engine in (O.ENGINE_DFA, O.ENGINE_PIKEVM):
+            assert o.is_match_at(hay, 0, engine) == expected, (name, engine)
 
 
 def test_regexdna_shootout():

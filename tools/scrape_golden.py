@@ -209,3 +209,45 @@ print(f"sherlock_counts.json: {len(sher)} benches; sherlock.txt copied (test cor
 shutil.copyfile(ref / "examples/regexdna-input.txt", out_dir / "regexdna-input.txt")
 shutil.copyfile(ref / "examples/regexdna-output.txt", out_dir / "regexdna-output.txt")
 print("regexdna-input/output copied")
+
+# ------------------------------------------------- bench/src/misc.rs is_match --
+# bench_match! / bench_not_match! (bench/src/bench.rs:131-152) assert the is_match outcome
+# before timing, so every entry is a known answer.  Patterns and haystack recipes are
+# transcribed from bench/src/misc.rs:24-195 (haystacks as part lists: literal / repeat / file).
+R = lambda s, n: {"rep": [s, n]}
+S = lambda s: {"s": s}
+F = lambda name: {"file": name}
+ABC = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+misc = [
+    ("no_exponential", "a?" * 100 + "a" * 100, True, [R("a", 100)], "misc.rs:24-29"),
+    ("literal", r"y", True, [R("x", 50), S("y")], "misc.rs:31-33"),
+    ("not_literal", r".y", True, [R("x", 50), S("y")], "misc.rs:35-37"),
+    ("match_class", "[abcdw]", True, [R("xxxx", 20), S("w")], "misc.rs:39-41"),
+    ("match_class_in_range", "[ac]", True, [R("bbbb", 20), S("c")], "misc.rs:43-45"),
+    ("match_class_unicode", r"\p{L}", True, [R("☃5☃5", 20), S("a")], "misc.rs:49-51"),
+    ("anchored_literal_short_non_match", r"^zbc(d|e)", False, [S("abcdefghijklmnopqrstuvwxyz")], "misc.rs:53-55"),
+    ("anchored_literal_long_non_match", r"^zbc(d|e)", False, [R("abcdefghijklmnopqrstuvwxyz", 15)], "misc.rs:57-59"),
+    ("anchored_literal_short_match", r"^.bc(d|e)", True, [S("abcdefghijklmnopqrstuvwxyz")], "misc.rs:61-63"),
+    ("anchored_literal_long_match", r"^.bc(d|e)", True, [R("abcdefghijklmnopqrstuvwxyz", 15)], "misc.rs:65-67"),
+    ("one_pass_short", r"^.bc(d|e)*$", True, [S("abcddddddeeeededd")], "misc.rs:69-71"),
+    ("one_pass_short_not", r".bc(d|e)*$", True, [S("abcddddddeeeededd")], "misc.rs:73-75"),
+    ("one_pass_long_prefix", r"^abcdefghijklmnopqrstuvwxyz.*$", True, [S("abcdefghijklmnopqrstuvwxyz")], "misc.rs:77-79"),
+    ("one_pass_long_prefix_not", r"^.bcdefghijklmnopqrstuvwxyz.*$", True, [S("abcdefghijklmnopqrstuvwxyz")], "misc.rs:81-83"),
+    ("long_needle1", "a" * 30 + "b", True, [R("a", 100000), S("b")], "misc.rs:85-87"),
+    ("long_needle2", "b" * 30 + "a", True, [R("b", 100000), S("a")], "misc.rs:89-91"),
+    ("reverse_suffix_no_quadratic", r"[r-z].*bcdefghijklmnopq", False, [R("bcdefghijklmnopq", 500)], "misc.rs:97-99"),
+]
+for size in ("32", "1K", "32K"):
+    misc += [
+        (f"easy0_{size}", ABC + "$", True, [F(f"{size}.txt"), S(ABC)], "misc.rs:124-129"),
+        (f"easy1_{size}", r"A[AB]B[BC]C[CD]D[DE]E[EF]F[FG]G[GH]H[HI]I[IJ]J$", True, [F(f"{size}.txt"), S("AABCCCDEEEFGGHHHIJJ")], "misc.rs:135-142"),
+        (f"medium_{size}", r"[XYZ]" + ABC + "$", True, [F(f"{size}.txt"), S("X" + ABC)], "misc.rs:148-153"),
+        (f"hard_{size}", r"[ -~]*" + ABC + "$", True, [F(f"{size}.txt"), S(ABC)], "misc.rs:159-164"),
+        (f"reallyhard_{size}", r"[ -~]*" + ABC + ".*", True, [F(f"{size}.txt"), S(ABC)], "misc.rs:170-184"),
+    ]
+misc.append(("reallyhard2_1K", r"\w+\s+Holmes", True, [F("1K.txt"), S("Sherlock Holmes")], "misc.rs:191-194"))
+(out_dir / "misc_is_match.json").write_text(json.dumps(
+    [{"name": n, "re": p, "is_match": m, "haystack": h, "src": src_} for n, p, m, h, src_ in misc], indent=0, ensure_ascii=True) + "\n")
+for size in ("32", "1K", "32K"):
+    shutil.copyfile(ref / f"bench/src/data/{size}.txt", out_dir / f"{size}.txt")
+print(f"misc_is_match.json: {len(misc)} is_match known answers; 32/1K/32K corpora copied")
