@@ -132,6 +132,11 @@ Regex::~Regex() {
 
 const rb::Dfa* Regex::host_dfa(DfaKind k, rb::Error* err) {
   if (host_[k]) return host_[k].get();
+  if (patterns_.empty()) {  // an empty RegexSet matches nothing and has no automaton
+    err->kind = rb::Error::Syntax;
+    err->msg = "an empty pattern set has no automaton";
+    return nullptr;
+  }
   rb::CompileOptions co;
   co.only_utf8 = opt_.only_utf8;
   co.size_limit = opt_.size_limit;

@@ -65,3 +65,14 @@ def test_pattern_info_and_tables():
     assert (d["trans"][0] == 0).all()  # state 0 is dead
     assert R.Regex(r"a*").pattern_info()["can_match_empty"]
     assert R.Regex(r"(?m)^a$").pattern_info()["has_looks"]
+
+
+def test_empty_set_has_no_automaton_but_does_not_crash():
+    """An empty RegexSet compiles (re_set.rs:96-104) and matches nothing; asking for its
+    table is an error, not a crash."""
+    import pytest
+    import regex_b200 as R
+    s = R.BytesRegexSet([])
+    assert len(s) == 0
+    with pytest.raises(R.Error):
+        s.dfa()
