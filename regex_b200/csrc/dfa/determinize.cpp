@@ -196,8 +196,7 @@ struct Builder {
   }
 
   // All transitions of one raw state.  Same results, in the same order, as calling step()
-  // for every class -- but a state without look-arounds (the common case) is handled in
-  // one pass: each Bytes instruction is appended to the classes its byte range covers
+  // for every class -- but in one pass per state: each Bytes instruction is appended to the classes its byte range covers
   // (instead of testing every instruction against every class), and classes that end up
   // with the same target list share one closure + intern (Unicode-aware classes have ~110
   // byte classes but a few dozen distinct successors).  \w+ compiled in 6.6 s before.
@@ -206,57 +205,84 @@ struct Builder {
   std::vector<uint32_t> memo_key;
   void step_all(uint32_t si, uint32_t* row) {
     const std::vector<uint32_t> key = keys[si];  // copy: intern() may reallocate keys
+    const bool is_word_last = key[0] != 0;
     bool has_empty = false;
     for (size_t k = key_header(); k < key.size(); k++)
       if (prog.insts[key[k]].op == Op::EmptyLook) has_empty = true;
-    if (has_empty) {  // the closure before the byte depends on the byte: one class at a time
-      for (uint32_t c = 0; c < n_classes; c++) row[c] = step(si, c == n_byte_classes ? 256 : rep[c]);
-      return;
-    }
+    // The ordered instruction list the byte is applied to.  With look-arounds in the state
+    // it is first re-closed under the flags the byte implies (dfa.rs:933-957) -- and those
+    // depend only on whether the byte is a newline / a word byte / the end of text, so
+    // there are at most four variants: 0 = other byte, 1 = word byte, 2 = newline, 3 = EOF.
+    auto variant_list = [&](int g, std::vector<uint32_t>* out) {
+      out->clear();
+      if (!has_empty) {
+        out->assign(key.begin() + key_header(), key.end());
+        return;
+      }
+      qcur.clear();
+      for (size_t k = key_header(); k < key.size(); k++) qcur.insert(key[k]);
+      EmptyFlags f;
+      if (g == 3) { f.end = true; f.end_line = true; }
+      else if (g == 2) f.end_line = true;
+      const bool is_word = g == 1;
+      if (is_word_last == is_word) f.not_word_boundary = true; else f.word_boundary = true;
+      qnext.clear();
+      for (uint32_t ip : qcur.dense) follow_epsilons(ip, qnext, f);
+      *out = qnext.dense;
+    };
+    auto group_of = [&](uint32_t c) { const int b = rep[c]; return b == '\n' ? 2 : is_word_byte(b) ? 1 : 0; };
     per_class.resize(n_byte_classes);
     for (auto& v : per_class) v.clear();
-    std::vector<uint64_t> mask(mask_words, 0);
-    for (size_t k = key_header(); k < key.size(); k++) {
-      const Inst& in = prog.insts[key[k]];
-      if (in.op == Op::Match) {
-        mask[in.a / 64] |= 1ull << (in.a % 64);
-        if (opt.leftmost_first) break;
-      } else if (in.op == Op::Bytes) {
-        for (uint32_t c = prog.byte_classes[in.lo]; c <= prog.byte_classes[in.hi]; c++) per_class[c].push_back(in.a);
+    std::vector<uint64_t> mask[4];
+    bool present[3] = {false, false, false};
+    for (uint32_t c = 0; c < n_byte_classes; c++) present[group_of(c)] = true;
+    std::vector<uint32_t> list;
+    for (int g = 0; g < 4; g++) {
+      mask[g].assign(mask_words, 0);
+      if (g < 3 && !present[g]) continue;
+      variant_list(g, &list);
+      for (uint32_t ip : list) {
+        const Inst& in = prog.insts[ip];
+        if (in.op == Op::Match) {
+          mask[g][in.a / 64] |= 1ull << (in.a % 64);
+          if (opt.leftmost_first) break;
+        } else if (in.op == Op::Bytes && g < 3) {
+          for (uint32_t c = prog.byte_classes[in.lo]; c <= prog.byte_classes[in.hi]; c++)
+            if (group_of(c) == g) per_class[c].push_back(in.a);
+        }
       }
     }
-    // classes whose Bytes targets, word-ness and newline-ness agree have the same successor
-    struct Seen { uint32_t cls; bool word, nl; uint32_t to; };
+    // classes of one variant with the same Bytes targets have the same successor; so do
+    // equal (targets, variant, mask) combinations met in other states
+    struct Seen { uint32_t cls; int g; uint32_t to; };
     std::vector<Seen> seen;
     for (uint32_t c = 0; c < n_byte_classes; c++) {
-      const int b = rep[c];
-      const bool word = is_word_byte(b), nl = b == '\n';
+      const int g = group_of(c);
       uint32_t to = 0xFFFFFFFFu;
       for (const Seen& e : seen)
-        if (e.word == word && e.nl == nl && per_class[e.cls] == per_class[c]) { to = e.to; break; }
+        if (e.g == g && per_class[e.cls] == per_class[c]) { to = e.to; break; }
       if (to == 0xFFFFFFFFu) {
-        // the successor is a function of (targets, word, newline, mask): remember it across states
         memo_key.clear();
-        memo_key.push_back((word ? 1u : 0u) | (nl ? 2u : 0u));
-        for (uint64_t m : mask) { memo_key.push_back((uint32_t)m); memo_key.push_back((uint32_t)(m >> 32)); }
+        memo_key.push_back((uint32_t)g);
+        for (uint64_t m : mask[g]) { memo_key.push_back((uint32_t)m); memo_key.push_back((uint32_t)(m >> 32)); }
         memo_key.insert(memo_key.end(), per_class[c].begin(), per_class[c].end());
         auto hit = memo.find(memo_key);
         if (hit != memo.end()) {
           to = hit->second;
         } else {
           EmptyFlags f;
-          f.start_line = nl;
+          f.start_line = g == 2;
           qnext.clear();
           for (uint32_t target : per_class[c]) follow_epsilons(target, qnext, f);
-          to = intern(qnext, word, mask);
+          to = intern(qnext, g == 1, mask[g]);
           if (!too_big) memo.emplace(memo_key, to);
         }
-        seen.push_back(Seen{c, word, nl, to});
+        seen.push_back(Seen{c, g, to});
       }
       row[c] = to;
     }
     qnext.clear();
-    row[n_byte_classes] = intern(qnext, false, mask);  // EOF: no byte is consumed
+    row[n_byte_classes] = intern(qnext, false, mask[3]);  // EOF: no byte is consumed
   }
 
   uint32_t start_state(int flagi) {  // dfa.rs:1370-1409
