@@ -175,17 +175,24 @@ struct PikeVm {
 // only decide *when* it falls back to the NFA, never the result).
 struct LazyDfa {
   struct Result { enum K { Match, NoMatch } k; size_t pos; };
-  static const uint32_t UNKNOWN = 0xFFFFFFFFu, DEAD = 0xFFFFFFFEu;
+  static constexpr uint32_t UNKNOWN = 0xFFFFFFFFu, DEAD = 0xFFFFFFFEu;
 
   const Program& prog;
-  struct State { std::vector<uint32_t> ips; uint8_t flags; std::vector<uint32_t> next; };
-  static const uint8_t F_MATCH = 1, F_WORD = 2, F_EMPTY = 4;
+  struct State { std::vector<uint32_t> ips; uint8_t flags; };
+  static constexpr uint8_t F_MATCH = 1, F_WORD = 2, F_EMPTY = 4;
   std::vector<State> states;
+  // Transition cache laid out like the reference's (dfa.rs:236-262, 373-400): one flat
+  // table, row = state, column = byte class; an entry is UNKNOWN, DEAD, or the successor's
+  // ROW OFFSET (index * ncls, the reference's premultiplied state pointer) with MATCH_BIT set
+  // when the successor is a match state, so the scan loop (dfa.rs:636-657) is two dependent
+  // loads and an add per byte and never looks at the state itself.
+  static constexpr uint32_t MATCH_BIT = 1u << 30, ID_MASK = MATCH_BIT - 1;
+  std::vector<uint32_t> flat;
   std::map<std::pair<uint8_t, std::vector<uint32_t>>, uint32_t> cache;
   uint32_t start_states[128];
   int ncls;
   std::vector<uint32_t> stack;
-  uint32_t last_match_si = UNKNOWN;
+  uint32_t last_match_off = UNKNOWN;  // row offset of the last match state seen (forward_many reads its ips)
 
   struct EmptyFlags { bool start = false, end = false, start_line = false, end_line = false, wb = false, nwb = false; };
   struct Sparse {
@@ -245,7 +252,8 @@ struct LazyDfa {
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     uint32_t id = (uint32_t)states.size();
-    states.push_back(State{std::move(ips), flags, std::vector<uint32_t>((size_t)ncls, UNKNOWN)});
+    states.push_back(State{std::move(ips), flags});
+    flat.resize(states.size() * (size_t)ncls, UNKNOWN);
     cache.emplace(std::move(key), id);
     return id;
   }
@@ -282,14 +290,25 @@ struct LazyDfa {
     bool cache_it = true;
     if (eof && prog.matches.size() > 1) { std::swap(qcur, qnext); cache_it = false; }  // dfa.rs:1004-1015
     uint32_t next = cached_state(qnext, flags);
-    if (cache_it) states[si].next[cls_of(b)] = next;
+    if (cache_it) flat[(size_t)si * ncls + cls_of(b)] = encode(next);
     return next;
   }
   int cls_of(int b) const { return b == 256 ? ncls - 1 : prog.byte_classes[b]; }
+  uint32_t encode(uint32_t id) const {
+    return id == DEAD ? DEAD : (id * (uint32_t)ncls) | ((states[id].flags & F_MATCH) ? MATCH_BIT : 0u);
+  }
   uint32_t next_state(uint32_t si, int b) {  // dfa.rs:1345-1361
     if (si == DEAD) return DEAD;
-    uint32_t n = states[si].next[cls_of(b)];
-    return n == UNKNOWN ? exec_byte(si, b) : n;
+    uint32_t n = flat[(size_t)si * ncls + cls_of(b)];
+    if (n == UNKNOWN) return exec_byte(si, b);
+    return n == DEAD ? DEAD : (n & ID_MASK) / (uint32_t)ncls;
+  }
+  // One byte of the scan loops from row offset `off`: the cached entry if there is one,
+  // else compute (and cache) it.  DEAD and UNKNOWN are the two largest values.
+  inline uint32_t step_cached(uint32_t off, uint8_t b) {
+    uint32_t v = flat[off + prog.byte_classes[b]];
+    if (v == UNKNOWN) v = encode(exec_byte(off / (uint32_t)ncls, b));
+    return v;
   }
   uint32_t start_state(int flagi) {  // dfa.rs:1370-1409
     if (start_states[flagi] != UNKNOWN) return start_states[flagi];
@@ -324,49 +343,54 @@ struct LazyDfa {
   }
   // dfa.rs:576-764 without the unrolling / prefix-skip fast paths.
   Result forward(const uint8_t* t, size_t n, size_t at, bool quit_after_match) {
-    last_match_si = UNKNOWN;
+    last_match_off = UNKNOWN;
     uint32_t si = start_state(flags_forward(t, n, at));
     Result r{Result::NoMatch, at};
     if (si == DEAD) return r;
+    uint32_t off = si * (uint32_t)ncls;
     while (at < n) {
-      si = next_state(si, t[at]);
+      const uint32_t v = step_cached(off, t[at]);
       at++;
-      if (si == DEAD) { if (r.k == Result::NoMatch) r.pos = at; return r; }
-      if (states[si].flags & F_MATCH) {
+      if (v == DEAD) { if (r.k == Result::NoMatch) r.pos = at; return r; }
+      off = v & ID_MASK;
+      if (v & MATCH_BIT) {
         r = Result{Result::Match, at - 1};
         if (quit_after_match) return r;
-        last_match_si = si;
+        last_match_off = off;
         if (prog.matches.size() > 1) {  // dfa.rs:675-682
+          si = off / (uint32_t)ncls;
           bool just = true;
           for (uint32_t ip : states[si].ips) just = just && prog.insts[ip].op == Op::Match;
           if (just) return r;
         }
       }
     }
-    si = next_state(si, 256);
+    si = next_state(off / (uint32_t)ncls, 256);
     if (si == DEAD) { if (r.k == Result::NoMatch) r.pos = n; return r; }
-    if (states[si].flags & F_MATCH) { last_match_si = si; r = Result{Result::Match, n}; }
+    if (states[si].flags & F_MATCH) { last_match_off = si * (uint32_t)ncls; r = Result{Result::Match, n}; }
     return r;
   }
   // dfa.rs:768-866
   Result reverse(const uint8_t* t, size_t n, size_t at, bool quit_after_match) {
-    last_match_si = UNKNOWN;
+    last_match_off = UNKNOWN;
     uint32_t si = start_state(flags_reverse(t, n, at));
     Result r{Result::NoMatch, at};
     if (si == DEAD) return r;
+    uint32_t off = si * (uint32_t)ncls;
     while (at > 0) {
       at--;
-      si = next_state(si, t[at]);
-      if (si == DEAD) { if (r.k == Result::NoMatch) r.pos = at; return r; }
-      if (states[si].flags & F_MATCH) {
+      const uint32_t v = step_cached(off, t[at]);
+      if (v == DEAD) { if (r.k == Result::NoMatch) r.pos = at; return r; }
+      off = v & ID_MASK;
+      if (v & MATCH_BIT) {
         r = Result{Result::Match, at + 1};
         if (quit_after_match) return r;
-        last_match_si = si;
+        last_match_off = off;
       }
     }
-    si = next_state(si, 256);
+    si = next_state(off / (uint32_t)ncls, 256);
     if (si == DEAD) { if (r.k == Result::NoMatch) r.pos = 0; return r; }
-    if (states[si].flags & F_MATCH) { last_match_si = si; r = Result{Result::Match, 0}; }
+    if (states[si].flags & F_MATCH) { last_match_off = si * (uint32_t)ncls; r = Result{Result::Match, 0}; }
     return r;
   }
   // dfa.rs:525-570
@@ -374,7 +398,7 @@ struct LazyDfa {
     Result r = forward(t, n, at, false);
     if (r.k != Result::Match) return false;
     if (matches.size() == 1) { matches[0] = true; return true; }
-    for (uint32_t ip : states[last_match_si].ips)
+    for (uint32_t ip : states[last_match_off / (uint32_t)ncls].ips)
       if (prog.insts[ip].op == Op::Match) matches[prog.insts[ip].a] = true;
     return true;
   }
