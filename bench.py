@@ -174,7 +174,8 @@ def run_reference(args):
                                f"(reference arm: each step scans a bounded {sample_bytes >> 20} MiB sample of that corpus on the host cores)",
                    "haystack_bytes_per_gpu": int(args.gib * GIB), "sample_bytes": sample_bytes},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_bytes >> 20} MiB of the C2 corpus, {threads} threads, byte ranges cut at newlines; matches={count}"},
+                         "sample": f"{sample_bytes >> 20} MiB of the C2 corpus, {threads} threads, byte ranges cut at newlines, oracle engine 'auto' "
+                                   f"(DfaSuffix where the reference selects it); matches={count}"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -360,7 +361,8 @@ def run_ours(args):
             gpu_count = R.BytesRegex(args.pattern).find_all_device(text[geom.own_lo:geom.own_lo + last_nl].contiguous())
             assert gpu_count == count, ("parity spot check failed", gpu_count, count)
             result["cpu_baseline"] = {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                                      "sample": f"first {last_nl >> 20} MiB of rank 0's shard, {threads} threads cut at newlines, count {count} == GPU count"}
+                                      "sample": f"first {last_nl >> 20} MiB of rank 0's shard, {threads} threads cut at newlines, oracle engine 'auto' "
+                                                f"(DfaSuffix as the reference selects for this pattern, exec.rs:1176-1210), count {count} == GPU count"}
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()

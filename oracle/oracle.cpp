@@ -18,6 +18,12 @@
 //   LazyDfa     src/dfa.rs:576-1580 -- on-line subset construction with a
 //               state cache, forward leftmost-first and reverse longest scans,
 //               one-byte match delay, EOF sentinel, set scan.
+//   DfaSuffix   src/exec.rs:725-794, 1176-1210 -- suffix-literal scan (memmem), reverse
+//               DFA from the literal's end, forward DFA from the start; the engine the
+//               reference selects for `[a-zA-Z]+ing` and the one the CPU baseline times
+//               (engine 2 = "auto"; recognised for concatenations ending in >= 3 literal
+//               characters, otherwise the plain pipeline).  The Teddy / Aho-Corasick
+//               literal engines of src/literals.rs are not restated.
 //   Exec        src/exec.rs:382-514, 632-662, 998-1038 -- shortest/is_match/find
 //               pipeline (forward DFA then reverse DFA over &text[start..]).
 //   iterate()   src/re_trait.rs:197-220 -- the find_iter chaining rule.
@@ -412,11 +418,49 @@ struct Regex {
   bool only_utf8 = false;
   std::string error;
 
-  // engine: 0 = default pipeline (lazy DFA forward + reverse-on-slice), 1 = Pike VM
+  // Longest common suffix literal when the reference would pick MatchType::DfaSuffix
+  // (exec.rs:1176-1210: at least 3 chars and longer than the common prefix literal).  Only
+  // the simple case is recognised here -- a concatenation that ends in plain literal
+  // characters and does not start with one -- which covers the headline `[a-zA-Z]+ing`.
+  std::string lcs;
+
+  // exec.rs:725-756: scan for the suffix literal, then the reverse DFA from its end over the
+  // slice that starts at the previous literal's end.  Returns 0 = no match, 1 = match start
+  // in *ms, 2 = gave up (the reverse scan reached the slice start: avoid quadratic time).
+  int exec_dfa_reverse_suffix(const uint8_t* t, size_t n, size_t original_start, size_t* ms) {
+    size_t start = original_start, end = start;
+    while (end <= n) {
+      start = end;
+      const void* hit = memmem(t + end, n - end, lcs.data(), lcs.size());
+      if (!hit) return 0;
+      end = (size_t)((const uint8_t*)hit - t) + lcs.size();
+      auto r = rev->reverse(t + start, end - start, end - start, false);
+      if (r.pos == 0) return 2;  // Match(0) | NoMatch(0)
+      if (r.k == LazyDfa::Result::Match) { *ms = r.pos + start; return 1; }
+    }
+    return 0;
+  }
+
+  // engine: 0 = default pipeline (lazy DFA forward + reverse-on-slice), 1 = Pike VM,
+  // 2 = the engine the reference itself selects: DfaSuffix when `lcs` is set (exec.rs:764-794),
+  // else the default pipeline
   bool find_at(int engine, const uint8_t* t, size_t n, size_t start, size_t* s, size_t* e) {
     if (engine == 1) {
       PikeVm vm(nfa);
       return vm.exec(t, n, start, false, nullptr, s, e);
+    }
+    if (engine == 2 && !lcs.empty()) {
+      size_t ms;
+      const int k = exec_dfa_reverse_suffix(t, n, start, &ms);
+      if (k == 0) return false;
+      if (k == 1) {
+        auto r = fwd->forward(t, n, ms, false);  // the literal only gives the earliest possible end
+        if (r.k != LazyDfa::Result::Match) return false;
+        *s = ms;
+        *e = r.pos;
+        return true;
+      }
+      // gave up: fall through to find_dfa_forward
     }
     // src/exec.rs:632-662
     auto r = fwd->forward(t, n, start, false);
@@ -483,6 +527,39 @@ static Regex* build(const std::vector<std::string>& pats, uint32_t flags, bool o
   }
   re->fwd = std::make_unique<LazyDfa>(re->dfa);
   re->rev = std::make_unique<LazyDfa>(re->dfa_rev);
+  if (exprs.size() == 1) {
+    const rb::Expr* x = &exprs[0];
+    while (x->kind == rb::EK::Group && x->es.size() == 1) x = &x->es[0];
+    if (x->kind == rb::EK::Concat && !x->es.empty()) {
+      auto literal_bytes = [](const rb::Expr& c, std::string* out) {
+        if (c.casei) return false;
+        if (c.kind == rb::EK::Literal) {
+          for (uint32_t ch : c.chars) {  // UTF-8 encode
+            if (ch < 0x80) out->push_back((char)ch);
+            else if (ch < 0x800) { out->push_back((char)(0xC0 | (ch >> 6))); out->push_back((char)(0x80 | (ch & 0x3F))); }
+            else if (ch < 0x10000) { out->push_back((char)(0xE0 | (ch >> 12))); out->push_back((char)(0x80 | ((ch >> 6) & 0x3F))); out->push_back((char)(0x80 | (ch & 0x3F))); }
+            else { out->push_back((char)(0xF0 | (ch >> 18))); out->push_back((char)(0x80 | ((ch >> 12) & 0x3F))); out->push_back((char)(0x80 | ((ch >> 6) & 0x3F))); out->push_back((char)(0x80 | (ch & 0x3F))); }
+          }
+          return true;
+        }
+        if (c.kind == rb::EK::LiteralBytes) { out->append((const char*)c.bytes.data(), c.bytes.size()); return true; }
+        return false;
+      };
+      std::string head;
+      const bool prefix_literal = literal_bytes(x->es.front(), &head);
+      size_t first = x->es.size();
+      while (first > 0) {
+        std::string tmp;
+        if (!literal_bytes(x->es[first - 1], &tmp)) break;
+        first--;
+      }
+      std::string suffix;
+      for (size_t i = first; i < x->es.size(); i++) literal_bytes(x->es[i], &suffix);
+      size_t chars = 0;
+      for (unsigned char c : suffix) chars += (c & 0xC0) != 0x80;
+      if (first > 0 && !prefix_literal && chars >= 3 && !re->nfa.is_anchored_start && !re->nfa.is_anchored_end) re->lcs = suffix;
+    }
+  }
   return re.release();
 }
 
@@ -570,7 +647,7 @@ size_t oracle_count_parallel(const char* pat, size_t pat_len, uint32_t flags, in
       const char* p[1] = {pat};
       size_t l[1] = {pat_len};
       void* h = oracle_compile(p, l, 1, flags, only_utf8, 10u << 20);
-      counts[k] = oracle_find_iter(h, 0, t + cuts[k], cuts[k + 1] - cuts[k], nullptr, 0);
+      counts[k] = oracle_find_iter(h, 2, t + cuts[k], cuts[k + 1] - cuts[k], nullptr, 0);  // the engine the reference would select
       oracle_free(h);
     });
   }

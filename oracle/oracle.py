@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 FLAG_CASEI, FLAG_MULTI, FLAG_DOTNL, FLAG_SWAP_GREED, FLAG_SPACE, FLAG_UNICODE = 1, 2, 4, 8, 16, 32
-ENGINE_DFA, ENGINE_PIKEVM = 0, 1
+ENGINE_DFA, ENGINE_PIKEVM, ENGINE_AUTO = 0, 1, 2  # AUTO: DfaSuffix where the reference would select it, else DFA
 
 
 def build():

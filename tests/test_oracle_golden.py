@@ -34,7 +34,7 @@ def _run(x, mode, engine):
     raise AssertionError(x["kind"])
 
 
-@pytest.mark.parametrize("engine", [O.ENGINE_DFA, O.ENGINE_PIKEVM], ids=["lazydfa", "pikevm"])
+@pytest.mark.parametrize("engine", [O.ENGINE_DFA, O.ENGINE_PIKEVM, O.ENGINE_AUTO], ids=["lazydfa", "pikevm", "auto-dfasuffix"])
 def test_reference_vectors(engine):
     bad = []
     n = 0
@@ -57,6 +57,22 @@ def test_sherlock_counts():
     for x in sherlock_counts():
         r = O.OracleRegex(x["re"], only_utf8=True)
         assert r.count(text) == x["count"], x
+        # the engine the reference itself selects (DfaSuffix for e.g. [a-zA-Z]+ing, exec.rs:1176-1210);
+        # this is the one bench.py times as the CPU baseline
+        assert r.count(text, engine=O.ENGINE_AUTO) == x["count"], x
+
+
+def test_dfasuffix_engine_equals_dfa_engine():
+    """exec.rs:725-794 (suffix literal scan + reverse DFA + forward DFA) must give the spans of
+    the plain DFA pipeline, including when the quadratic-behaviour guard makes it give up."""
+    text = sherlock_text()[:200000]
+    adversarial = b"inginginginginging" * 50 + b" xing ing singing"
+    for pat in [r"[a-zA-Z]+ing", r"\w+ing", r"[a-z]+ation", r"(?s).{0,5}olmes", r"[A-Z][a-z]*son", r"\s[a-z]+ing\s",
+                r"[a-z]*ing", r"x+ing|y+ing", r"(?i)[a-z]+ing", r"[a-zA-Z]+ing$"]:
+        for only_utf8 in (False, True):
+            r = O.OracleRegex(pat, only_utf8=only_utf8)
+            for t in (text, adversarial):
+                assert r.find_iter(t, engine=O.ENGINE_AUTO) == r.find_iter(t, engine=O.ENGINE_DFA), (pat, only_utf8)
 
 
 def test_misc_is_match_known_answers():
