@@ -833,9 +833,110 @@ const uint8_t* Regex::upload_text(const uint8_t* text, uint64_t n, int* rc) {
   return d;
 }
 
+// 0 = off.  The pipelined upload is opt-in (RB200_PIPELINE_PIECE=<bytes>) until it has been
+// through the GPU parity tests; tools/micro/pipeline_probe.py compares it with the plain path.
+static constexpr uint64_t kPipelinePieceDefault = 0;
+
+// Host haystack, pipelined: the upload is cut into pieces on a copy stream and every piece is
+// searched as a byte-range shard of the (partly resident) device buffer as soon as it and
+// the halo behind it have arrived, so the search hides under the PCIe transfer and the
+// spans of a piece travel back while later pieces are still going up.  Pieces are taken
+// left to right, so each enters the find_iter chain with its predecessor's exact exit
+// state; the reverse-scan state a piece assumed at its top is checked against the exact
+// one its successor computes.  Anything unusual (a wrong assumption, a match running past
+// the halo) abandons the pipeline: the caller then runs the plain path on the resident text.
+// Returns 0 = done, 1 = not applicable / abandoned (text is fully resident), < 0 = error.
+int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, uint64_t* d_out, uint64_t* out, uint64_t cap,
+                                   uint64_t* total) {
+  uint64_t piece = kPipelinePieceDefault;
+  if (const char* e = getenv("RB200_PIPELINE_PIECE")) piece = (uint64_t)atoll(e) / 256 * 256;
+  const uint64_t halo = 64 << 10;
+  if (piece == 0 || n < 2 * piece || is_set_ || patterns_.empty()) {
+    RB_CUDA(cudaMemcpy(d, text, n, cudaMemcpyHostToDevice));
+    return 1;
+  }
+  if (!copy_stream_) {
+    cudaStream_t s1, s2;
+    RB_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    copy_stream_ = s1;
+    back_stream_ = s2;
+  }
+  cudaStream_t up = (cudaStream_t)copy_stream_, back = (cudaStream_t)back_stream_;
+  const uint64_t n_pieces = (n + piece - 1) / piece;
+  std::vector<cudaEvent_t> arrived(n_pieces);
+  for (uint64_t i = 0; i < n_pieces; i++) {
+    const uint64_t lo = i * piece, len = std::min(piece, n - lo);
+    RB_CUDA(cudaMemcpyAsync(d + lo, text + lo, len, cudaMemcpyHostToDevice, up));
+    RB_CUDA(cudaEventCreateWithFlags(&arrived[i], cudaEventDisableTiming));
+    RB_CUDA(cudaEventRecord(arrived[i], up));
+  }
+  auto cleanup = [&](int rc) {
+    cudaStreamSynchronize(up);  // the plain path needs the whole text anyway
+    cudaStreamSynchronize(back);
+    for (auto& e : arrived) cudaEventDestroy(e);
+    return rc;
+  };
+  // scratch sized for the whole haystack up front (DeviceBuf::ensure reallocates on growth)
+  if (!bitmap_.ensure(((n >> 6) + 2) * 8)) return cleanup(fail("out of device memory (bitmap)"));
+  uint64_t done = 0, chain_p = 0, chain_lm = kNone;
+  uint32_t prev_guess = kNoState;
+  for (uint64_t i = 0; i < n_pieces; i++) {
+    const uint64_t lo = i * piece, hi = std::min(n, lo + piece);
+    const uint64_t n_i = std::min(n, hi + halo);  // resident prefix this piece may read
+    RB_CUDA(cudaEventSynchronize(arrived[std::min(n_pieces - 1, (n_i - 1) / piece)]));
+    ShardIO io;
+    io.own_lo = lo;
+    io.own_hi = hi;
+    io.is_first = i == 0;
+    io.is_last = n_i == n;
+    io.chain_p = chain_p;
+    io.chain_lm = chain_lm;
+    uint64_t* dst = d_out && cap > done ? d_out + 2 * done : nullptr;
+    const uint64_t room = cap > done ? cap - done : 0;
+    const int rc = find_all_shard_device(d, n_i, &io, dst, room);
+    if (rc) {
+      if (io.halo_overflow) return cleanup(1);  // a match longer than the halo: do it in one piece
+      return cleanup(rc);
+    }
+    if (i > 0 && prev_guess != io.rev_left) return cleanup(1);  // the previous piece guessed its top state wrong
+    prev_guess = hi < n ? io.rev_guess : kNoState;
+    if (dst) {
+      const uint64_t k = std::min(room, io.n_matches);
+      if (k) RB_CUDA(cudaMemcpyAsync(out + 2 * done, dst, k * 16, cudaMemcpyDeviceToHost, back));
+    }
+    done += io.n_matches;
+    chain_p = io.exit_p;
+    chain_lm = io.exit_lm;
+    if (chain_p == kNone) {  // the iteration ended (a failed slice emulation): nothing further matches
+      break;
+    }
+  }
+  *total = done;
+  return cleanup(0);
+}
+
 int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64_t* out, uint64_t cap, uint64_t* total) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   int rc;
+  if (start == 0 && n >= (8u << 20) && out && cap) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail("no CUDA device available: regex_b200 has no CPU matching path");
+    uint8_t* dd = (uint8_t*)text_.ensure(n + 64);
+    uint64_t* d_out = (uint64_t*)out_.ensure(cap * 16);
+    if (!dd || !d_out) return fail("out of device memory (haystack / spans)");
+    DeviceDfa* warm;  // picks the stream, creates the pinned scratch
+    if ((rc = ensure(kFwdAnchoredLF, &warm))) return rc;
+    *total = 0;
+    rc = find_all_host_pipelined(text, n, dd, d_out, out, cap, total);
+    if (rc <= 0) return rc < 0 ? rc : 0;
+    // not applicable or abandoned: the text is resident now, search it in one piece
+    if ((rc = find_all_device(dd, n, 0, d_out, cap, total))) return rc;
+    const uint64_t k = std::min(cap, *total);
+    if (k) RB_CUDA(cudaMemcpy(out, d_out, k * 16, cudaMemcpyDeviceToHost));
+    return 0;
+  }
   const uint8_t* d = upload_text(text, n, &rc);
   if (rc) return rc;
   uint64_t* d_out = nullptr;

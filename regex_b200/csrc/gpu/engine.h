@@ -127,6 +127,7 @@ class Regex {
                   const void* fused_walk);
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
   const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
+  int find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, uint64_t* d_out, uint64_t* out, uint64_t cap, uint64_t* total);
 
   std::vector<std::string> patterns_;
   bool is_set_ = false;
@@ -138,6 +139,8 @@ class Regex {
   std::recursive_mutex mu_;
   void* stream_ = nullptr;
   void* own_stream_ = nullptr;
+  void* copy_stream_ = nullptr;  // host -> device pieces of a pipelined find_all
+  void* back_stream_ = nullptr;  // device -> host spans
   void* ext_stream_ = nullptr;
   bool use_ext_stream_ = false;
   // scratch (grow-only)
