@@ -337,7 +337,8 @@ def run_ours(args):
             result["e2e"] = {"value": round(e2e_n * world / float(t[0]) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": e2e_n,
                              "d2h_bytes_per_step": int(min(tot.value, cap) * 16 + 8), "haystack_bytes": e2e_n,
                              "note": "rure_b200_find_all on pinned host memory per rank (independent haystacks); H2D of the haystack and "
-                                     "D2H of all spans inside the timed region"}
+                                     "D2H of all spans inside the timed region; the library pipelines upload, search and "
+                                     "download in 64 MiB pieces"}
         del host
 
     if rank == 0:

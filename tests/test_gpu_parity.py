@@ -468,3 +468,28 @@ def test_sharded_search_short_haystacks(world):
                 assert off == len(merged), (pat, n, world)
                 merged += sp
             assert merged == exp_all.find_iter(t), (pat, n, world)
+
+
+@pytest.mark.gpu
+def test_pipelined_host_find_all(monkeypatch):
+    """rure_b200_find_all on host memory uploads in pieces and searches each piece as a shard
+    while later pieces are still in flight; spans must equal the upload-then-search path --
+    with ragged last pieces, empty matches, look-arounds, and a match longer than the halo
+    (which makes the pipeline give up and redo the haystack in one piece)."""
+    n = 12 << 20
+    corpus = tiled_corpus(n)
+    special = bytearray(corpus)
+    special[5_000_000:5_300_000] = b"a" * 300_000
+    for data in (corpus, bytes(special)):
+        for pat in [r"[a-zA-Z]+ing", r"\w+", r"a+", r"(?m)^\w+", r"a*", r"(?-u:\b)the(?-u:\b)"]:
+            r = R.BytesRegex(pat)
+            monkeypatch.setenv("RB200_PIPELINE_PIECE", "0")
+            plain = r.find_all(data, cap=4_000_000)
+            for piece in (1 << 20, 3 << 20):
+                monkeypatch.setenv("RB200_PIPELINE_PIECE", str(piece))
+                got = r.find_all(data, cap=4_000_000)
+                assert got.shape == plain.shape and np.array_equal(got, plain), (pat, piece)
+    exp = O.OracleRegex(r"[a-zA-Z]+ing").find_iter(corpus[:3 << 20])
+    monkeypatch.setenv("RB200_PIPELINE_PIECE", str(1 << 20))
+    got = _spans(R.BytesRegex(r"[a-zA-Z]+ing").find_all(corpus))
+    assert got[:len(exp) - 1] == exp[:len(exp) - 1]
