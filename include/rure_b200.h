@@ -38,6 +38,10 @@ rure_set *rure_b200_compile_set_str(const uint8_t **patterns, const size_t *patt
                                     rure_error *error);
 
 /* ---- single haystack ------------------------------------------------------ */
+/* Host haystack.  Large haystacks (>= 128 MiB) are uploaded in 64 MiB pieces and each piece
+ * is searched while later pieces are still in flight, spans travelling back meanwhile; the
+ * result is identical to uploading first (environment RB200_PIPELINE_PIECE=<bytes> changes
+ * the piece size, 0 turns the pipeline off).  Pinned host memory gives the full PCIe rate. */
 bool rure_b200_find_all(rure *re, const uint8_t *haystack, size_t length, rure_match *out,
                         size_t cap, size_t *n_total);
 bool rure_b200_count_all(rure *re, const uint8_t *haystack, size_t length, size_t *n_total);
