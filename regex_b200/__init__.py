@@ -9,6 +9,7 @@ library has not been built, and searching fails loudly without a GPU.
 """
 import ctypes
 import os
+import sys
 from ctypes import POINTER, byref, c_bool, c_char_p, c_double, c_int, c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p
 
 import numpy as np
@@ -39,7 +40,7 @@ class _Shard(ctypes.Structure):  # include/rure_b200.h: rure_b200_shard
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
-            f"{_LIB_PATH} is missing: build it with `python -m regex_b200.build` "
+            f"{_LIB_PATH} is missing: build it with `python regex_b200/build.py` "
             "(nvcc, sm_100a).  regex_b200 has no CPU fallback.")
     L = ctypes.CDLL(_LIB_PATH)
     vp, sz, u8p = c_void_p, c_size_t, c_void_p
@@ -98,7 +99,12 @@ def _load():
     return L
 
 
-_lib = _load()
+def _building():
+    """`python -m regex_b200.build` imports this package before the library exists."""
+    return "regex_b200.build" in getattr(sys, "orig_argv", [])
+
+
+_lib = None if (_building() and not os.path.exists(_LIB_PATH)) else _load()
 
 
 def lib():
