@@ -107,7 +107,9 @@ struct Builder {
   }
 
   // dfa.rs:1196-1244 (+ canonicalisation that cannot change results: the word
-  // flag is kept only when a word-boundary look can still read it, and
+  // flag is kept only when a word-boundary look can still read it -- i.e. when the state
+  // holds any look-around at all, since a word look may be reached through another look
+  // at the next re-closure (`(?-u:\b)^`: the reverse program meets `^` first) -- and
   // priority order is dropped when no leftmost-first cut will ever use it).
   uint32_t intern(const OrderedSet& q, bool word, const std::vector<uint64_t>& mask) {
     std::vector<uint32_t> key(key_header(), 0);
@@ -123,7 +125,7 @@ struct Builder {
         const Inst& in = prog.insts[ip];
         if (in.op == Op::Save || in.op == Op::Split) continue;
         key.push_back(ip);
-        if (in.op == Op::EmptyLook && is_word_look(in.look)) word_look = true;
+        if (in.op == Op::EmptyLook) word_look = prog_has_word_looks;  // a word look may sit behind this look
         if (in.op == Op::Match) break;
       }
     } else {
@@ -134,7 +136,7 @@ struct Builder {
         const Inst& in = prog.insts[ip];
         if (in.op == Op::Save || in.op == Op::Split) continue;
         ipbits[ip >> 6] |= 1ull << (ip & 63);
-        if (in.op == Op::EmptyLook && is_word_look(in.look)) word_look = true;
+        if (in.op == Op::EmptyLook) word_look = prog_has_word_looks;  // a word look may sit behind this look
       }
       for (size_t w = 0; w < ipbits.size(); w++) {
         uint64_t m = ipbits[w];
@@ -322,7 +324,54 @@ int start_flag_index_reverse(const uint8_t* text, size_t len, size_t at) {
   return f;
 }
 
+// The lazy DFA resolves `^`-type looks only in the closure taken right AFTER a byte and `$`-type
+// and word looks only in the re-closure right BEFORE the next byte (dfa.rs:933-957, 971-999).
+// Two adjacent look-arounds (no byte in between) in the "wrong" order never pass inside a scan:
+//   word look, then multi-line `^`   -- forward scans miss it (the reference's DFA and NFA disagree);
+//   multi-line `$`, then word look   -- the reverse program reads "word look, then start-of-line
+//                                       look", so the start bitmap would silently miss matches.
+// Neither occurs in the reference's tests or in practice (`\b(?m:^)`, `(?m:$)\b`); both are rejected
+// instead of answered differently from the reference.
+static bool has_unresolvable_look_pair(const Program& prog) {
+  if (prog.is_reverse) return false;  // the forward programs of the same regex carry the check
+  std::vector<uint32_t> stack;
+  std::vector<uint8_t> seen;
+  for (uint32_t ip0 = 0; ip0 < prog.insts.size(); ip0++) {
+    const Inst& first = prog.insts[ip0];
+    if (first.op != Op::EmptyLook) continue;
+    const bool from_end_line = first.look == Look::EndLine, from_word = is_word_look(first.look);
+    if (!from_end_line && !from_word) continue;
+    seen.assign(prog.insts.size(), 0);
+    stack.assign(1, first.a);
+    while (!stack.empty()) {
+      const uint32_t ip = stack.back();
+      stack.pop_back();
+      if (seen[ip]) continue;
+      seen[ip] = 1;
+      const Inst& in = prog.insts[ip];
+      switch (in.op) {
+        case Op::Save: stack.push_back(in.a); break;
+        case Op::Split: stack.push_back(in.a); stack.push_back(in.b); break;
+        case Op::EmptyLook:
+          if (from_end_line && is_word_look(in.look)) return true;
+          if (from_word && in.look == Look::StartLine) return true;
+          stack.push_back(in.a);
+          break;
+        default: break;
+      }
+    }
+  }
+  return false;
+}
+
 bool determinize(const Program& prog, const DfaOptions& opt, Dfa* out, Error* err) {
+  if (has_unresolvable_look_pair(prog)) {
+    err->kind = Error::UnicodeWordBoundary;
+    err->msg = "look-around sequence not supported by the B200 DFA backend: a word boundary directly followed by a "
+               "multi-line `^`, or a multi-line `$` directly followed by a word boundary, cannot be resolved inside a "
+               "DFA scan (the reference's own DFA and NFA engines disagree on such patterns).";
+    return false;
+  }
   if (prog.has_unicode_word_boundary) {
     err->kind = Error::UnicodeWordBoundary;
     err->msg = "Unicode word boundaries (\\b, \\B without (?-u)) need a look-around engine; "
