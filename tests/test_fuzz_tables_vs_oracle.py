@@ -71,3 +71,30 @@ def test_unresolvable_look_pairs_are_explicit_errors(pat, ok):
     else:
         with pytest.raises(R.Error, match="look-around sequence"):
             R.BytesRegex(pat)
+
+
+def test_set_tables_equal_forward_many_on_random_sets():
+    """RegexSet: the OR of the per-state pattern masks along the forward scan must equal
+    RegexSet::matches (dfa.rs:525-570) for random pattern sets."""
+    rng = np.random.Generator(np.random.PCG64(0x5E7))
+    cases = 0
+    for _ in range(160):
+        pats = [_pattern(rng) for _ in range(int(rng.integers(2, 6)))]
+        for cls, utf8 in ((R.BytesRegexSet, False), (R.RegexSet, True)):
+            try:
+                s = cls(pats)
+            except R.Error:
+                continue
+            o = O.OracleRegex(pats, only_utf8=utf8)
+            sim = Sim(s)
+            for t in TEXTS:
+                if utf8:
+                    try:
+                        t.decode()
+                    except UnicodeDecodeError:
+                        continue
+                _, acc = sim.forward_scan(t)
+                got = [i for i in range(len(pats)) if (acc >> i) & 1]
+                assert got == list(o.set_matches(t)), (pats, utf8, t)
+                cases += 1
+    assert cases > 800, cases
