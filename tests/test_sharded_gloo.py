@@ -134,3 +134,80 @@ def test_sharded_protocol_tiny_haystacks(world):
             exp = O.OracleRegex(pat).find_iter(t)
             assert merged == exp, (pat, n, world, merged[:4], exp[:4])
             assert all(o[2] == len(exp) for o in out)
+
+
+def _run_threads(pat, text, world, halo=256):
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_sim import SimShardEngine
+    re_ = R.BytesRegex(pat)
+    info = re_.pattern_info()
+    comm = sharded.ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def work(rank):
+        try:
+            geom = sharded.plan(len(text), world, rank, halo=halo)
+            eng = SimShardEngine(re_, text[geom.buf_lo:geom.buf_hi], warm=0)
+            n_local, offset, total, _ = sharded.find_all_sharded(eng, geom, comm.view(rank), info["can_match_empty"], info["has_looks"])
+            out[rank] = (offset, [(s + geom.buf_lo, e + geom.buf_lo) for s, e in (eng.spans if n_local else [])], total)
+        except Exception as e:  # noqa: BLE001 -- surface instead of dead-locking the barrier
+            errs.append(e)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+        assert not th.is_alive()
+    if errs:
+        real = [e for e in errs if "BrokenBarrier" not in type(e).__name__]
+        raise real[0] if real else errs[0]
+    merged = []
+    for off, sp, _ in sorted(out):
+        assert off == len(merged)
+        merged += sp
+    return merged
+
+
+def test_sharded_protocol_random_patterns_without_look_arounds():
+    """Seeded fuzz of the boundary protocol (2-4 shards, 256-byte halo, cold warm-up so that
+    guesses are often wrong) over random patterns, empty matches included."""
+    import numpy as np
+    from helpers import xorshift_bytes
+    from test_fuzz_tables_vs_oracle import _pattern
+    rng = np.random.Generator(np.random.PCG64(0x5AAD))
+    cases = 0
+    for _ in range(400):
+        pat = _pattern(rng)
+        try:
+            info = R.BytesRegex(pat).pattern_info()
+        except R.Error:
+            continue
+        if info["has_looks"]:
+            continue  # see test_sharded_protocol_slice_rule_at_a_speculative_boundary
+        text = xorshift_bytes(int(rng.integers(0, 1000)), int(rng.integers(300, 1500)), b"abc \n" if rng.random() < 0.7 else b"ab1 _\n\xc3\xa9")
+        try:
+            got = _run_threads(pat, text, int(rng.integers(2, 5)))
+        except AssertionError as e:
+            if "halo too short" in str(e):
+                continue
+            raise
+        assert got == O.OracleRegex(pat).find_iter(text), pat
+        cases += 1
+    assert cases > 150, cases
+
+
+@pytest.mark.xfail(reason="known gap: the reference's reverse-on-slice rule (SURVEY H1) is not re-applied to the first match of a "
+                          "speculatively entered chunk/shard when the real restart point lies before it (DESIGN.md, known divergences)",
+                   strict=False)
+def test_sharded_protocol_slice_rule_at_a_speculative_boundary():
+    pat = r"^[ab]{2,}\w*?|(?m:$)"
+    from helpers import xorshift_bytes
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(7))
+    for seed in range(40):
+        text = xorshift_bytes(seed, 948, b"abc \n")
+        assert _run_threads(pat, text, 3) == O.OracleRegex(pat).find_iter(text), seed
