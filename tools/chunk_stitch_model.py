@@ -5,7 +5,12 @@ start with slice_start at the real entry point).  Usage: python tools/chunk_stit
 Round-1 finding (tiny 8/24-byte chunks, random look-around patterns): the current rule is wrong in
 ~1.4 % of cases; the candidate fix removes ~90 % of them but not all (matches whose slice-rule
 start is no true match start need the walk itself to apply the rule at speculative entries).
-Patterns without look-arounds are unaffected (tests/test_stitch_trim_sim.py, shard fuzz)."""
+Two things are needed for exactness: (1) the first span of an accepted speculative chunk gets its
+start from slice_start(real entry, end) -- the candidate fix modelled here -- and (2) a chunk
+without matches must hand on the restart point it RECEIVED, not the one it assumed (its own first
+position); (2) is a "last chunk with matches" prefix propagation over runs of empty chunks and is
+what the remaining ~10 % are.  Patterns without look-arounds are unaffected
+(tests/test_stitch_trim_sim.py, shard fuzz)."""
 import sys, time
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np
