@@ -98,8 +98,9 @@ typedef struct rure_b200_shard {
   uint32_t rev_left;       /* (x) exact state at own_lo */
   uint64_t exit_p, exit_lm;   /* (x) iterator state leaving the shard */
   uint64_t n_matches;      /* (x) */
-  uint32_t halo_overflow;  /* a match ran past the end of the right halo (call failed) */
-  uint32_t reserved;
+  uint32_t halo_overflow;  /* call failed: bit 0 = a match ran past the end of the right halo, bit 1 = the
+                              reverse-on-slice scan of a look-around pattern reached a clamped chain_p (left context too short) */
+  uint32_t chain_clamped;  /* in: chain_p is the buffer position standing in for a restart point LEFT of the buffer */
 } rure_b200_shard;
 bool rure_b200_find_all_shard_device(rure *re, const uint8_t *d_buffer, size_t n_buffer,
                                      rure_b200_shard *io, rure_match *d_out, size_t cap);

@@ -34,7 +34,7 @@ class _Shard(ctypes.Structure):  # include/rure_b200.h: rure_b200_shard
     _fields_ = [("own_lo", c_uint64), ("own_hi", c_uint64), ("is_first", ctypes.c_int32), ("is_last", ctypes.c_int32),
                 ("rev_entry", c_uint32), ("reuse_scan", c_uint32), ("chain_p", c_uint64), ("chain_lm", c_uint64),
                 ("rev_guess", c_uint32), ("rev_left", c_uint32), ("exit_p", c_uint64), ("exit_lm", c_uint64),
-                ("n_matches", c_uint64), ("halo_overflow", c_uint32), ("reserved", c_uint32)]
+                ("n_matches", c_uint64), ("halo_overflow", c_uint32), ("chain_clamped", c_uint32)]
 
 
 def _load():
@@ -283,7 +283,8 @@ class _Compiled:
         """One shard of a sharded haystack (see regex_b200/sharded.py).  `io` carries the
         in-fields of rure_b200_shard; returns its out-fields as a dict."""
         sh = _Shard(own_lo=io["own_lo"], own_hi=io["own_hi"], is_first=int(io["is_first"]), is_last=int(io["is_last"]),
-                    rev_entry=io["rev_entry"], reuse_scan=int(io["reuse_scan"]), chain_p=io["chain_p"], chain_lm=io["chain_lm"])
+                    rev_entry=io["rev_entry"], reuse_scan=int(io["reuse_scan"]), chain_p=io["chain_p"], chain_lm=io["chain_lm"],
+                    chain_clamped=int(io.get("chain_clamped", False)))
         cap = 0 if d_out is None else d_out.shape[0]
         ptr = 0 if d_out is None else d_out.data_ptr()
         if not _lib.rure_b200_find_all_shard_device(self._h, d_buffer.data_ptr(), d_buffer.numel(), byref(sh), ptr, cap):

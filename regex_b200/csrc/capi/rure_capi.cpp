@@ -303,10 +303,11 @@ bool rure_b200_find_all_shard_device(rure* re, const uint8_t* d_buffer, size_t n
   s.is_first = io->is_first != 0; s.is_last = io->is_last != 0;
   s.rev_entry = io->rev_entry; s.reuse_scan = io->reuse_scan != 0;
   s.chain_p = io->chain_p; s.chain_lm = io->chain_lm;
+  s.chain_clamped = io->chain_clamped != 0;
   bool r = ok(re->re, re->re->find_all_shard_device(d_buffer, n_buffer, &s, (uint64_t*)d_out, d_out ? cap : 0));
   io->rev_guess = s.rev_guess; io->rev_left = s.rev_left;
   io->exit_p = s.exit_p; io->exit_lm = s.exit_lm;
-  io->n_matches = s.n_matches; io->halo_overflow = s.halo_overflow;
+  io->n_matches = s.n_matches; io->halo_overflow = (s.halo_overflow ? 1u : 0u) | (s.left_ctx_short ? 2u : 0u);
   return r;
 }
 

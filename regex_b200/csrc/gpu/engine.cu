@@ -127,6 +127,9 @@ Regex* Regex::compile(const std::vector<std::string>& patterns, const CompileOpt
 Regex::~Regex() {
   for (auto*& d : dev_) { delete d; d = nullptr; }
   if (pinned_) cudaFreeHost(pinned_);
+  for (void* e : timing_events_) if (e) cudaEventDestroy((cudaEvent_t)e);
+  if (copy_stream_) cudaStreamDestroy((cudaStream_t)copy_stream_);
+  if (back_stream_) cudaStreamDestroy((cudaStream_t)back_stream_);
   if (own_stream_) cudaStreamDestroy((cudaStream_t)own_stream_);
 }
 
@@ -179,7 +182,11 @@ int Regex::check(int e, const char* what) {
     if (rc__) return rc__;                              \
   } while (0)
 
-int Regex::ensure(DfaKind k, DeviceDfa** out) {
+// Stream, pinned scalars and timing events of this object.  Every copy and kernel of the
+// library is issued on stream_ (or on the two pipeline streams, ordered by events), never on
+// the legacy default stream: own_stream_ is non-blocking, so a default-stream copy would not
+// be ordered with the kernels that follow it.
+int Regex::init_device() {
   if (!pinned_) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -188,9 +195,20 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
     RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     own_stream_ = s;
     RB_CUDA(cudaMallocHost(&pinned_, 4096));
+    for (void*& e : timing_events_) {
+      cudaEvent_t ev;
+      RB_CUDA(cudaEventCreate(&ev));
+      e = ev;
+    }
   }
   stream_ = use_ext_stream_ ? ext_stream_ : own_stream_;
+  return 0;
+}
+
+int Regex::ensure(DfaKind k, DeviceDfa** out) {
+  if (int rc = init_device()) return rc;
   if (dev_[k]) { *out = dev_[k]; return 0; }
+  cudaStream_t up = (cudaStream_t)stream_;
   rb::Error err;
   const rb::Dfa* h = host_dfa(k, &err);
   if (!h) return fail(err.msg);
@@ -199,9 +217,9 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
   RB_CUDA(cudaMalloc(&d->trans, std::max<size_t>(tb, 16)));
   RB_CUDA(cudaMalloc(&d->classes, 256));
   RB_CUDA(cudaMalloc(&d->masks, std::max<size_t>(h->masks.size() * 8, 16)));
-  RB_CUDA(cudaMemcpy(d->trans, h->trans.data(), tb, cudaMemcpyHostToDevice));
-  RB_CUDA(cudaMemcpy(d->classes, h->classes, 256, cudaMemcpyHostToDevice));
-  RB_CUDA(cudaMemcpy(d->masks, h->masks.data(), h->masks.size() * 8, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpyAsync(d->trans, h->trans.data(), tb, cudaMemcpyHostToDevice, up));
+  RB_CUDA(cudaMemcpyAsync(d->classes, h->classes, 256, cudaMemcpyHostToDevice, up));
+  RB_CUDA(cudaMemcpyAsync(d->masks, h->masks.data(), h->masks.size() * 8, cudaMemcpyHostToDevice, up));
   DfaView& v = d->view;
   v.trans = (const uint16_t*)d->trans;
   v.classes = (const uint8_t*)d->classes;
@@ -257,10 +275,11 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
       RB_CUDA(cudaMalloc(&d->eof, eof.size() * 2));
       RB_CUDA(cudaMalloc(&d->hot2full, hot2full.size() * 2));
       RB_CUDA(cudaMalloc(&d->full2hot, full2hot.size() * 2));
-      RB_CUDA(cudaMemcpy(d->next256, n256.data(), n256.size() * 2, cudaMemcpyHostToDevice));
-      RB_CUDA(cudaMemcpy(d->eof, eof.data(), eof.size() * 2, cudaMemcpyHostToDevice));
-      RB_CUDA(cudaMemcpy(d->hot2full, hot2full.data(), hot2full.size() * 2, cudaMemcpyHostToDevice));
-      RB_CUDA(cudaMemcpy(d->full2hot, full2hot.data(), full2hot.size() * 2, cudaMemcpyHostToDevice));
+      RB_CUDA(cudaMemcpyAsync(d->next256, n256.data(), n256.size() * 2, cudaMemcpyHostToDevice, up));
+      RB_CUDA(cudaMemcpyAsync(d->eof, eof.data(), eof.size() * 2, cudaMemcpyHostToDevice, up));
+      RB_CUDA(cudaMemcpyAsync(d->hot2full, hot2full.data(), hot2full.size() * 2, cudaMemcpyHostToDevice, up));
+      RB_CUDA(cudaMemcpyAsync(d->full2hot, full2hot.data(), full2hot.size() * 2, cudaMemcpyHostToDevice, up));
+      RB_CUDA(cudaStreamSynchronize(up));  // the host vectors above die with this scope
       d->hot.next256 = (const uint16_t*)d->next256;
       d->hot.eof = (const uint16_t*)d->eof;
       d->hot.hot2full = (const uint16_t*)d->hot2full;
@@ -271,7 +290,8 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
     }
   }
   RB_CUDA(cudaMalloc(&d->view_dev, sizeof(DfaView)));
-  RB_CUDA(cudaMemcpy(d->view_dev, &d->view, sizeof(DfaView), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpyAsync(d->view_dev, &d->view, sizeof(DfaView), cudaMemcpyHostToDevice, up));
+  RB_CUDA(cudaStreamSynchronize(up));
   dev_[k] = d.release();
   *out = dev_[k];
   return 0;
@@ -349,7 +369,6 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (!a.bitmap || !a.guess || !a.fin || !redo || !counters) return fail("out of device memory (scan scratch)");
   a.flag0 = (uint8_t*)(counters + 24);
   a.utf8_boundaries = utf8_mask;
-  if (const char* pr = getenv("RB200_PROBE_SKIP_TABLE")) a.probe_skip_table = atoi(pr);
   a.hot = rev->hot;
   size_t smem;
   uint32_t block;
@@ -461,6 +480,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   std::lock_guard<std::recursive_mutex> lock(mu_);
   io->n_matches = 0;
   io->halo_overflow = false;
+  io->left_ctx_short = false;
   if (is_set_) return fail("find requires exactly one pattern (RegexSet cannot be used with find, exec.rs:510-512)");
   if (io->own_hi > n || io->own_lo > io->own_hi || (io->own_lo & 255) || (!io->is_last && ((io->own_hi & 255) || io->own_hi == n)))
     return fail("bad shard geometry: own_lo/own_hi must be multiples of 256 inside the buffer (own_hi == n only for the last shard)");
@@ -471,8 +491,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   DeviceDfa* revall;
   if (int rc = ensure(kRevUnanchoredAll, &revall)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  cudaEvent_t ev[3];
-  for (auto& e : ev) RB_CUDA(cudaEventCreate(&e));
+  cudaEvent_t ev[3] = {(cudaEvent_t)timing_events_[0], (cudaEvent_t)timing_events_[1], (cudaEvent_t)timing_events_[2]};
   RB_CUDA(cudaEventRecord(ev[0], st));
   const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi,
                                    revall->hot.n != 0 && fast_scan_smem(hot_bytes(revall->hot.n)) <= 227 * 1024);
@@ -509,11 +528,12 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   uint32_t* dirty_list = (uint32_t*)dirty_.ensure(nc * 4);
   w.first_cand = (uint64_t*)first_cand_.ensure(nc * 8);
   w.skip = (uint32_t*)skip_.ensure(nc * 4);
+  w.meta = (uint32_t*)meta_.ensure(nc * 4);
   w.stage = (uint64_t*)stage_.ensure(nc * (uint64_t)w.stage_cap * 16);
   const uint64_t n_blocks = (nc + 1023) / 1024;
   uint64_t* block_sums = (uint64_t*)block_sums_.ensure(n_blocks * 8);
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
-  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !dirty_list || !w.first_cand || !w.skip || !w.stage || !block_sums || !counters)
+  if (!w.in_p || !w.in_lm || !w.out_p || !w.out_lm || !w.count || !offset || !dirty_list || !w.first_cand || !w.skip || !w.meta || !w.stage || !block_sums || !counters)
     return fail("out of device memory (walk scratch)");
   w.offset = offset;
   w.out = d_out;
@@ -523,7 +543,9 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   w.can_match_empty = can_match_empty;
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
   w.err_flag = counters + 28;
-  RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 4, st));
+  w.floor_flag = counters + 29;
+  w.clamp_p = io->chain_clamped ? io->chain_p : kNone;
+  RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 8, st));
   init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, w.skip, nc, io->chain_p, io->chain_lm);
   RB_LAUNCH_CHECK("init_walk_entries");
   size_t wsmem = 0;
@@ -552,23 +574,58 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     launch_walk(w, nc);
     RB_LAUNCH_CHECK("walk_chunks");
   }
-  stats.stitch_rounds = stats.stitch_dirty_chunks = 0;
-  for (;;) {
-    RB_CUDA(cudaMemsetAsync(counters, 0, 8, st));  // [0] chunks to walk again, [1] chunks whose exit state changed by trimming
+  // ---- stitch: bring the speculative chunk walks into agreement with the sequential iterator ----
+  stats.stitch_rounds = stats.stitch_dirty_chunks = stats.sequential_passes = 0;
+  const bool strict = emulate || can_match_empty;
+  bool general = strict;
+  uint32_t* hc = (uint32_t*)pinned_ + 64;  // host copy of counters[0..3]
+  if (!strict) {
+    RB_CUDA(cudaMemsetAsync(counters, 0, 16, st));
+    stitch_fast<<<grid_for(nc, 256, 8), 256, 0, st>>>(w, counters);
+    RB_LAUNCH_CHECK("stitch_fast");
+    RB_CUDA(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    general = hc[2] != 0;
+  }
+  ChainKey* grand_key = nullptr;
+  if (general) {
+    ChainKey* excl = (ChainKey*)excl_.ensure(nc * sizeof(ChainKey));
+    ChainKey* btot = (ChainKey*)btot_.ensure((n_blocks + 1) * sizeof(ChainKey));
+    if (!excl || !btot) return fail("out of device memory (stitch scratch)");
+    grand_key = btot + n_blocks;
     WalkArgs wd = w;
     wd.dirty_list = dirty_list;
     wd.n_dirty = counters;
-    stitch_check<<<grid_for(nc, 256, 8), 256, 0, st>>>(wd, counters);
-    RB_LAUNCH_CHECK("stitch_check");
-    RB_CUDA(cudaMemcpyAsync(pinned_, counters, 8, cudaMemcpyDeviceToHost, st));
-    RB_CUDA(cudaStreamSynchronize(st));
-    const uint32_t n_dirty = ((uint32_t*)pinned_)[0], n_changed = ((uint32_t*)pinned_)[1];
-    if (n_dirty == 0 && n_changed == 0) break;
-    stats.stitch_rounds++;
-    stats.stitch_dirty_chunks += n_dirty;
-    if (n_dirty) {
-      launch_walk(wd, n_dirty);
-      RB_LAUNCH_CHECK("walk_chunks(dirty)");
+    uint32_t dirty_rounds = 0;
+    for (;;) {
+      entries_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w, excl, btot);
+      RB_LAUNCH_CHECK("entries_local");
+      entries_blocks<<<1, 1024, 0, st>>>(btot, n_blocks, grand_key);
+      RB_LAUNCH_CHECK("entries_blocks");
+      RB_CUDA(cudaMemsetAsync(counters, 0, 12, st));       // [0] chunks to walk again, [1] changed decisions
+      RB_CUDA(cudaMemsetAsync(counters + 3, 0xFF, 4, st));  // [3] smallest chunk index to walk again
+      stitch_resolve<<<grid_for(nc, 256, 8), 256, 0, st>>>(wd, excl, btot, counters);
+      RB_LAUNCH_CHECK("stitch_resolve");
+      RB_CUDA(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, st));
+      RB_CUDA(cudaStreamSynchronize(st));
+      const uint32_t n_dirty = hc[0], n_changed = hc[1];
+      if (n_dirty == 0 && n_changed == 0) break;
+      stats.stitch_rounds++;
+      stats.stitch_dirty_chunks += n_dirty;
+      if (n_dirty == 0) continue;
+      if (++dirty_rounds > tuning.max_stitch_rounds) {
+        // chains that do not meet again: one sequential pass from the leftmost such chunk
+        wd.seq_from = hc[3];
+        if (wkind == 2) walk_sequential<2><<<1, 256, 0, st>>>(wd);
+        else if (wkind == 1) walk_sequential<1><<<1, 256, wsmem, st>>>(wd);
+        else walk_sequential<0><<<1, 256, wsmem, st>>>(wd);
+        RB_LAUNCH_CHECK("walk_sequential");
+        stats.sequential_passes++;
+        dirty_rounds = 0;
+      } else {
+        launch_walk(wd, n_dirty);
+        RB_LAUNCH_CHECK("walk_chunks(dirty)");
+      }
     }
   }
   unsigned long long* grand = (unsigned long long*)(counters + 4);
@@ -587,21 +644,32 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   }
   uint64_t* h = (uint64_t*)pinned_;
   RB_CUDA(cudaMemcpyAsync(h, grand, 8, cudaMemcpyDeviceToHost, st));
-  RB_CUDA(cudaMemcpyAsync(h + 1, w.out_p + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
-  RB_CUDA(cudaMemcpyAsync(h + 2, w.out_lm + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
-  RB_CUDA(cudaMemcpyAsync(h + 3, w.err_flag, 4, cudaMemcpyDeviceToHost, st));
+  if (grand_key) {  // exit state = the last contribution of the whole range
+    RB_CUDA(cudaMemcpyAsync(h + 1, grand_key, 16, cudaMemcpyDeviceToHost, st));
+  } else {
+    RB_CUDA(cudaMemcpyAsync(h + 1, w.out_p + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(h + 2, w.out_lm + (nc - 1), 8, cudaMemcpyDeviceToHost, st));
+  }
+  RB_CUDA(cudaMemcpyAsync(h + 3, w.err_flag, 8, cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaEventRecord(ev[2], st));
   RB_CUDA(cudaStreamSynchronize(st));
   io->n_matches = h[0];
-  io->exit_p = h[1];
-  io->exit_lm = h[2];
-  io->halo_overflow = *(uint32_t*)(h + 3) != 0;
+  if (grand_key) {  // ChainKey: 0 = nothing in this range moved the iterator (speculative shard without candidates)
+    io->exit_p = h[1] == 0 ? kSpec : (h[1] == ~0ull ? kNone : h[1] - 1);
+    io->exit_lm = h[1] == 0 ? kNone : h[2];
+  } else {
+    io->exit_p = h[1];
+    io->exit_lm = h[2];
+  }
+  io->halo_overflow = ((uint32_t*)(h + 3))[0] != 0;
+  io->left_ctx_short = ((uint32_t*)(h + 3))[1] != 0;
   stats.fused = fused;
   cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
   cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
   cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);
-  for (auto& e : ev) cudaEventDestroy(e);
   if (io->halo_overflow) return fail("a match runs past the end of the shard halo; enlarge the halo");
+  if (io->left_ctx_short)
+    return fail("the reverse-on-slice scan of a look-around pattern reaches the start of the shard buffer; enlarge the left context");
   return 0;
 }
 
@@ -615,7 +683,8 @@ int Regex::find_at_device(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   if (int rc = find_all_device(d_text, n, start, d_out, 1, &total)) return rc;
   if (total == 0) return 0;
   uint64_t h[2];
-  RB_CUDA(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   *found = true;
   *s = h[0];
   *e = h[1];
@@ -733,7 +802,12 @@ int Regex::set_matches_device(const uint8_t* d_text, uint64_t n, uint64_t start,
 int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (n_rec == 0) return 0;
-  if (patterns_.empty()) { RB_CUDA(cudaMemset(d_bits, 0, (n_rec + 31) / 32 * 4)); return 0; }
+  if (patterns_.empty()) {
+    if (int rc = init_device()) return rc;
+    RB_CUDA(cudaMemsetAsync(d_bits, 0, (n_rec + 31) / 32 * 4, (cudaStream_t)stream_));
+    RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+    return 0;
+  }
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
   BatchArgs a{};
@@ -798,7 +872,12 @@ int Regex::set_matches_batch_device(const uint8_t* d_text, const uint64_t* d_off
   std::lock_guard<std::recursive_mutex> lock(mu_);
   if (n_rec == 0) return 0;
   const uint32_t mw = (uint32_t)std::max<size_t>(1, (patterns_.size() + 63) / 64);
-  if (patterns_.empty()) { RB_CUDA(cudaMemset(d_masks, 0, n_rec * 8 * mw)); return 0; }
+  if (patterns_.empty()) {
+    if (int rc = init_device()) return rc;
+    RB_CUDA(cudaMemsetAsync(d_masks, 0, n_rec * 8 * mw, (cudaStream_t)stream_));
+    RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+    return 0;
+  }
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
   BatchArgs a{};
@@ -817,17 +896,19 @@ int Regex::set_matches_batch_device(const uint8_t* d_text, const uint64_t* d_off
 }
 
 // ------------------------------------------------------------ host wrappers ----
+// device -> host on the library's stream, complete on return
+int Regex::d2h(void* dst, const void* src, size_t bytes) {
+  int e = (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream_);
+  if (e != cudaSuccess) return e;
+  return (int)cudaStreamSynchronize((cudaStream_t)stream_);
+}
+
 const uint8_t* Regex::upload_text(const uint8_t* text, uint64_t n, int* rc) {
-  *rc = 0;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-    *rc = fail("no CUDA device available: regex_b200 has no CPU matching path");
-    return nullptr;
-  }
+  if ((*rc = init_device())) return nullptr;
   uint8_t* d = (uint8_t*)text_.ensure(n + 64);
   if (!d) { *rc = fail("out of device memory (haystack)"); return nullptr; }
-  if (n) {
-    int e = (int)cudaMemcpy(d, text, n, cudaMemcpyHostToDevice);
+  if (n) {  // stream-ordered with the kernels that read it
+    int e = (int)cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, (cudaStream_t)stream_);
     if (e != cudaSuccess) { *rc = check(e, "haystack upload"); return nullptr; }
   }
   return d;
@@ -854,7 +935,7 @@ int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, 
   if (const char* e = getenv("RB200_PIPELINE_PIECE")) piece = (uint64_t)atoll(e) / 256 * 256;
   const uint64_t halo = 64 << 10;
   if (piece == 0 || n < 2 * piece || is_set_ || patterns_.empty()) {
-    RB_CUDA(cudaMemcpy(d, text, n, cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
     return 1;
   }
   if (!copy_stream_) {
@@ -866,19 +947,24 @@ int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, 
   }
   cudaStream_t up = (cudaStream_t)copy_stream_, back = (cudaStream_t)back_stream_;
   const uint64_t n_pieces = (n + piece - 1) / piece;
-  std::vector<cudaEvent_t> arrived(n_pieces);
-  for (uint64_t i = 0; i < n_pieces; i++) {
-    const uint64_t lo = i * piece, len = std::min(piece, n - lo);
-    RB_CUDA(cudaMemcpyAsync(d + lo, text + lo, len, cudaMemcpyHostToDevice, up));
-    RB_CUDA(cudaEventCreateWithFlags(&arrived[i], cudaEventDisableTiming));
-    RB_CUDA(cudaEventRecord(arrived[i], up));
-  }
-  auto cleanup = [&](int rc) {
+  std::vector<cudaEvent_t> arrived(n_pieces, nullptr);
+  auto cleanup = [&](int rc) {  // every exit goes through here
     cudaStreamSynchronize(up);  // the plain path needs the whole text anyway
     cudaStreamSynchronize(back);
-    for (auto& e : arrived) cudaEventDestroy(e);
+    for (auto& e : arrived) if (e) cudaEventDestroy(e);
     return rc;
   };
+#define RB_PIPE(call)                                    \
+  do {                                                   \
+    int rc__ = check((int)(call), #call);                \
+    if (rc__) return cleanup(rc__);                      \
+  } while (0)
+  for (uint64_t i = 0; i < n_pieces; i++) {
+    const uint64_t lo = i * piece, len = std::min(piece, n - lo);
+    RB_PIPE(cudaMemcpyAsync(d + lo, text + lo, len, cudaMemcpyHostToDevice, up));
+    RB_PIPE(cudaEventCreateWithFlags(&arrived[i], cudaEventDisableTiming));
+    RB_PIPE(cudaEventRecord(arrived[i], up));
+  }
   // scratch sized for the whole haystack up front (DeviceBuf::ensure reallocates on growth)
   if (!bitmap_.ensure(((n >> 6) + 2) * 8)) return cleanup(fail("out of device memory (bitmap)"));
   uint64_t done = 0, chain_p = 0, chain_lm = kNone;
@@ -886,7 +972,7 @@ int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, 
   for (uint64_t i = 0; i < n_pieces; i++) {
     const uint64_t lo = i * piece, hi = std::min(n, lo + piece);
     const uint64_t n_i = std::min(n, hi + halo);  // resident prefix this piece may read
-    RB_CUDA(cudaEventSynchronize(arrived[std::min(n_pieces - 1, (n_i - 1) / piece)]));
+    RB_PIPE(cudaEventSynchronize(arrived[std::min(n_pieces - 1, (n_i - 1) / piece)]));
     ShardIO io;
     io.own_lo = lo;
     io.own_hi = hi;
@@ -905,7 +991,7 @@ int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, 
     prev_guess = hi < n ? io.rev_guess : kNoState;
     if (dst) {
       const uint64_t k = std::min(room, io.n_matches);
-      if (k) RB_CUDA(cudaMemcpyAsync(out + 2 * done, dst, k * 16, cudaMemcpyDeviceToHost, back));
+      if (k) RB_PIPE(cudaMemcpyAsync(out + 2 * done, dst, k * 16, cudaMemcpyDeviceToHost, back));
     }
     done += io.n_matches;
     chain_p = io.exit_p;
@@ -916,15 +1002,14 @@ int Regex::find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, 
   }
   *total = done;
   return cleanup(0);
+#undef RB_PIPE
 }
 
 int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64_t* out, uint64_t cap, uint64_t* total) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
   int rc;
   if (start == 0 && n >= (8u << 20) && out && cap) {
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-      return fail("no CUDA device available: regex_b200 has no CPU matching path");
+    if ((rc = init_device())) return rc;
     uint8_t* dd = (uint8_t*)text_.ensure(n + 64);
     uint64_t* d_out = (uint64_t*)out_.ensure(cap * 16);
     if (!dd || !d_out) return fail("out of device memory (haystack / spans)");
@@ -936,7 +1021,7 @@ int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64
     // not applicable or abandoned: the text is resident now, search it in one piece
     if ((rc = find_all_device(dd, n, 0, d_out, cap, total))) return rc;
     const uint64_t k = std::min(cap, *total);
-    if (k) RB_CUDA(cudaMemcpy(out, d_out, k * 16, cudaMemcpyDeviceToHost));
+    if (k) RB_CUDA(d2h(out, d_out, k * 16));
     return 0;
   }
   const uint8_t* d = upload_text(text, n, &rc);
@@ -948,7 +1033,7 @@ int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64
   }
   if ((rc = find_all_device(d, n, start, d_out, cap, total))) return rc;
   const uint64_t k = std::min(cap, *total);
-  if (d_out && k) RB_CUDA(cudaMemcpy(out, d_out, k * 16, cudaMemcpyDeviceToHost));
+  if (d_out && k) RB_CUDA(d2h(out, d_out, k * 16));
   return 0;
 }
 int Regex::find_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e) {
@@ -981,9 +1066,9 @@ int Regex::is_match_batch_host(const uint8_t* text, const uint64_t* offsets, uin
   uint64_t* d_off = (uint64_t*)offsets_.ensure((n_rec + 1) * 8);
   uint32_t* d_bits = (uint32_t*)bits_.ensure((n_rec + 31) / 32 * 4 + 4);
   if (!d_off || !d_bits) return fail("out of device memory (batch)");
-  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpyAsync(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
   if ((rc = is_match_batch_device(d, d_off, n_rec, d_bits))) return rc;
-  RB_CUDA(cudaMemcpy(out_bits, d_bits, (n_rec + 7) / 8, cudaMemcpyDeviceToHost));
+  RB_CUDA(d2h(out_bits, d_bits, (n_rec + 7) / 8));
   return 0;
 }
 int Regex::find_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* spans, uint8_t* out_bits) {
@@ -996,10 +1081,10 @@ int Regex::find_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_
   uint32_t* d_bits = (uint32_t*)bits_.ensure((n_rec + 31) / 32 * 4 + 4);
   uint64_t* d_spans = (uint64_t*)out_.ensure(std::max<uint64_t>(n_rec, 1) * 16);
   if (!d_off || !d_bits || !d_spans) return fail("out of device memory (batch)");
-  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpyAsync(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
   if ((rc = find_batch_device(d, d_off, n_rec, d_spans, d_bits))) return rc;
-  RB_CUDA(cudaMemcpy(out_bits, d_bits, (n_rec + 7) / 8, cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaMemcpy(spans, d_spans, n_rec * 16, cudaMemcpyDeviceToHost));
+  RB_CUDA(d2h(out_bits, d_bits, (n_rec + 7) / 8));
+  RB_CUDA(d2h(spans, d_spans, n_rec * 16));
   return 0;
 }
 int Regex::set_matches_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint64_t* masks) {
@@ -1012,9 +1097,9 @@ int Regex::set_matches_batch_host(const uint8_t* text, const uint64_t* offsets, 
   uint64_t* d_off = (uint64_t*)offsets_.ensure((n_rec + 1) * 8);
   uint64_t* d_masks = (uint64_t*)masks_.ensure(std::max<uint64_t>(n_rec, 1) * 8 * mw);
   if (!d_off || !d_masks) return fail("out of device memory (batch)");
-  RB_CUDA(cudaMemcpy(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpyAsync(d_off, offsets, (n_rec + 1) * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
   if ((rc = set_matches_batch_device(d, d_off, n_rec, d_masks))) return rc;
-  RB_CUDA(cudaMemcpy(masks, d_masks, n_rec * 8 * mw, cudaMemcpyDeviceToHost));
+  RB_CUDA(d2h(masks, d_masks, n_rec * 8 * mw));
   return 0;
 }
 

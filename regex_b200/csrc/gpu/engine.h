@@ -33,11 +33,13 @@ struct Tuning {
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;
   uint32_t blocks_per_sm = 8;
+  uint32_t max_stitch_rounds = 16;  // re-walk rounds before the stitch falls back to one sequential pass
+  uint32_t max_redo_rounds = 3;     // scan redo rounds before segment entry states are solved by state-map composition
 };
 
 struct Stats {  // filled by the last single-haystack call (diagnostics, bench roofline)
   uint64_t scan_redo_rounds = 0, scan_redo_segments = 0;
-  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0;
+  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0, sequential_passes = 0, map_passes = 0;
   float scan_ms = 0, walk_ms = 0, total_ms = 0;
   bool fused = false;  // the scan kernel also walked the chains (scan_ms covers both)
 };
@@ -53,12 +55,15 @@ struct ShardIO {
   uint32_t rev_entry = kNoState;    // exact reverse-scan state at own_hi from the right neighbour
   uint64_t chain_p = 0, chain_lm = ~0ull;  // iterator state entering the shard (kSpec = speculate)
   bool reuse_scan = false;          // keep the start bitmap of the previous call on this buffer
+  bool chain_clamped = false;       // chain_p stands in for a restart point left of the buffer (look-around patterns:
+                                    // the call fails with left_ctx_short if the answer would depend on bytes before it)
   // out
   uint32_t rev_guess = 0;           // state assumed at own_hi
   uint32_t rev_left = 0;            // exact state at own_lo (what the left neighbour must assume)
   uint64_t exit_p = 0, exit_lm = 0; // iterator state leaving the shard
   uint64_t n_matches = 0;
   bool halo_overflow = false;
+  bool left_ctx_short = false;
 };
 
 class DeviceBuf {
@@ -118,6 +123,8 @@ class Regex {
  private:
   Regex() = default;
   struct DeviceDfa;
+  int init_device();
+  int d2h(void* dst, const void* src, size_t bytes);
   int ensure(DfaKind k, DeviceDfa** out);
   int fail(const std::string& msg);
   int check(int cuda_err, const char* what);
@@ -145,8 +152,9 @@ class Regex {
   bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
-  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, stage_, block_sums_, out_, bits_, masks_;
+  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
+  void* timing_events_[3] = {nullptr, nullptr, nullptr};
 };
 
 uint64_t kernel_launches();  // total kernels launched by this library in this process

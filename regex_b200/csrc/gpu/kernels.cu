@@ -332,7 +332,10 @@ __device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const Table& 
 // Start of the match ending at e, found the way the reference does it: the
 // reverse DFA over the slice text[p..] (src/exec.rs:651-657), so position p is
 // judged as beginning-of-text (SURVEY.md §8 hazard H1).
-__device__ __forceinline__ uint64_t slice_start(const DfaView& d, const uint8_t* text, uint64_t n, uint64_t p, uint64_t e) {
+// floor: non-null when p is only a stand-in for a restart point left of a shard's buffer;
+// set when the reverse scan reaches p alive, i.e. when the answer depends on what lies there.
+__device__ __forceinline__ uint64_t slice_start(const DfaView& d, const uint8_t* text, uint64_t n, uint64_t p, uint64_t e,
+                                                uint32_t* floor = nullptr) {
   const uint8_t* t = text + p;
   const uint64_t len = n - p;
   uint64_t at = e - p;
@@ -345,6 +348,7 @@ __device__ __forceinline__ uint64_t slice_start(const DfaView& d, const uint8_t*
     if (st == 0) return last == kNone ? kNone : p + last;
     if (st >= d.match_lo) last = at + 1;
   }
+  if (floor) *floor = 1;
   st = d.trans[st * d.stride + d.stride - 1];
   if (st >= d.match_lo) last = 0;
   return last == kNone ? kNone : p + last;
@@ -459,17 +463,6 @@ struct Chain {
   bool chain;      // p is a real restart point of the reference iterator
 };
 
-// Is a speculative walk that assumed "the chain enters at or before `region_first`"
-// still valid when the chain really enters at (tp, tl)?  (strict: patterns that can
-// match empty or need the slice emulation depend on the exact entry.)
-__device__ __forceinline__ bool spec_ok(const WalkArgs& a, uint64_t tp, uint64_t tl, uint64_t region_first,
-                                        uint64_t first_cand, uint64_t region_next) {
-  if (tp == kNone) return false;
-  if (a.emulate_slice || a.can_match_empty)
-    return tp < region_first || (tp == region_first && !a.emulate_slice && !(a.can_match_empty && tl == region_first));
-  return tp <= first_cand && tp <= region_next;
-}
-
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
                                                       uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz);
@@ -536,7 +529,7 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
     if (a.emulate_slice && c.chain && e != c.p) {
       // exec.rs:647-657: an empty match at the restart point short-circuits; otherwise
       // the start comes from the reverse DFA over text[p..].
-      ms = slice_start(a.rev, a.text, a.n, c.p, e);
+      ms = slice_start(a.rev, a.text, a.n, c.p, e, c.p == a.clamp_p ? a.floor_flag : nullptr);
       if (ms == kNone) { c.p = kNone; break; }  // NoMatch => find_at None => the iteration stops
     }
     c.chain = true;
@@ -681,6 +674,18 @@ struct RunnerSetup<1> {
   }
 };
 
+// What every walk leaves behind for the stitch: exit state, counts, and whether the chunk
+// holds any candidate at all (a speculative walk that met none is IDENT: the iterator
+// passes through it unchanged whatever its entry state).
+__device__ __forceinline__ void finish_chunk(const WalkArgs& a, uint64_t k, const Chain& c, uint64_t total, uint64_t fc, bool spec) {
+  a.out_p[k] = c.p;
+  a.out_lm[k] = c.lm;
+  a.count[k] = total;
+  a.first_cand[k] = fc;
+  a.skip[k] = 0;
+  a.meta[k] = (uint32_t)min(total, (uint64_t)kMetaCount) | ((spec && fc == kNone ? kChunkIdent : kChunkOk) << 30);
+}
+
 // One thread per chunk: walk the chain speculatively (or from a given entry state),
 // staging up to stage_cap spans per chunk.  With a dirty list (after stitch_check)
 // only the listed chunks are walked again, densely packed into warps.
@@ -695,14 +700,11 @@ __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
     c.p = a.in_p[k];
     c.lm = a.in_lm[k];
     c.chain = c.p != kSpec;
-    if (!c.chain) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
+    const bool spec = !c.chain;
+    if (spec) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
     uint64_t fc = kNone, total = 0;
     if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
-    a.out_p[k] = c.p;
-    a.out_lm[k] = c.lm;
-    a.count[k] = total;
-    a.first_cand[k] = fc;
-    if (a.dirty_list) a.skip[k] = 0;  // the staged list is a fresh chain from in_p[k]
+    finish_chunk(a, k, c, total, fc, spec);
   }
 }
 template __global__ void walk_chunks<0>(WalkArgs);
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
     const uint64_t my_cnt = k < a.n_chunks ? a.count[k] : 0;
     const uint64_t my_at = k < a.n_chunks ? a.offset[k] : 0;
     const uint32_t my_skip = k < a.n_chunks ? a.skip[k] : 0;
-    if (my_cnt > a.stage_cap) {  // rare: dense chunk, redo it in place
+    if (my_cnt > a.stage_cap) {  // rare: dense chunk, redo it in place (such a chunk is never trimmed: count == walk count)
       Chain c;
       c.p = a.in_p[k];
       c.lm = a.in_lm[k];
@@ -929,10 +931,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
         uint32_t bhi, blo;
-        if (a.probe_skip_table) { bhi = c0.x ^ c1.y ^ c2.z; blo = c3.w ^ c0.y; }
-        else do_group(c0, c1, c2, c3, rec, bhi, blo);
-        if (a.probe_skip_table == 2) { if ((bhi | blo) == 0x12345u) *bw = 1; }  // probe: no bitmap stores either
-        else if (rec) {
+        do_group(c0, c1, c2, c3, rec, bhi, blo);
+        if (rec) {
           // Bitmap words leave as whole 32-byte sectors (four words, every fourth group):
           // an 8-byte store per group is a partial-sector write from each lane, and those
           // capped the whole kernel at 3.0 TB/s (5.0 TB/s with the stores removed).
@@ -1001,16 +1001,14 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         c.p = wa.in_p[t];
         c.lm = wa.in_lm[t];
         c.chain = c.p != kSpec;
-        if (!c.chain) { c.p = wa.base + t * (uint64_t)wa.chunk + 1; c.lm = kNone; }
+        const bool spec = !c.chain;
+        if (spec) { c.p = wa.base + t * (uint64_t)wa.chunk + 1; c.lm = kNone; }
         uint64_t fc = kNone, total = 0;
         // segments longer than 64 words, the ragged last segment and position 0 fall back to "unknown"
         const bool nz_ok = a.seg <= 4096 && !(hi & 63) && lo != 0;
         if (c.p != kNone)
           total = chunk_walk(wa, R, t, c, &fc, wa.stage, t * (uint64_t)wa.stage_cap, (t + 1) * (uint64_t)wa.stage_cap, nz_ok ? nz : ~0ull);
-        wa.out_p[t] = c.p;
-        wa.out_lm[t] = c.lm;
-        wa.count[t] = total;
-        wa.first_cand[t] = fc;
+        finish_chunk(wa, t, c, total, fc, spec);
       }
     }
   }
@@ -1144,51 +1142,224 @@ __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint32_t* ski
   }
 }
 
-// Compare each chunk's assumed entry state with what its predecessor produced.
-__global__ void stitch_check(WalkArgs a, uint32_t* n_dirty) {
+// ----------------------------------------------------------------- stitch ------
+// Bring the speculative chunk walks into agreement with the sequential iterator
+// (src/re_trait.rs:197-220).  tests/stitch_model.py is the CPU model of this section.
+//
+// A chunk's true entry state is the exit state of the last chunk to its left that
+// CONTRIBUTES: not IDENT (no candidate bit at all -- the iterator passes through, so the
+// chunk hands on what it received, not the first position it assumed) and not COVERED
+// (the iterator jumps over it).  That is an exclusive prefix "max by p, later chunk wins
+// ties" (entries_local / entries_blocks); stitch_resolve then decides per chunk:
+//   - entry beyond the chunk                       -> COVERED, contributes no spans
+//   - speculative walk, entry before the chunk     -> keep; with look-arounds the START of the
+//     first span is re-derived by the reverse-on-slice rule from the true entry
+//     (src/exec.rs:651-657, SURVEY hazard H1) and the chunk is walked again only if that
+//     changes whether the span is empty (or the reverse scan fails: the iteration stops)
+//   - speculative walk entered late, pattern without empty matches / look-arounds -> the real
+//     chain and the speculative one meet at the first staged span that starts at or after the
+//     entry, provided the span before it had ended by then: drop the spans before it
+//   - anything else -> walk again from the exact entry (dirty list)
+// Rounds repeat until nothing changes; the leftmost wrong chunk is right after each round.
+__device__ __forceinline__ uint64_t chain_key(uint64_t p) { return p == kNone ? ~0ull : p + 1; }
+__device__ __forceinline__ uint64_t key_pos(uint64_t key) { return key == ~0ull ? kNone : key - 1; }
+__device__ __forceinline__ ChainKey key_join(const ChainKey& left, const ChainKey& right) {  // associative
+  return right.key != 0 && right.key >= left.key ? right : left;
+}
+__device__ __forceinline__ ChainKey chunk_contribution(const WalkArgs& a, uint64_t k) {
+  ChainKey c{0, kNone};
+  const uint32_t st = a.meta[k] >> 30;
+  if (st == kChunkOk || (k == 0 && a.in_p[0] != kSpec)) { c.key = chain_key(a.out_p[k]); c.lm = a.out_lm[k]; }
+  return c;
+}
+// Drop staged spans in front of tp (see above).  Returns false when the chunk must be walked again.
+__device__ __forceinline__ bool trim_staged(const WalkArgs& a, uint64_t k, uint64_t tp, uint32_t cnt, uint32_t* skip_out) {
+  if (cnt > a.stage_cap) return false;
+  const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
+  uint32_t lo = 0, hi = cnt;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sp[mid].x < tp) lo = mid + 1; else hi = mid;
+  }
+  if (lo != 0 && sp[lo - 1].y > tp) return false;
+  *skip_out = lo;
+  return true;
+}
+
+// Patterns without empty matches / look-arounds, first pass: every chunk looks at its left
+// neighbour only.  Exact unless some exit reaches past the following chunk or a chunk lost
+// all its spans (counters[2] asks for the general loop then; nothing is lost, the loop
+// decides everything again).
+__global__ void stitch_fast(WalkArgs a, uint32_t* counters) {
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
        k += (uint64_t)gridDim.x * blockDim.x) {
-    if (k == 0) continue;
-    const uint64_t tp = a.out_p[k - 1], tl = a.out_lm[k - 1];
-    const uint64_t c_first = a.base + k * (uint64_t)a.chunk + 1;  // first position of the chunk
-    const uint64_t cp = a.in_p[k], cl = a.in_lm[k];
-    bool ok;
-    if (cp == kSpec) ok = spec_ok(a, tp, tl, c_first, a.first_cand[k], c_first + a.chunk);
-    else ok = cp == tp && cl == tl;
-    if (!ok) {
-      // Most wrong speculations are one match of the left neighbour reaching into this chunk.
-      // Without empty matches or look-arounds the speculative chain and the real one meet
-      // again at the first staged span that starts at or after tp, provided the span before
-      // it ended by tp (no candidate lies between a span's end and the next span's start):
-      // drop the spans before it instead of walking the chunk again.
-      bool trimmed = false;
-      if (cp == kSpec && tp != kNone && !a.emulate_slice && !a.can_match_empty) {
-        const uint64_t cnt = a.count[k];
-        if (cnt <= a.stage_cap) {
-          const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
-          uint32_t lo = 0, hi = (uint32_t)cnt;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sp[mid].x < tp) lo = mid + 1; else hi = mid;
-          }
-          if (lo == 0 || sp[lo - 1].y <= tp) {
-            trimmed = true;
-            a.skip[k] = lo;
-            a.count[k] = cnt - lo;
-            if (lo == cnt) {  // nothing left: the chain passes through unchanged; the right neighbour must be looked at again
-              a.out_p[k] = tp;
-              a.out_lm[k] = tl;
-              atomicAdd(n_dirty + 1, 1u);
-            }
-          }
-        }
+    const uint32_t meta = a.meta[k];
+    const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+    const uint64_t ce_next = min(cb + 2 * (uint64_t)a.chunk, a.limit);
+    if ((meta >> 30) == kChunkOk && k + 1 < a.n_chunks && a.out_p[k] > ce_next) counters[2] = 1;  // a match longer than a chunk
+    if (k == 0 || (meta >> 30) != kChunkOk) continue;
+    if ((a.meta[k - 1] >> 30) != kChunkOk) continue;  // the neighbour holds no candidate: the entry cannot lie inside this chunk
+    const uint64_t tp = a.out_p[k - 1];
+    if (tp <= a.first_cand[k]) continue;
+    uint32_t lo;
+    const uint32_t cnt = meta & kMetaCount;
+    if (tp == kNone || !trim_staged(a, k, tp, cnt, &lo) || lo == cnt) { counters[2] = 1; continue; }
+    a.skip[k] = lo;
+    a.count[k] = cnt - lo;
+  }
+}
+
+// Exclusive scan of the chunk contributions inside blocks of blockDim.x chunks.
+__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot) {
+  __shared__ ChainKey ws[32];
+  const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  ChainKey mine = k < a.n_chunks ? chunk_contribution(a, k) : ChainKey{0, kNone};
+  ChainKey x = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    ChainKey y{__shfl_up_sync(0xffffffffu, x.key, o), __shfl_up_sync(0xffffffffu, x.lm, o)};
+    if (lane >= o) x = key_join(y, x);
+  }
+  if (lane == 31) ws[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    ChainKey w = lane < (int)(blockDim.x >> 5) ? ws[lane] : ChainKey{0, kNone};
+    for (int o = 1; o < 32; o <<= 1) {
+      ChainKey y{__shfl_up_sync(0xffffffffu, w.key, o), __shfl_up_sync(0xffffffffu, w.lm, o)};
+      if (lane >= o) w = key_join(y, w);
+    }
+    ws[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  // exclusive value of this thread = (warps before) join (lanes before)
+  ChainKey before{__shfl_up_sync(0xffffffffu, x.key, 1), __shfl_up_sync(0xffffffffu, x.lm, 1)};
+  if (lane == 0) before = ChainKey{0, kNone};
+  if (wid) before = key_join(ws[wid - 1], before);
+  if (k < a.n_chunks) excl[k] = before;
+  if (threadIdx.x == blockDim.x - 1) block_tot[blockIdx.x] = ws[(blockDim.x >> 5) - 1];
+}
+// block_tot[b] := join of the blocks before b (exclusive); *grand = join of all blocks.
+__global__ void entries_blocks(ChainKey* block_tot, uint64_t n_blocks, ChainKey* grand) {
+  __shared__ ChainKey ws[32];
+  __shared__ ChainKey carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = ChainKey{0, kNone};
+  __syncthreads();
+  for (uint64_t base = 0; base < n_blocks; base += blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    const ChainKey mine = i < n_blocks ? block_tot[i] : ChainKey{0, kNone};
+    ChainKey x = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      ChainKey y{__shfl_up_sync(0xffffffffu, x.key, o), __shfl_up_sync(0xffffffffu, x.lm, o)};
+      if (lane >= o) x = key_join(y, x);
+    }
+    if (lane == 31) ws[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      ChainKey w = lane < (int)(blockDim.x >> 5) ? ws[lane] : ChainKey{0, kNone};
+      for (int o = 1; o < 32; o <<= 1) {
+        ChainKey y{__shfl_up_sync(0xffffffffu, w.key, o), __shfl_up_sync(0xffffffffu, w.lm, o)};
+        if (lane >= o) w = key_join(y, w);
       }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    ChainKey before{__shfl_up_sync(0xffffffffu, x.key, 1), __shfl_up_sync(0xffffffffu, x.lm, 1)};
+    if (lane == 0) before = ChainKey{0, kNone};
+    if (wid) before = key_join(ws[wid - 1], before);
+    const ChainKey carry = carry_s;
+    if (i < n_blocks) block_tot[i] = key_join(carry, before);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = key_join(carry, ws[(blockDim.x >> 5) - 1]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand = carry_s;
+}
+
+__global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey* block_tot, uint32_t* counters) {
+  const bool strict = a.emulate_slice || a.can_match_empty;
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
+       k += (uint64_t)gridDim.x * blockDim.x) {
+    if (k == 0) continue;  // chunk 0 holds the real entry state
+    const uint32_t meta = a.meta[k];
+    const uint32_t state = meta >> 30, cnt = meta & kMetaCount;
+    if (state == kChunkIdent) continue;
+    const ChainKey t = key_join(block_tot[k >> 10], excl[k]);  // entries_local runs with 1024 threads per block
+    const bool spec = a.in_p[k] == kSpec;
+    if (t.key == 0) {  // nothing to the left contributes (a shard entered speculatively): the chunk's own speculation stands
+      if (!spec || state != kChunkOk || a.skip[k] != 0 || (meta & kMetaPatched)) { a.dirty_list[atomicAdd(&counters[0], 1u)] = (uint32_t)k; a.in_p[k] = kSpec; a.in_lm[k] = kNone; atomicMin(&counters[3], (uint32_t)k); }
+      continue;
+    }
+    const uint64_t tp = key_pos(t.key), tl = t.lm;
+    const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+    const uint64_t ce = min(cb + a.chunk, a.limit), c_first = cb + 1;
+    uint32_t new_state = kChunkOk, new_skip = 0;
+    uint64_t new_count = cnt;
+    bool rewalk = false;
+    if (tp == kNone || tp > ce) {
+      new_state = kChunkCovered;
+      new_count = 0;
+    } else if (spec) {
+      if (strict) {
+        bool ok = tp < c_first || (tp == c_first && !a.emulate_slice && !(a.can_match_empty && tl == c_first));
+        if (ok && a.emulate_slice && cnt != 0) {
+          // the first staged span came from the chunk's first candidate with its start taken
+          // at face value; the reference finds it by the reverse DFA over text[tp..]
+          ulonglong2* sp = reinterpret_cast<ulonglong2*>(a.stage) + k * (uint64_t)a.stage_cap;
+          const ulonglong2 first = sp[0];
+          const uint64_t ms = slice_start(a.rev, a.text, a.n, tp, first.y, tp == a.clamp_p ? a.floor_flag : nullptr);
+          if (ms == kNone || (ms == first.y) != (first.x == first.y) || cnt > a.stage_cap) ok = false;
+          else if (ms != first.x) { sp[0].x = ms; a.meta[k] = meta | kMetaPatched; }
+        }
+        rewalk = !ok;
+      } else if (tp > a.first_cand[k]) {
+        if (!trim_staged(a, k, tp, cnt, &new_skip)) rewalk = true;
+        else new_count = cnt - new_skip;
+      }
+    } else {
+      rewalk = a.in_p[k] != tp || (strict && a.in_lm[k] != tl);
+    }
+    if (rewalk) {
       a.in_p[k] = tp;
       a.in_lm[k] = tl;
-      if (!trimmed) a.dirty_list[atomicAdd(n_dirty, 1u)] = (uint32_t)k;
+      a.dirty_list[atomicAdd(&counters[0], 1u)] = (uint32_t)k;
+      atomicMin(&counters[3], (uint32_t)k);
+      continue;
+    }
+    if (state != new_state || a.skip[k] != new_skip || a.count[k] != new_count) {
+      a.meta[k] = (a.meta[k] & (kMetaCount | kMetaPatched)) | (new_state << 30);
+      a.skip[k] = new_skip;
+      a.count[k] = new_count;
+      atomicAdd(&counters[1], 1u);
     }
   }
 }
+
+// Last resort for chains that never meet again (e.g. `(?s).{7}` tiling the haystack out of
+// phase with every chunk): ONE thread walks chunk after chunk from a.seq_from to the end, each
+// entered with its predecessor's exact exit state.  Linear time, no host round trips; the
+// stitch loop then finds everything at and after seq_from consistent.
+template <int FAST>
+__global__ void __launch_bounds__(256) walk_sequential(WalkArgs a) {
+  const auto R = RunnerSetup<FAST>::make(a);
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Chain c;
+  c.p = a.in_p[a.seq_from];
+  c.lm = a.in_lm[a.seq_from];
+  c.chain = c.p != kSpec;
+  for (uint64_t k = a.seq_from; k < a.n_chunks; k++) {
+    const bool spec = !c.chain;  // only the first chunk of a speculatively entered shard
+    if (spec) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
+    else { a.in_p[k] = c.p; a.in_lm[k] = c.lm; }
+    uint64_t fc = kNone, total = 0;
+    if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    finish_chunk(a, k, c, total, fc, spec);
+    c.chain = true;  // an IDENT first chunk hands on its assumed first position: nothing lies before it in this shard
+  }
+}
+template __global__ void walk_sequential<0>(WalkArgs);
+template __global__ void walk_sequential<1>(WalkArgs);
+template __global__ void walk_sequential<2>(WalkArgs);
 
 // ------------------------------------------------------------- prefix sums ----
 __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* warp_sums) {

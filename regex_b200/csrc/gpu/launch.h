@@ -31,7 +31,6 @@ struct ScanArgs {
   const uint32_t* n_redo;
   int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
   uint64_t skip_lo, skip_hi;  // scan_fwd_reduce: segments [skip_lo, skip_hi) belong to scan_fwd_fast
-  int probe_skip_table; // measurement probe (RB200_PROBE_SKIP_TABLE=1): move the bytes, skip the automaton
 };
 
 struct WalkArgs {
@@ -42,6 +41,8 @@ struct WalkArgs {
   uint64_t limit;        // candidate bits [base, limit) (== n except for shards)
   int text_continues;    // shard: the haystack goes on after n (no EOF there)
   uint32_t* err_flag;    // set when a match runs past the end of a shard's halo
+  uint64_t clamp_p;      // shard entered at a restart point left of its buffer: the buffer position standing in for it (else kNone)
+  uint32_t* floor_flag;  // set when a reverse-on-slice scan from clamp_p's match reaches clamp_p alive (left context too short)
   const uint64_t* bitmap;
   const uint8_t* flag0;
   uint64_t base;  // first bitmap bit of chunk 0 (64-aligned); bit i <-> position i+1
@@ -55,11 +56,13 @@ struct WalkArgs {
   uint64_t* in_lm;
   uint64_t* out_p;
   uint64_t* out_lm;
-  uint64_t* count;
+  uint64_t* count;          // per chunk: spans it contributes to the output (after trimming / covering)
   const uint64_t* offset;
-  uint32_t* skip;           // per chunk: staged spans dropped from the front by stitch_check (trimmed speculation)
+  uint32_t* skip;           // per chunk: staged spans dropped from the front by the stitch (trimmed speculation)
+  uint32_t* meta;           // per chunk: spans the walk produced (bits 0-28, may exceed stage_cap) | kMetaPatched | chunk state << 30
   uint32_t* dirty_list;     // chunks to walk again (nullable: all chunks)
   const uint32_t* n_dirty;
+  uint64_t seq_from;        // walk_sequential: first chunk of the sequential pass
   HotView fwd_hot;              // fast runner: byte-indexed forward anchored table (hot states)
   uint64_t fixed_len;           // fixed-length runner: every match has this many bytes
   uint64_t* out;  // spans: start, end pairs
@@ -99,8 +102,21 @@ template <int FAST>
 __global__ void walk_chunks(WalkArgs a);
 template <int FAST>
 __global__ void compact_spans(WalkArgs a);
+template <int FAST>
+__global__ void walk_sequential(WalkArgs a);
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint32_t* skip, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
-__global__ void stitch_check(WalkArgs a, uint32_t* n_dirty);
+// Chunk states kept in WalkArgs::meta (bits 30-31).
+constexpr uint32_t kChunkOk = 0, kChunkIdent = 1, kChunkCovered = 2;
+constexpr uint32_t kMetaCount = 0x1FFFFFFFu;
+constexpr uint32_t kMetaPatched = 0x20000000u;  // the first staged span's start was re-derived by the slice rule
+// One entry of the "exit of the last contributing chunk to the left" scan: key = p + 1 (0 = no
+// contribution yet, ~0 = the iteration is over), lm = previous match end that goes with it.
+struct ChainKey { uint64_t key, lm; };
+// counters: [0] dirty chunks, [1] changed decisions, [2] need the general loop, [3] smallest dirty chunk index
+__global__ void stitch_fast(WalkArgs a, uint32_t* counters);
+__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot);
+__global__ void entries_blocks(ChainKey* block_tot, uint64_t n_blocks, ChainKey* grand);
+__global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey* block_tot, uint32_t* counters);
 __global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);
 __global__ void scan_block_sums(uint64_t* block_sums, uint64_t n_blocks, unsigned long long* grand_total);
 __global__ void scan_add_block_offsets(uint64_t* out, const uint64_t* block_sums, uint64_t n);

@@ -136,11 +136,16 @@ class SingleComm:
 
 
 def _spec_ok(tp, tl, c_first, can_match_empty, has_looks):
-    """Mirror of spec_ok() in csrc/gpu/kernels.cu at shard granularity."""
-    if tp == NONE:
+    """Shard-granularity mirror of stitch_resolve() in csrc/gpu/kernels.cu: may a shard that
+    assumed "the iterator enters at my first position" keep its result when the iterator really
+    enters at (tp, tl)?  Look-around patterns never may: the START of the shard's first match
+    comes from the reverse DFA over text[tp..] (src/exec.rs:651-657), so such a shard is always
+    walked again from the exact entry state (the kernels patch the first span in place; across
+    ranks a re-walk is simpler and costs no re-scan)."""
+    if tp == NONE or has_looks:
         return False
-    if can_match_empty or has_looks:
-        return tp < c_first or (tp == c_first and not has_looks and not (can_match_empty and tl == c_first))
+    if can_match_empty:
+        return tp < c_first or (tp == c_first and tl != c_first)
     return tp <= c_first
 
 
@@ -161,7 +166,7 @@ def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
     to_glob = lambda v: v if v in (NONE, SPEC) else v + geom.buf_lo
     owns_bytes = not (geom.a >= geom.b and not geom.is_first)
     io = dict(own_lo=geom.own_lo, own_hi=geom.own_hi, is_first=geom.is_first, is_last=geom.is_last,
-              rev_entry=NO_STATE, reuse_scan=False,
+              rev_entry=NO_STATE, reuse_scan=False, chain_clamped=False,
               chain_p=to_buf(start) if geom.is_first else SPEC, chain_lm=NONE)
     res = engine.run(io) if owns_bytes else None
     rounds = 0
@@ -194,18 +199,21 @@ def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
             buf_lo_g, a_g = allv[g][8], allv[g][9]
             tp, tl = next(((allv[h][2], allv[h][3]) for h in range(g - 1, -1, -1) if allv[h][2] != SPEC))
             cp, cl = allv[g][5], allv[g][6]
-            # an entry left of the buffer is "before my first byte" whatever its value
-            entry = (buf_lo_g, NONE) if (tp != NONE and tp < buf_lo_g) else (tp, NONE if (tl != NONE and tl < buf_lo_g) else tl)
+            # an entry left of the buffer is "before my first byte" whatever its value; look-around
+            # patterns then enter at the buffer's first byte as a stand-in (the engine fails loudly
+            # if a reverse-on-slice scan gets that far: the left context was too short)
+            clamped = tp != NONE and tp < buf_lo_g
+            entry = (buf_lo_g, NONE) if clamped else (tp, NONE if (tl != NONE and tl < buf_lo_g) else tl)
             if cp == SPEC:
-                ok = (tp != NONE and tp < buf_lo_g) or _spec_ok(entry[0], entry[1], a_g + 1, can_match_empty, has_looks)
+                ok = (clamped and not has_looks) or _spec_ok(entry[0], entry[1], a_g + 1, can_match_empty, has_looks)
             else:
                 ok = (cp, cl) == entry
             if not ok:
-                redo_chain[g] = entry
+                redo_chain[g] = entry + (clamped,)
         if redo_chain:
             if me in redo_chain:
-                p_g, l_g = redo_chain[me]
-                io.update(chain_p=to_buf(p_g), chain_lm=to_buf(l_g), reuse_scan=True)
+                p_g, l_g, clamped = redo_chain[me]
+                io.update(chain_p=to_buf(p_g), chain_lm=to_buf(l_g), chain_clamped=clamped, reuse_scan=True)
                 res = engine.run(io)
             rounds += 1
             continue

@@ -46,14 +46,17 @@ class SimShardEngine:
             p, lm = lo + 1, NONE
         out = []
         cands = sorted(S)
+        spec_entry = not chain
+        moved = False
         while p != NONE:
             c = next((q for q in cands if q >= p), None)
             if c is None:
                 break
+            moved = True
             e = s.anchored_end(t, c) if io["is_last"] else self._anchored_end_halo(t, c)
             ms = c
             if info["has_looks"] and chain and e != p:
-                ms = s.slice_start(t, p, e)
+                ms = self._slice_start(t, p, e, io.get("chain_clamped") and p == io["chain_p"])
                 if ms is None:
                     p = NONE
                     break
@@ -67,7 +70,33 @@ class SimShardEngine:
             lm = e
             out.append((ms, e))
         self.spans = out
+        if spec_entry and not moved:  # no candidate at all: the iterator passes through (engine: exit SPEC)
+            p, lm = SPEC, NONE
         return dict(rev_guess=guess, rev_left=rev_left, exit_p=p, exit_lm=lm, n_matches=len(out))
+
+    def _slice_start(self, t, p, e, clamped):
+        """dfa_sim.Sim.slice_start; with a clamped entry, a reverse scan that reaches p alive would
+        depend on bytes left of the buffer (engine: left_ctx_short error)."""
+        s = self.sim
+        d = s.d(R.DFA_REV_ANCHORED_LONGEST)
+        sl = t[p:]
+        at = e - p
+        st = int(d["start"][flags_reverse(sl, at)])
+        last = None
+        if st == 0:
+            return None
+        while at > 0:
+            at -= 1
+            st = s.step(d, st, sl[at])
+            if st == 0:
+                return None if last is None else p + last
+            if st >= d["match_lo"]:
+                last = at + 1
+        assert not clamped, "left context too short"
+        st = s.eof(d, st)
+        if st >= d["match_lo"]:
+            last = 0
+        return None if last is None else p + last
 
     def _anchored_end_halo(self, t, c):
         """anchored_end where running into the end of the buffer is a halo overflow, not EOF."""

@@ -493,3 +493,99 @@ def test_pipelined_host_find_all(monkeypatch):
     monkeypatch.setenv("RB200_PIPELINE_PIECE", str(1 << 20))
     got = _spans(R.BytesRegex(r"[a-zA-Z]+ing").find_all(corpus))
     assert got[:len(exp) - 1] == exp[:len(exp) - 1]
+
+
+# ------------------------------------------- look-arounds at every kind of boundary ----
+def _run_gpu_shards(pat, text, d_text, world, exp_len, halo=256, tuning=None):
+    """Byte-range shards of `text` through one GPU (one thread per shard, in-process collectives)."""
+    import threading
+    from regex_b200 import sharded
+    comm = sharded.ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def work(rank):
+        try:
+            re_ = R.BytesRegex(pat)
+            if tuning:
+                re_.set_tuning(**tuning)
+            info = re_.pattern_info()
+            geom = sharded.plan(len(text), world, rank, halo=halo)
+            buf = d_text[geom.buf_lo:geom.buf_hi].clone()
+            eng = sharded.GpuShardEngine(re_, buf, cap=exp_len + 16)
+            n_local, offset, total, _ = sharded.find_all_sharded(eng, geom, comm.view(rank), info["can_match_empty"], info["has_looks"])
+            out[rank] = (offset, (eng.spans[:n_local] + geom.buf_lo).cpu().numpy(), total)
+        except Exception as e:  # noqa: BLE001 -- surface instead of dead-locking the barrier
+            errs.append(e)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    if errs:
+        real = [e for e in errs if "BrokenBarrier" not in type(e).__name__]
+        raise real[0] if real else errs[0]
+    merged = []
+    for off, sp, total in out:
+        assert off == len(merged) and total == exp_len
+        merged += [tuple(int(v) for v in r) for r in sp.tolist()]
+    return merged
+
+
+def test_look_around_patterns_at_chunk_and_shard_boundaries():
+    """>= 2000 random patterns WITH look-arounds (the grammar of test_fuzz_tables_vs_oracle: ^ $ (?m:^)
+    (?m:$) \\b \\B next to classes, lazy/greedy repeats, alternations) on 64-byte segments and
+    64-bit chunks, whole haystack and 2-4 shards, against the oracle: the reference's
+    reverse-on-slice rule (src/exec.rs:651-657) at speculative chunk / shard entries, chunks
+    without candidates, empty matches at boundaries."""
+    import torch
+    from test_fuzz_tables_vs_oracle import _pattern
+    rng = np.random.Generator(np.random.PCG64(0x100C5))
+    cases = shard_cases = explicit = 0
+    tries = 0
+    while cases < 2000 and tries < 20000:
+        tries += 1
+        p = _pattern(rng)
+        if all(x not in p for x in ("α", "é", "3b1", "pL")):
+            p = "(?-u)" + p
+        try:
+            r = R.BytesRegex(p)
+        except R.Error:
+            continue
+        if not r.pattern_info()["has_looks"]:
+            continue
+        o = O.OracleRegex(p)
+        text = xorshift_bytes(int(rng.integers(0, 1 << 30)), int(rng.integers(600, 2600)), b"abc \n" if rng.random() < 0.7 else b"ab1 _\n")
+        exp = o.find_iter(text)
+        r.set_tuning(seg=64, chunk=64, warm=int(rng.integers(0, 2)) * 16)
+        r.force_generic(bool(rng.integers(0, 2)))
+        got = _spans(r.find_all(text))
+        assert got == exp, (p, text, got[:5], exp[:5])
+        cases += 1
+        if cases % 4 == 0:
+            d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+            try:
+                got = _run_gpu_shards(p, text, d_text, int(rng.integers(2, 5)), len(exp), tuning=dict(seg=64, chunk=64, warm=0))
+            except R.Error as e:
+                assert "enlarge" in str(e), (p, str(e))  # halo / left context too short: explicit, not wrong
+                explicit += 1
+                continue
+            assert got == exp, ("sharded", p, text)
+            shard_cases += 1
+    assert cases >= 2000 and shard_cases >= 300, (cases, shard_cases, explicit)
+
+
+def test_round1_slice_rule_case_on_the_gpu():
+    pat = r"^[ab]{2,}\w*?|(?m:$)"
+    import torch
+    for seed in range(8):
+        text = xorshift_bytes(seed, 948, b"abc \n")
+        exp = O.OracleRegex(pat).find_iter(text)
+        for seg, chunk in ((64, 64), (64, 256), (0, 4096)):
+            r = R.BytesRegex(pat)
+            r.set_tuning(seg=seg, chunk=chunk, warm=0)
+            assert _spans(r.find_all(text)) == exp, (seed, seg, chunk)
+        d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+        assert _run_gpu_shards(pat, text, d_text, 3, len(exp)) == exp, seed
