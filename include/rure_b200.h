@@ -114,6 +114,16 @@ uint64_t rure_b200_kernel_launches(void);
  * total_ms, scan_redo_rounds, scan_redo_segments, stitch_rounds, stitch_dirty_chunks,
  * fused (1 when the scan kernel also walked the chains, so scan_ms covers both) */
 void rure_b200_last_stats(rure *re, double *out8);
+/* The same plus out[8..11] = sequential stitch passes, state-map passes (segments run from
+ * every boundary state), waves of the last forward search, path of the last find_all
+ * (0 generic scan, 1 fast scan, 2 fused scan+walk, 3 literal prefilter).  n = doubles to write. */
+void rure_b200_last_stats_ex(rure *re, double *out, size_t n);
+void rure_b200_set_last_stats_ex(rure_set *set, double *out, size_t n);
+/* Named knobs (tests, tuning): "wave0" bytes of the first wave of is_match / shortest_match /
+ * set matches (x8 per wave, 0 = one wave), "narrow_sets" 0/1, "max_stitch_rounds",
+ * "max_redo_rounds", "prefilter" 0/1.  Returns false for an unknown name. */
+bool rure_b200_set_option(rure *re, const char *name, uint64_t value);
+bool rure_b200_set_set_option(rure_set *set, const char *name, uint64_t value);
 /* seg/chunk are positions per scan segment / walk chunk (multiples of 64);
  * warm = warm-up bytes (0 = automatic); 0 keeps the current value elsewhere. */
 void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block,

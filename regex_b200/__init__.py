@@ -22,6 +22,10 @@ FLAG_CASEI, FLAG_MULTI, FLAG_DOTNL, FLAG_SWAP_GREED, FLAG_SPACE, FLAG_UNICODE = 
 DFA_FWD_ANCHORED_LF, DFA_REV_UNANCHORED_ALL, DFA_FWD_UNANCHORED_ALL, DFA_REV_ANCHORED_LONGEST, DFA_FWD_UNANCHORED_LF = range(5)
 
 
+_STAT_KEYS = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks",
+              "fused", "sequential_passes", "map_passes", "waves", "path"]
+
+
 class Error(Exception):
     """Compile error (syntax, size limit, unsupported construct) or GPU runtime error."""
 
@@ -84,6 +88,10 @@ def _load():
         "rure_b200_last_error": (c_char_p, []),
         "rure_b200_kernel_launches": (c_uint64, []),
         "rure_b200_last_stats": (None, [vp, POINTER(c_double)]),
+        "rure_b200_last_stats_ex": (None, [vp, POINTER(c_double), sz]),
+        "rure_b200_set_last_stats_ex": (None, [vp, POINTER(c_double), sz]),
+        "rure_b200_set_option": (c_bool, [vp, c_char_p, c_uint64]),
+        "rure_b200_set_set_option": (c_bool, [vp, c_char_p, c_uint64]),
         "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
         "rure_b200_force_generic": (None, [vp, c_int]),
         "rure_b200_set_stream": (None, [vp, vp]),
@@ -310,10 +318,14 @@ class _Compiled:
 
     # ---- diagnostics ------------------------------------------------------------
     def last_stats(self):
-        out = (c_double * 8)()
-        _lib.rure_b200_last_stats(self._h, out)
-        keys = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks", "fused"]
-        return dict(zip(keys, list(out)))
+        out = (c_double * 12)()
+        _lib.rure_b200_last_stats_ex(self._h, out, 12)
+        return dict(zip(_STAT_KEYS, list(out)))
+
+    def set_option(self, name, value):
+        """Named engine knobs (include/rure_b200.h: rure_b200_set_option)."""
+        if not _lib.rure_b200_set_option(self._h, name.encode(), int(value)):
+            raise Error(_last_error())
 
     def set_tuning(self, seg=0, chunk=0, warm=0, block=0, blocks_per_sm=0):
         _lib.rure_b200_set_tuning(self._h, seg, chunk, warm, block, blocks_per_sm)
@@ -363,6 +375,15 @@ class Regex(_Compiled):
 
 class _SetBase:
     _only_utf8 = False
+
+    def last_stats(self):
+        out = (c_double * 12)()
+        _lib.rure_b200_set_last_stats_ex(self._h, out, 12)
+        return dict(zip(_STAT_KEYS, list(out)))
+
+    def set_option(self, name, value):
+        if not _lib.rure_b200_set_set_option(self._h, name.encode(), int(value)):
+            raise Error(_last_error())
 
     def __init__(self, patterns, flags=FLAG_UNICODE, size_limit=10 << 20, dfa_size_limit=2 << 20):
         pats = [p.encode("utf-8") if isinstance(p, str) else bytes(p) for p in patterns]
@@ -424,6 +445,11 @@ class _SetBase:
         if not _lib.rure_b200_set_matches_device(self._h, d_text.data_ptr(), d_text.numel(), start, out):
             raise Error(_last_error())
         return list(out)
+
+    def matches_device(self, d_text, start=0):
+        """RegexSet::matches over a device-resident haystack: indices of the matching patterns."""
+        words = self.matches_mask_device(d_text, start)
+        return [i for i in range(len(self)) if (words[i // 64] >> (i % 64)) & 1]
 
     def matches_batch_device(self, d_text, d_offsets, d_masks):
         n_rec = d_offsets.numel() - 1

@@ -321,6 +321,28 @@ void rure_b200_last_stats(rure* re, double* out8) {
   out7[3] = (double)s.scan_redo_rounds; out7[4] = (double)s.scan_redo_segments;
   out7[5] = (double)s.stitch_rounds; out7[6] = (double)s.stitch_dirty_chunks;
 }
+static void stats_ex(Regex* r, double* out, size_t n) {
+  const rbgpu::Stats& s = r->stats;
+  const double v[12] = {s.scan_ms, s.walk_ms, s.total_ms, (double)s.scan_redo_rounds, (double)s.scan_redo_segments,
+                        (double)s.stitch_rounds, (double)s.stitch_dirty_chunks, s.fused ? 1.0 : 0.0,
+                        (double)s.sequential_passes, (double)s.map_passes, (double)s.waves, (double)s.path};
+  for (size_t i = 0; i < n && i < 12; i++) out[i] = v[i];
+}
+void rure_b200_last_stats_ex(rure* re, double* out, size_t n) { stats_ex(re->re, out, n); }
+void rure_b200_set_last_stats_ex(rure_set* set, double* out, size_t n) { stats_ex(set->re, out, n); }
+static bool set_option(Regex* r, const char* name, uint64_t value) {
+  rbgpu::Tuning& t = r->tuning;
+  const std::string k(name ? name : "");
+  if (k == "wave0") t.wave0 = value;
+  else if (k == "narrow_sets") t.narrow_sets = value != 0;
+  else if (k == "max_stitch_rounds") t.max_stitch_rounds = (uint32_t)value;
+  else if (k == "max_redo_rounds") t.max_redo_rounds = (uint32_t)value;
+  else if (k == "prefilter") t.prefilter = value != 0;
+  else { g_last_error = "unknown option: " + k; return false; }
+  return true;
+}
+bool rure_b200_set_option(rure* re, const char* name, uint64_t value) { return set_option(re->re, name, value); }
+bool rure_b200_set_set_option(rure_set* set, const char* name, uint64_t value) { return set_option(set->re, name, value); }
 void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm, uint32_t block, uint32_t blocks_per_sm) {
   rbgpu::Tuning& t = re->re->tuning;
   if (seg) t.seg = (seg + 63) / 64 * 64;

@@ -323,6 +323,71 @@ static uint32_t pick_warm(const Regex& re) {
   return 128;
 }
 
+// ------------------------------------------------- bounded fix-up of entry states --
+// Exact entry state of every segment by state-map composition (kernels.cu, "exact entry states"):
+// K = the states seen at segment boundaries, closed under the per-segment maps; on return
+// fin[] holds, next to every segment, the exact state it is entered with, so that one
+// verify + redo round completes the scan.  Used when the plain redo rounds do not converge.
+int Regex::solve_entries(const void* scan_args, bool reverse) {
+  ScanArgs g = *(const ScanArgs*)scan_args;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t smem = smem_for(g.dfa);
+  g.use_smem = smem != 0;
+  g.redo_list = nullptr;
+  RB_CUDA(allow_smem(scan_map, smem));
+  const uint64_t n_seg = g.n_seg;
+  uint8_t* present = (uint8_t*)present_.ensure(65536);
+  uint16_t* d_kidx = (uint16_t*)kidx_.ensure(65536 * 2);
+  uint32_t* counters = (uint32_t*)counters_.ptr;
+  if (!present || !d_kidx) return fail("out of device memory (state maps)");
+  RB_CUDA(cudaMemsetAsync(present, 0, 65536, st));
+  mark_states<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(g.guess, n_seg, present);
+  RB_LAUNCH_CHECK("mark_states");
+  mark_states<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(g.fin, n_seg, present);
+  RB_LAUNCH_CHECK("mark_states");
+  std::vector<uint8_t> h_present(65536);
+  std::vector<uint16_t> K, kidx;
+  uint16_t *d_states = nullptr, *maps = nullptr;
+  for (;;) {
+    RB_CUDA(d2h(h_present.data(), present, 65536));
+    K.clear();
+    kidx.assign(65536, 0xFFFF);
+    for (uint32_t v = 0; v < 65536; v++)
+      if (h_present[v] && v < g.dfa.n_states) { kidx[v] = (uint16_t)K.size(); K.push_back((uint16_t)v); }
+    const uint32_t k = (uint32_t)K.size();
+    if (k > 512) return fail("the automaton reaches more than 512 distinct states at segment boundaries; state-map composition refused");
+    d_states = (uint16_t*)kstates_.ensure(k * 2);
+    maps = (uint16_t*)maps_.ensure(n_seg * k * 2);
+    if (!d_states || !maps) return fail("out of device memory (state maps)");
+    RB_CUDA(cudaMemcpyAsync(d_states, K.data(), k * 2, cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(d_kidx, kidx.data(), 65536 * 2, cudaMemcpyHostToDevice, st));
+    scan_map<<<grid_for(n_seg * k, 256, tuning.blocks_per_sm), 256, smem, st>>>(g, reverse ? 1 : 0, d_states, k, maps);
+    RB_LAUNCH_CHECK("scan_map");
+    stats.map_passes += k;
+    RB_CUDA(cudaMemsetAsync(counters + 8, 0, 4, st));
+    closure_check<<<grid_for(n_seg * k, 256, 8), 256, 0, st>>>(maps, n_seg * k, d_kidx, present, counters + 8);
+    RB_LAUNCH_CHECK("closure_check");
+    uint32_t n_new = 0;
+    RB_CUDA(d2h(&n_new, counters + 8, 4));  // also orders the host vectors above before they are rebuilt
+    if (n_new == 0) break;
+  }
+  const uint32_t k = (uint32_t)K.size();
+  const uint64_t n_blocks = (n_seg + kMapBlock - 1) / kMapBlock;
+  uint16_t* comp = (uint16_t*)comp_.ensure(n_blocks * k * 2);
+  uint16_t* bentry = (uint16_t*)bentry_.ensure(n_blocks * 2);
+  uint16_t* exact = (uint16_t*)exact_.ensure(n_seg * 2);
+  if (!comp || !bentry || !exact) return fail("out of device memory (state maps)");
+  compose_blocks<<<(uint32_t)((n_blocks * k + 255) / 256), 256, 0, st>>>(maps, d_kidx, d_states, k, n_seg, reverse ? 1 : 0, comp);
+  RB_LAUNCH_CHECK("compose_blocks");
+  compose_top<<<1, 32, 0, st>>>(comp, d_kidx, k, n_blocks, reverse ? 1 : 0, reverse ? g.guess + (n_seg - 1) : g.guess, bentry);
+  RB_LAUNCH_CHECK("compose_top");
+  compose_fill<<<(uint32_t)((n_blocks + 255) / 256), 256, 0, st>>>(maps, d_kidx, k, n_seg, reverse ? 1 : 0, bentry, exact);
+  RB_LAUNCH_CHECK("compose_fill");
+  publish_exact<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(exact, n_seg, reverse ? 1 : 0, g.fin);
+  RB_LAUNCH_CHECK("publish_exact");
+  return 0;
+}
+
 // ------------------------------------------------------------- start bitmap --
 Regex::ScanPlan Regex::plan_scan(const uint8_t* d_text, uint64_t base, uint64_t limit, bool fast_table) {
   ScanPlan p;
@@ -414,7 +479,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     launch(a, n_seg);
     RB_LAUNCH_CHECK("scan_rev");
   }
-  stats.scan_redo_rounds = stats.scan_redo_segments = 0;
+  stats.scan_redo_rounds = stats.scan_redo_segments = stats.map_passes = 0;
   auto redo_round = [&](uint32_t n_redo) -> int {
     stats.scan_redo_rounds++;
     stats.scan_redo_segments += n_redo;
@@ -444,7 +509,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
       io->rev_guess = io->rev_entry;
     }
   }
-  for (;;) {
+  for (uint32_t round = 0;; round++) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
     verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 1, redo, counters);
     RB_LAUNCH_CHECK("verify_segments");
@@ -452,6 +517,11 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     RB_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_redo = *(uint32_t*)pinned_;
     if (n_redo == 0) break;
+    if (round == tuning.max_redo_rounds) {
+      // wrong guesses keep cascading: solve every entry state at once, then one more redo round
+      if (int rc = solve_entries(&a, true)) return rc;
+      continue;
+    }
     if (int rc = redo_round(n_redo)) return rc;
   }
   if (shard) {
@@ -664,6 +734,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   io->halo_overflow = ((uint32_t*)(h + 3))[0] != 0;
   io->left_ctx_short = ((uint32_t*)(h + 3))[1] != 0;
   stats.fused = fused;
+  stats.path = fused ? 2 : plan.fast ? 1 : 0;
   cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
   cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
   cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);
@@ -692,16 +763,23 @@ int Regex::find_at_device(const uint8_t* d_text, uint64_t n, uint64_t start, boo
 }
 
 // ------------------------------------------------------ forward reductions ----
-int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host) {
+// One wave of a forward all-match scan: positions [start, limit) of the haystack (limit == n + 1
+// includes the end-of-text step), entered in state `entry` (kNoEntry: the start state for the
+// flags at `start`).  result_host[0] = first match end, [1..] = OR of the pattern masks;
+// *exit_state = exact state after the last position (the next wave's entry).
+int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t limit, uint32_t entry, bool want_masks,
+                         uint64_t* result_host, uint32_t* exit_state) {
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  // fast path (scan_fwd_fast): single pattern, hot table, 16-byte aligned haystack and start
-  const bool fast_ok = !want_masks && fwd->hot.n != 0 && !tuning.force_generic && tuning.tensor_tma && encode_tiled() &&
+  // fast path (scan_fwd_fast): hot table, 16-byte aligned haystack and start; RegexSets only when
+  // matches are known to be rare (a narrowed set, see forward_reduce): the fast kernel finds the
+  // patterns of a match by redoing that 64-byte group on the full table
+  const bool fast_ok = (!want_masks || sparse_set_) && fwd->hot.n != 0 && !tuning.force_generic && tuning.tensor_tma && encode_tiled() &&
                        ((uintptr_t)d_text & 15) == 0 && (start & 63) == 0 &&
                        fast_scan_smem(hot_bytes(fwd->hot.n)) <= 227 * 1024;
   const uint32_t seg = tuning.seg ? tuning.seg : (fast_ok ? 4096 : 1024);
-  const uint64_t n_seg = (n + 1 - start + seg - 1) / seg;
+  const uint64_t n_seg = (limit - start + seg - 1) / seg;
   if (n_seg >= 0xFFFFFFFFull) return fail("haystack too large for one scan (segment index overflow)");
   const uint32_t mw = fwd->view.mask_words;
   ScanArgs a{};
@@ -711,6 +789,8 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   a.text = d_text;
   a.n = n;
   a.base = start;
+  a.fwd_limit = limit;
+  a.entry0 = entry;
   a.n_seg = n_seg;
   a.seg = seg;
   a.warm = pick_warm(*this);
@@ -725,7 +805,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
     return fail("out of device memory (scan scratch)");
   RB_CUDA(allow_smem(scan_fwd_reduce, smem));
   // whole warps of full segments go to the fast kernel; segment 0, the ragged end and the EOF step stay generic
-  const uint64_t n_full = (n - start) / seg;
+  const uint64_t n_full = (std::min(limit, n) - start) / seg;
   if (fast_ok && seg % 64 == 0 && a.warm <= seg && n_full >= 34) {
     const uint64_t skip_lo = 1, skip_hi = 1 + (n_full - 1) / 32 * 32;
     CUtensorMap tmap;
@@ -749,7 +829,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   }
   scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
   RB_LAUNCH_CHECK("scan_fwd_reduce");
-  for (;;) {
+  for (uint32_t round = 0;; round++) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
     verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 0, redo, counters);
     RB_LAUNCH_CHECK("verify_segments");
@@ -757,6 +837,12 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
     RB_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_redo = *(uint32_t*)pinned_;
     if (n_redo == 0) break;
+    stats.scan_redo_rounds++;
+    stats.scan_redo_segments += n_redo;
+    if (round == tuning.max_redo_rounds) {
+      if (int rc = solve_entries(&a, false)) return rc;
+      continue;
+    }
     ScanArgs r = a;
     r.redo_list = redo;
     r.n_redo = counters;
@@ -771,10 +857,92 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
   reduce_segments<<<grid_for(n_seg, 256, 4), 256, 0, st>>>(a.seg_first, a.seg_mask, n_seg, mw, result);
   RB_LAUNCH_CHECK("reduce_segments");
   RB_CUDA(cudaMemcpyAsync(h, result, 8 * (1 + kMaxMaskWords), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(h + 8, a.fin + (n_seg - 1), 2, cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
   for (uint32_t w = 0; w < 1 + kMaxMaskWords; w++) result_host[w] = h[w];
+  *exit_state = *(uint16_t*)(h + 8);
   return 0;
 }
+
+// is_match / shortest_match / RegexSet::matches over one haystack, in waves of growing size
+// (32 MiB, x8 each) so that the search stops early the way the reference does:
+//   - a single pattern stops at the first wave that holds a match (dfa.rs:658-667, quit_after_match);
+//   - a set stops once every pattern has matched (dfa.rs:675-682);
+//   - a set ALSO narrows: patterns that matched in the first waves need no further tracking,
+//     so the rest of the haystack is scanned with the automaton of the patterns that are still
+//     open (usually a handful of rare ones: small, shared-memory resident, fast kernel) instead
+//     of the product automaton of all of them.  That automaton knows nothing about the bytes
+//     already passed, so it scans from `start` again; narrowing happens after the first two
+//     waves only, which bounds the repeated work to 1/8 of the haystack.
+int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host) {
+  result_host[0] = kNone;
+  for (uint32_t w = 0; w < kMaxMaskWords; w++) result_host[1 + w] = 0;
+  const uint32_t n_pat = (uint32_t)patterns_.size();
+  uint64_t wave = tuning.wave0 ? (tuning.wave0 + 4095) / 4096 * 4096 : 0;
+  uint64_t lo = start;
+  uint32_t entry = kNoEntry;
+  stats.scan_redo_rounds = stats.scan_redo_segments = stats.map_passes = stats.waves = 0;
+  for (uint32_t wi = 0;; wi++) {
+    uint64_t limit = n + 1;
+    if (wave && n + 1 - lo > 2 * wave) limit = (lo + wave) / 4096 * 4096;
+    uint64_t r[1 + kMaxMaskWords];
+    uint32_t exit_state = 0;
+    if (int rc = forward_range(d_text, n, lo, limit, entry, want_masks, r, &exit_state)) return rc;
+    stats.waves++;
+    result_host[0] = std::min(result_host[0], r[0]);
+    bool fresh = false;
+    for (uint32_t w = 0; w < kMaxMaskWords; w++) {
+      fresh = fresh || (r[1 + w] & ~result_host[1 + w]);
+      result_host[1 + w] |= r[1 + w];
+    }
+    if (limit == n + 1) break;
+    if (!want_masks && result_host[0] != kNone) break;
+    if (exit_state == 0) break;  // dead state: an anchored search that can no longer match
+    if (want_masks) {
+      std::vector<uint32_t> open;
+      for (uint32_t i = 0; i < n_pat; i++)
+        if (!((result_host[1 + i / 64] >> (i % 64)) & 1)) open.push_back(i);
+      if (open.empty()) break;
+      if (tuning.narrow_sets && wi < 2 && fresh && open.size() < n_pat) {
+        Regex* sub = nullptr;
+        if (int rc = subset(open, &sub)) return rc;
+        uint64_t sr[1 + kMaxMaskWords];
+        sub->tuning.wave0 = tuning.wave0;
+        sub->set_stream(stream_);
+        std::lock_guard<std::recursive_mutex> lock(sub->mu_);
+        if (int rc = sub->forward_reduce(d_text, n, start, true, sr)) return fail(sub->last_error());
+        stats.waves += sub->stats.waves;
+        for (uint32_t j = 0; j < open.size(); j++)
+          if ((sr[1 + j / 64] >> (j % 64)) & 1) result_host[1 + open[j] / 64] |= 1ull << (open[j] % 64);
+        break;
+      }
+    }
+    lo = limit;
+    entry = exit_state;
+    wave *= 8;
+  }
+  return 0;
+}
+
+// The RegexSet of a subset of this set's patterns (cached; used by forward_reduce's narrowing).
+int Regex::subset(const std::vector<uint32_t>& members, Regex** out) {
+  auto it = subsets_.find(members);
+  if (it == subsets_.end()) {
+    std::vector<std::string> pats;
+    for (uint32_t i : members) pats.push_back(patterns_[i]);
+    CompileOptions o = opt_;
+    o.as_set = true;
+    rb::Error err;
+    std::unique_ptr<Regex> sub(Regex::compile(pats, o, &err));
+    if (!sub) return fail("narrowed pattern set: " + err.msg);
+    sub->sparse_set_ = true;
+    sub->tuning = tuning;
+    it = subsets_.emplace(members, std::move(sub)).first;
+  }
+  *out = it->second.get();
+  return 0;
+}
+
 
 int Regex::shortest_match_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* found, uint64_t* end) {
   std::lock_guard<std::recursive_mutex> lock(mu_);

@@ -4,6 +4,7 @@
 // search runs on the GPU -- there is no CPU matching path in this library.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -33,15 +34,19 @@ struct Tuning {
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;
   uint32_t blocks_per_sm = 8;
+  uint64_t wave0 = 32ull << 20;  // first wave of a forward search in bytes (x8 per wave); 0 = one wave
+  bool narrow_sets = true;
+  bool prefilter = true;         // literal patterns with a rare byte: memchr-style candidate scan instead of the DFA scan       // RegexSet::matches: continue with the automaton of the still-unmatched patterns
   uint32_t max_stitch_rounds = 16;  // re-walk rounds before the stitch falls back to one sequential pass
   uint32_t max_redo_rounds = 3;     // scan redo rounds before segment entry states are solved by state-map composition
 };
 
 struct Stats {  // filled by the last single-haystack call (diagnostics, bench roofline)
   uint64_t scan_redo_rounds = 0, scan_redo_segments = 0;
-  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0, sequential_passes = 0, map_passes = 0;
+  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0, sequential_passes = 0, map_passes = 0, waves = 0;
   float scan_ms = 0, walk_ms = 0, total_ms = 0;
   bool fused = false;  // the scan kernel also walked the chains (scan_ms covers both)
+  int path = 0;        // last find_all: 0 generic scan, 1 fast scan, 2 fused scan + walk, 3 literal prefilter
 };
 
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
@@ -132,12 +137,18 @@ class Regex {
   ScanPlan plan_scan(const uint8_t* d_text, uint64_t base, uint64_t limit, bool fast_table);
   int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
                   const void* fused_walk);
+  int solve_entries(const void* scan_args, bool reverse);
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
+  int forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t limit, uint32_t entry, bool want_masks,
+                    uint64_t* result_host, uint32_t* exit_state);
+  int subset(const std::vector<uint32_t>& members, Regex** out);
   const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
   int find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, uint64_t* d_out, uint64_t* out, uint64_t cap, uint64_t* total);
 
   std::vector<std::string> patterns_;
   bool is_set_ = false;
+  bool sparse_set_ = false;  // a narrowed RegexSet: none of its patterns matched in the first waves
+  std::map<std::vector<uint32_t>, std::unique_ptr<Regex>> subsets_;
   CompileOptions opt_;
   std::vector<rb::Expr> exprs_;
   std::unique_ptr<rb::Dfa> host_[kNumDfaKinds];
@@ -152,7 +163,7 @@ class Regex {
   bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
-  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, stage_, block_sums_, out_, bits_, masks_;
+  DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};
 };

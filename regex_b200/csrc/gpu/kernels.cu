@@ -202,10 +202,12 @@ __global__ void scan_fwd_reduce(ScanArgs a) {
     const uint64_t t = a.redo_list ? a.redo_list[idx] : idx;
     if (!a.redo_list && t >= a.skip_lo && t < a.skip_hi) continue;  // scan_fwd_fast's share
     const uint64_t lo = a.base + t * a.seg;
-    const uint64_t hi = min(lo + a.seg, a.n + 1);
+    const uint64_t hi = min(lo + a.seg, a.fwd_limit);
     uint32_t s;
     if (a.redo_list) {
       s = a.fin[t - 1];
+    } else if (t == 0 && a.entry0 != kNoEntry) {
+      s = a.entry0;
     } else {
       const uint64_t w = (lo - a.base > a.warm) ? lo - a.warm : a.base;
       s = pick_start_fwd(a.dfa, a.text, a.n, w);
@@ -244,7 +246,7 @@ __global__ void scan_fwd_reduce(ScanArgs a) {
       q += 16;
     }
     while (q < text_hi) { consume(T.step(s, a.text[q]), q); q++; }
-    if (q < hi) consume(T.step_eof(s), q);  // q == n
+    if (q < hi) consume(T.step_eof(s), q);  // q == n, fwd_limit == n + 1
     a.fin[t] = (uint16_t)s;
     a.seg_first[t] = first;
     if (a.seg_mask) {
@@ -263,6 +265,90 @@ __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint
     if (reverse) bad = t + 1 < n_seg && guess[t] != fin[t + 1];
     else bad = t > 0 && guess[t] != fin[t - 1];
     if (bad) redo_list[atomicAdd(n_redo, 1u)] = (uint32_t)t;
+  }
+}
+
+// ---- exact entry states by state-map composition ------------------------------------
+// The warm-up guess of a segment's entry state is wrong for automata whose state depends
+// on far context (`(?s)foo.*bar`: "a bar lies somewhere to the right"), and redoing from
+// the neighbour's state repairs only one more segment per round.  After a few rounds the
+// engine switches to the north star's formulation: run every segment from EVERY state
+// that occurs at a boundary (K, closed under the maps), compose the per-segment maps
+// K -> K along the scan direction in three short kernels (blocks, block entries, fill),
+// and redo once from the exact entry states.  Work: (|K| + 2) passes, no cascade.
+__global__ void mark_states(const uint16_t* a, uint64_t n, uint8_t* present) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) present[a[i]] = 1;
+}
+__global__ void scan_map(ScanArgs a, int reverse, const uint16_t* states, uint32_t k, uint16_t* maps) {
+  const Table T = stage_table(a.dfa, g_smem, a.use_smem);
+  const uint64_t total = a.n_seg * k;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t t = idx / k;  // the k threads of a segment are neighbours: their haystack loads coalesce into one
+    uint32_t s = states[idx - t * k];
+    const bool vec = (reinterpret_cast<uintptr_t>(a.text) & 15) == 0;
+    if (reverse) {  // bytes [lo, hi) from the top down, as scan_rev_bitmap
+      const uint64_t lo = min(a.base + t * a.seg, a.limit), hi = min(lo + a.seg, a.limit);
+      uint64_t i = hi;
+      while (i > lo && (!vec || (i & 15) || i - lo < 16)) { i--; s = T.step(s, a.text[i]); }
+      while (i > lo) {  // i and lo are 16-byte aligned here
+        const uint4 v = ldg128(a.text + i - 16);
+#pragma unroll
+        for (int j = 15; j >= 0; j--) s = T.step(s, word_byte(v, j));
+        i -= 16;
+      }
+    } else {        // bytes [lo, hi) upwards, as scan_fwd_reduce (the EOF step belongs to no map)
+      const uint64_t lo = a.base + t * a.seg, hi = min(lo + a.seg, a.n);
+      uint64_t q = lo;
+      while (q < hi && (!vec || (q & 15) || hi - q < 16)) { s = T.step(s, a.text[q]); q++; }
+      while (q + 16 <= hi) {
+        const uint4 v = ldg128(a.text + q);
+#pragma unroll
+        for (int j = 0; j < 16; j++) s = T.step(s, word_byte(v, j));
+        q += 16;
+      }
+      while (q < hi) { s = T.step(s, a.text[q]); q++; }
+    }
+    maps[idx] = (uint16_t)s;
+  }
+}
+__global__ void closure_check(const uint16_t* maps, uint64_t n, const uint16_t* kidx, uint8_t* present, uint32_t* n_new) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint16_t v = maps[i];
+    if (kidx[v] == 0xFFFFu && !present[v]) { present[v] = 1; atomicAdd(n_new, 1u); }
+  }
+}
+__global__ void compose_blocks(const uint16_t* maps, const uint16_t* kidx, const uint16_t* states, uint32_t k, uint64_t n_seg,
+                               int reverse, uint16_t* comp) {
+  const uint64_t n_blocks = (n_seg + kMapBlock - 1) / kMapBlock;
+  const uint64_t id = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (id >= n_blocks * k) return;
+  const uint64_t b = id / k;
+  uint32_t s = states[id - b * k];
+  const uint64_t t_lo = b * kMapBlock, t_hi = min(t_lo + kMapBlock, n_seg);
+  if (reverse) for (uint64_t t = t_hi; t-- > t_lo;) s = maps[t * k + kidx[s]];
+  else for (uint64_t t = t_lo; t < t_hi; t++) s = maps[t * k + kidx[s]];
+  comp[id] = (uint16_t)s;
+}
+__global__ void compose_top(const uint16_t* comp, const uint16_t* kidx, uint32_t k, uint64_t n_blocks, int reverse,
+                            const uint16_t* first_entry, uint16_t* block_entry) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint32_t s = *first_entry;
+  if (reverse) for (uint64_t b = n_blocks; b-- > 0;) { block_entry[b] = (uint16_t)s; s = comp[b * k + kidx[s]]; }
+  else for (uint64_t b = 0; b < n_blocks; b++) { block_entry[b] = (uint16_t)s; s = comp[b * k + kidx[s]]; }
+}
+__global__ void compose_fill(const uint16_t* maps, const uint16_t* kidx, uint32_t k, uint64_t n_seg, int reverse,
+                             const uint16_t* block_entry, uint16_t* exact) {
+  const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (b * kMapBlock >= n_seg) return;
+  uint32_t s = block_entry[b];
+  const uint64_t t_lo = b * kMapBlock, t_hi = min(t_lo + kMapBlock, n_seg);
+  if (reverse) for (uint64_t t = t_hi; t-- > t_lo;) { exact[t] = (uint16_t)s; s = maps[t * k + kidx[s]]; }
+  else for (uint64_t t = t_lo; t < t_hi; t++) { exact[t] = (uint16_t)s; s = maps[t * k + kidx[s]]; }
+}
+__global__ void publish_exact(const uint16_t* exact, uint64_t n_seg, int reverse, uint16_t* fin) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n_seg; t += (uint64_t)gridDim.x * blockDim.x) {
+    if (reverse) { if (t + 1 < n_seg) fin[t + 1] = exact[t]; }  // segment t enters with the final state of t + 1
+    else if (t > 0) fin[t - 1] = exact[t];
   }
 }
 
@@ -1053,6 +1139,20 @@ __device__ __noinline__ uint32_t slow_group_fwd(const uint16_t* trans, const uin
   *bits_out = bits;
   return s;
 }
+// One group again on the full table, OR-ing the pattern masks of the match states it enters.
+__device__ __noinline__ void slow_group_masks(const uint16_t* trans, const uint8_t* classes, const uint64_t* masks, uint32_t stride,
+                                              uint32_t match_lo, uint32_t mw, uint32_t s, uint4 c0, uint4 c1, uint4 c2, uint4 c3, uint64_t* acc) {
+  const uint32_t w[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+  uint32_t last = 0;
+  for (int j = 0; j < 64; j++) {
+    const uint32_t byte = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+    s = trans[s * stride + classes[byte]];
+    if (s >= match_lo && s != last) {
+      last = s;
+      for (uint32_t i = 0; i < mw; i++) acc[i] |= masks[(uint64_t)s * mw + i];
+    }
+  }
+}
 __global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1100,13 +1200,14 @@ __global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __gri
         if (j < n_groups) issue_box(j, (slot_b + j) % kBoxStages);
     }
     uint64_t first = kNone;
+    uint64_t acc[kMaxMaskWords] = {0, 0, 0, 0};
     for (uint32_t k = 0; k < n_groups; k++) {
       mbar_wait(barb + slot_b * 8, par_b);
       const uint32_t b = my_b + slot_b * kRingStageBytes;
       const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
       if (k == n_warm) a.guess[t] = (uint16_t)full_state();
       const bool rec = k >= n_warm;
-      const uint32_t e0 = e;
+      const uint32_t e0 = e, cold0 = cold;
       const uint32_t th = rec ? thr : 0xFFFFFFFFu;
       uint32_t blo = 0, bhi = 0;
       fwd_block16<0>(tbase, c0, e, blo, th);
@@ -1125,12 +1226,17 @@ __global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __gri
         const uint64_t bits = ((uint64_t)bhi << 32) | blo;
         first = lo + 64ull * (k - n_warm) + (uint64_t)(__ffsll((long long)bits) - 1);
       }
+      if (a.seg_mask && (bhi | blo))  // RegexSet: a match state was entered in this group (rare on this path): which patterns?
+        slow_group_masks(a.dfa.trans, a.dfa.classes, a.dfa.masks, a.dfa.stride, a.dfa.match_lo, a.dfa.mask_words,
+                         cold0 ? cold0 : a.hot.hot2full[e0], c0, c1, c2, c3, acc);
       __syncwarp();
       if (lane == 0 && k + kBoxStages < n_groups) issue_box(k + kBoxStages, slot_b);
       if (++slot_b == kBoxStages) { slot_b = 0; par_b ^= 1; }
     }
     a.fin[t] = (uint16_t)full_state();
     a.seg_first[t] = first;
+    if (a.seg_mask)
+      for (uint32_t w = 0; w < a.dfa.mask_words; w++) a.seg_mask[t * a.dfa.mask_words + w] = acc[w];
   }
 }
 

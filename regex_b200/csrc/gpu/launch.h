@@ -8,6 +8,7 @@
 namespace rbgpu {
 
 constexpr uint32_t kMaxMaskWords = 4;  // RegexSet of up to 256 patterns per scan
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
 
 struct ScanArgs {
   DfaView dfa;
@@ -31,6 +32,8 @@ struct ScanArgs {
   const uint32_t* n_redo;
   int utf8_boundaries;  // drop starts that are not UTF-8 scalar boundaries (Regex on str)
   uint64_t skip_lo, skip_hi;  // scan_fwd_reduce: segments [skip_lo, skip_hi) belong to scan_fwd_fast
+  uint64_t fwd_limit;   // forward scan: positions [base, fwd_limit) are stepped; n + 1 includes the end-of-text step
+  uint32_t entry0;      // forward scan: exact state at `base` (a later wave of one search), kNoEntry = start state by flags
 };
 
 struct WalkArgs {
@@ -96,6 +99,24 @@ __global__ void scan_fwd_reduce(ScanArgs a);
 __global__ void scan_fwd_fast(ScanArgs a, const __grid_constant__ CUtensorMap tmap);
 __global__ void verify_segments(const uint16_t* guess, const uint16_t* fin, uint64_t n_seg, int reverse,
                                 uint32_t* redo_list, uint32_t* n_redo);
+// ---- exact segment entry states by state-map composition (bounded fix-up; engine.cu solve_entries) ----
+__global__ void mark_states(const uint16_t* a, uint64_t n, uint8_t* present);
+// maps[t * k + j] = state after running segment t from states[j]  (reverse: right to left)
+__global__ void scan_map(ScanArgs a, int reverse, const uint16_t* states, uint32_t k, uint16_t* maps);
+// *n_new += map values that are not in the state list (kidx == 0xFFFF); those are marked in present[]
+__global__ void closure_check(const uint16_t* maps, uint64_t n, const uint16_t* kidx, uint8_t* present, uint32_t* n_new);
+// blocks of kMapBlock segments: comp[b * k + j] = composite of the block's maps applied to states[j]
+constexpr uint32_t kMapBlock = 1024;
+__global__ void compose_blocks(const uint16_t* maps, const uint16_t* kidx, const uint16_t* states, uint32_t k, uint64_t n_seg,
+                               int reverse, uint16_t* comp);
+// one thread: entry state of every block, walking the blocks in scan direction from the exact state `first_entry`
+__global__ void compose_top(const uint16_t* comp, const uint16_t* kidx, uint32_t k, uint64_t n_blocks, int reverse,
+                            const uint16_t* first_entry, uint16_t* block_entry);
+// exact[t] = entry state of segment t
+__global__ void compose_fill(const uint16_t* maps, const uint16_t* kidx, uint32_t k, uint64_t n_seg, int reverse,
+                             const uint16_t* block_entry, uint16_t* exact);
+// neighbour[t -/+ 1] := exact[t] so that verify_segments + one redo round finish the job
+__global__ void publish_exact(const uint16_t* exact, uint64_t n_seg, int reverse, uint16_t* fin);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result);
 template <int FAST>
