@@ -323,6 +323,58 @@ static uint32_t pick_warm(const Regex& re) {
   return 128;
 }
 
+// ---------------------------------------------------------- literal prefilter --
+// Estimated byte frequencies, parts per 65536 (tools/gen_byte_freq.py).
+static const uint16_t kByteFreq[256] = {
+#include "byte_freq.inc"
+};
+// A pattern qualifies when every match must have one of at most four bytes of small total
+// estimated frequency at some fixed offset o < min_len (the reference scans for its rarest
+// literal byte, src/literals.rs:466-489; here the bytes come from the automaton, so character
+// classes and alternations qualify as well: `Sher[a-z]+|Hol[a-z]+` scans for S and H).
+static constexpr uint32_t kPrefilterMaxFreq = 600;  // ~0.9 % of the haystack's bytes
+static constexpr uint32_t kPrefilterState = 0xFFFEu; // what a prefilter shard reports as its boundary states
+bool Regex::plan_prefilter() {
+  if (pf_state_) return pf_state_ > 0;
+  pf_state_ = -1;
+  if (is_set_ || has_looks || min_len == 0 || patterns_.size() != 1) return false;
+  rb::Error err;
+  const rb::Dfa* d = host_dfa(kFwdAnchoredLF, &err);
+  if (!d || !d->uniform_start) return false;
+  const uint32_t depth = (uint32_t)std::min<uint64_t>(min_len, 8);
+  std::vector<std::vector<uint8_t>> allowed(depth, std::vector<uint8_t>(256, 0));
+  std::vector<uint8_t> reach(d->n_states, 0), next(d->n_states, 0);
+  reach[d->start[32]] = 1;
+  for (uint32_t dep = 0; dep < depth; dep++) {
+    std::fill(next.begin(), next.end(), 0);
+    for (uint32_t st = 1; st < d->n_states; st++) {
+      if (!reach[st]) continue;
+      for (int b = 0; b < 256; b++) {
+        const uint16_t t = d->next((uint16_t)st, (uint8_t)b);
+        if (t) { allowed[dep][b] = 1; next[t] = 1; }
+      }
+    }
+    reach.swap(next);
+  }
+  uint32_t best_o = 0, best_f = ~0u;
+  for (uint32_t o = 0; o < depth; o++) {
+    uint32_t cnt = 0, f = 0;
+    for (int b = 0; b < 256; b++) if (allowed[o][b]) { cnt++; f += kByteFreq[b]; }
+    if (cnt >= 1 && cnt <= 4 && f < best_f) { best_f = f; best_o = o; }
+  }
+  if (best_f > kPrefilterMaxFreq) return false;
+  PfArgs a{};
+  a.o = best_o;
+  for (int b = 0; b < 256; b++) if (allowed[best_o][b]) a.bcast[a.n_bytes++] = 0x01010101u * (uint32_t)b;
+  a.n_sets = std::min<uint32_t>(depth, 4);
+  for (uint32_t dep = 0; dep < a.n_sets; dep++)
+    for (int b = 0; b < 256; b++) if (allowed[dep][b]) a.sets[dep][b >> 5] |= 1u << (b & 31);
+  pf_words_.resize(sizeof(PfArgs) / 4);
+  std::memcpy(pf_words_.data(), &a, sizeof a);
+  pf_state_ = 1;
+  return true;
+}
+
 // ------------------------------------------------- bounded fix-up of entry states --
 // Exact entry state of every segment by state-map composition (kernels.cu, "exact entry states"):
 // K = the states seen at segment boundaries, closed under the per-segment maps; on return
@@ -570,8 +622,13 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;
   const bool wfast = !wfixed && fwd->hot.n != 0 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
+  // literal prefilter: no start bitmap at all -- literal_scan finds, verifies and chains the candidates
+  const bool use_pf = tuning.prefilter && !tuning.force_generic && ((uintptr_t)d_text & 15) == 0 && plan_prefilter();
+  PfArgs pf{};
+  if (use_pf) std::memcpy(&pf, pf_words_.data(), sizeof pf);
+  const bool pf_fast = use_pf && fwd->hot.n != 0 && fwd->view.uniform_start;
   // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
-  const bool fused = plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
+  const bool fused = !use_pf && plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
                      fast_scan_smem(hot_bytes(revall->hot.n) + (wkind == 1 ? hot_bytes(fwd->hot.n) : 0)) <= 227 * 1024;
 
   WalkArgs w{};
@@ -585,7 +642,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   w.base = io->own_lo;
   w.limit = io->own_hi;
   w.text_continues = !io->is_last;
-  w.chunk = fused ? plan.seg : std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
+  w.chunk = use_pf ? 8192 : fused ? plan.seg : std::max<uint32_t>(256, (tuning.chunk + 255) / 256 * 256);
   w.stage_cap = std::max<uint32_t>(4, w.chunk / 64);
   w.n_chunks = std::max<uint64_t>(1, (w.limit - w.base + w.chunk - 1) / w.chunk);
   const uint64_t nc = w.n_chunks;
@@ -632,17 +689,44 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     RB_CUDA(allow_smem(walk_chunks<0>, wsmem));
     RB_CUDA(allow_smem(compact_spans<0>, wsmem));
   }
+  if (use_pf) {  // the prefilter's verifier: table runner (shared-memory hot table) or generic
+    w.fixed_len = 0;
+    if (pf_fast) {
+      wsmem = hot_bytes(fwd->hot.n) + 256;
+      w.fwd_hot = fwd->hot;
+      RB_CUDA(allow_smem(literal_scan<1>, wsmem));
+    } else {
+      wsmem = smem_for(fwd->view);
+      w.use_smem = wsmem != 0;
+      RB_CUDA(allow_smem(literal_scan<0>, wsmem));
+    }
+  }
+  auto launch_pf = [&](const WalkArgs& args, uint64_t chunks, int mode) {
+    const uint32_t g = mode == 2 ? 1 : grid_for(chunks * 32, 256, 3);  // one warp per chunk
+    if (pf_fast) literal_scan<1><<<g, 256, wsmem, st>>>(args, pf, mode);
+    else literal_scan<0><<<g, 256, wsmem, st>>>(args, pf, mode);
+  };
   auto launch_walk = [&](const WalkArgs& args, uint64_t work) {
+    if (use_pf) { launch_pf(args, work, 1); return; }
     const uint32_t g = grid_for(work, 256, 6);
     if (wkind == 2) walk_chunks<2><<<g, 256, 0, st>>>(args);
     else if (wkind == 1) walk_chunks<1><<<g, 256, wsmem, st>>>(args);
     else walk_chunks<0><<<g, 256, wsmem, st>>>(args);
   };
-  if (int rc = scan_starts(d_text, n, io->own_lo, io->own_hi, io, plan, fused ? &w : nullptr)) return rc;
-  RB_CUDA(cudaEventRecord(ev[1], st));
-  if (!fused) {
-    launch_walk(w, nc);
-    RB_LAUNCH_CHECK("walk_chunks");
+  if (use_pf) {
+    launch_pf(w, nc, 0);
+    RB_LAUNCH_CHECK("literal_scan");
+    io->rev_guess = io->rev_entry != kNoState ? io->rev_entry : kPrefilterState;  // no reverse scan, nothing to guess
+    io->rev_left = kPrefilterState;
+    stats.scan_redo_rounds = stats.scan_redo_segments = stats.map_passes = 0;
+    RB_CUDA(cudaEventRecord(ev[1], st));
+  } else {
+    if (int rc = scan_starts(d_text, n, io->own_lo, io->own_hi, io, plan, fused ? &w : nullptr)) return rc;
+    RB_CUDA(cudaEventRecord(ev[1], st));
+    if (!fused) {
+      launch_walk(w, nc);
+      RB_LAUNCH_CHECK("walk_chunks");
+    }
   }
   // ---- stitch: bring the speculative chunk walks into agreement with the sequential iterator ----
   stats.stitch_rounds = stats.stitch_dirty_chunks = stats.sequential_passes = 0;
@@ -686,7 +770,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
       if (++dirty_rounds > tuning.max_stitch_rounds) {
         // chains that do not meet again: one sequential pass from the leftmost such chunk
         wd.seq_from = hc[3];
-        if (wkind == 2) walk_sequential<2><<<1, 256, 0, st>>>(wd);
+        if (use_pf) launch_pf(wd, 1, 2);
+        else if (wkind == 2) walk_sequential<2><<<1, 256, 0, st>>>(wd);
         else if (wkind == 1) walk_sequential<1><<<1, 256, wsmem, st>>>(wd);
         else walk_sequential<0><<<1, 256, wsmem, st>>>(wd);
         RB_LAUNCH_CHECK("walk_sequential");
@@ -705,7 +790,12 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   RB_LAUNCH_CHECK("scan_block_sums");
   scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(offset, block_sums, nc);
   RB_LAUNCH_CHECK("scan_add_block_offsets");
-  if (w.cap > 0) {
+  if (w.cap > 0 && use_pf) {
+    compact_staged<<<grid_for(nc, 256, 6), 256, 0, st>>>(w);
+    RB_LAUNCH_CHECK("compact_staged");
+    launch_pf(w, nc, 3);  // chunks with more matches than staging slots: straight into the output
+    RB_LAUNCH_CHECK("literal_scan(overflow)");
+  } else if (w.cap > 0) {
     const uint32_t g = grid_for(nc, 256, 6);
     if (wkind == 2) compact_spans<2><<<g, 256, 0, st>>>(w);
     else if (wkind == 1) compact_spans<1><<<g, 256, wsmem, st>>>(w);
@@ -734,7 +824,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   io->halo_overflow = ((uint32_t*)(h + 3))[0] != 0;
   io->left_ctx_short = ((uint32_t*)(h + 3))[1] != 0;
   stats.fused = fused;
-  stats.path = fused ? 2 : plan.fast ? 1 : 0;
+  stats.path = use_pf ? 3 : fused ? 2 : plan.fast ? 1 : 0;
   cudaEventElapsedTime(&stats.scan_ms, ev[0], ev[1]);
   cudaEventElapsedTime(&stats.walk_ms, ev[1], ev[2]);
   cudaEventElapsedTime(&stats.total_ms, ev[0], ev[2]);

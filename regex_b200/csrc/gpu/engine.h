@@ -138,6 +138,7 @@ class Regex {
   int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
+  bool plan_prefilter();  // fills pf_ (launch.h PfArgs) when the pattern has a rare byte at a fixed offset
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
   int forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t limit, uint32_t entry, bool want_masks,
                     uint64_t* result_host, uint32_t* exit_state);
@@ -166,6 +167,8 @@ class Regex {
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};
+  int pf_state_ = 0;               // 0 = not decided yet, 1 = prefilter applies, -1 = it does not
+  std::vector<uint32_t> pf_words_; // PfArgs image (engine.cu)
 };
 
 uint64_t kernel_launches();  // total kernels launched by this library in this process

@@ -857,6 +857,233 @@ template __global__ void compact_spans<0>(WalkArgs);
 template __global__ void compact_spans<1>(WalkArgs);
 template __global__ void compact_spans<2>(WalkArgs);
 
+// ---------------------------------------------------------- literal prefilter --
+// The GPU analogue of the reference's literal searchers (src/literals.rs:92-102 LiteralSearcher,
+// :353-371 memchr sets, :466-489 FreqyPacked; Teddy src/simd_accel/teddy128.rs:435-675) and of the
+// prefix skip of the DFA loop (src/dfa.rs:700-711): for patterns that cannot match without one of
+// a few RARE bytes at a fixed offset (`Holmes|Watson`, `Sherlock|Holmes`, `Sher[a-z]+|Hol[a-z]+`),
+// the haystack is streamed once with coalesced 16-byte loads and tested for those bytes with
+// word-wide arithmetic -- no table look-up and no loop-carried dependency, so the loads of a
+// warp are always in flight -- and only the hits are looked at again:
+//   1. the byte is confirmed, and the bytes at the first offsets of the would-be match are
+//      tested against the sets the automaton allows there (the Teddy fingerprint idea);
+//   2. survivors run the anchored leftmost-first automaton (exec_at) from the candidate start:
+//      that decides whether a match starts there and where it ends, so results are the DFA's;
+//   3. the warp applies the find_iter rule (re_trait.rs:197-220) to its chunk's matches in
+//      position order, speculatively entered like every other chunk walk; stitch, prefix sums
+//      and compaction are the common ones.
+// One warp per chunk of a.chunk bytes; chunk k owns the candidates whose scanned byte lies in
+// [base + k*chunk, base + (k+1)*chunk), i.e. the match starts `o` bytes before.
+__device__ __forceinline__ uint4 ldg128_stream(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// flag (bit 7 of each byte) where a byte of w equals the byte replicated in cc; flags above a
+// true hit may be spurious, the lowest one never is -- hits are confirmed anyway
+__device__ __forceinline__ uint32_t swar_eq(uint32_t w, uint32_t cc) {
+  const uint32_t x = w ^ cc;
+  return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t swar_any(const PfArgs& pf, uint32_t w) {
+  uint32_t t = swar_eq(w, pf.bcast[0]);
+  if (pf.n_bytes > 1) t |= swar_eq(w, pf.bcast[1]);
+  if (pf.n_bytes > 2) t |= swar_eq(w, pf.bcast[2]);
+  if (pf.n_bytes > 3) t |= swar_eq(w, pf.bcast[3]);
+  return t;
+}
+__device__ __forceinline__ uint32_t flags_to_bits(uint32_t t) {  // bits 7,15,23,31 -> bits 0..3
+  return (((t >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+template <typename Runner>
+__device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArgs& pf, const uint32_t* sets, const Runner& R, uint64_t k,
+                                                  Chain& c, uint64_t* first_cand, uint64_t* dst, uint64_t w_at, uint64_t limit_out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+  const uint64_t ce = min(cb + a.chunk, a.limit);
+  const uint64_t q_hi = min(ce, a.n);       // scanned bytes [cb, q_hi)
+  uint64_t total = 0, fc = kNone;
+  uint64_t p = c.p, lm = c.lm;               // warp-uniform iterator state
+  // candidate at scanned byte q: confirm the byte and the fingerprint; returns the start or kNone
+  auto candidate = [&](uint64_t q, uint32_t byte) -> uint64_t {
+    bool is = false;
+    for (uint32_t i = 0; i < pf.n_bytes; i++) is = is || byte == (pf.bcast[i] & 0xFFu);
+    if (!is || q < pf.o) return kNone;
+    const uint64_t s = q - pf.o;
+    for (uint32_t d = 0; d < pf.n_sets; d++) {
+      if (d == pf.o) continue;
+      if (s + d >= a.n) return a.text_continues ? s : kNone;  // a shard's halo ends here: let the automaton report it
+      const uint32_t b = __ldg(a.text + s + d);
+      if (!((sets[d * 8 + (b >> 5)] >> (b & 31)) & 1u)) return kNone;
+    }
+    return s;
+  };
+  auto accept = [&](uint64_t s, uint64_t e) {  // uniform arguments
+    if (s < p) return;
+    if (fc == kNone) fc = s;
+    if (lane == 0 && w_at + total < limit_out) {
+      dst[2 * (w_at + total)] = s;
+      dst[2 * (w_at + total) + 1] = e;
+    }
+    total++;
+    p = lm = e;
+  };
+  for (uint64_t off = cb; off < q_hi; off += 2048) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint64_t pos = off + u * 512 + lane * 16;
+      if (pos + 16 <= a.n) {
+        v[u] = ldg128_stream(a.text + pos);
+      } else {  // the last bytes of the buffer
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 16; j++)
+          if (pos + j < a.n) w[j >> 2] |= (uint32_t)a.text[pos + j] << (8 * (j & 3));
+        v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint64_t pos = off + u * 512 + lane * 16;
+      const uint32_t t0 = swar_any(pf, v[u].x), t1 = swar_any(pf, v[u].y), t2 = swar_any(pf, v[u].z), t3 = swar_any(pf, v[u].w);
+      const bool mine = (t0 | t1 | t2 | t3) != 0 && pos < q_hi;
+      if (!__any_sync(0xffffffffu, mine)) continue;
+      // ---- rare path: some lane of the warp saw one of the bytes ----
+      uint32_t bits = 0;
+      if (mine) {
+        bits = flags_to_bits(t0) | (flags_to_bits(t1) << 4) | (flags_to_bits(t2) << 8) | (flags_to_bits(t3) << 12);
+        if (pos + 16 > q_hi) bits &= (1u << (uint32_t)(q_hi - pos)) - 1u;
+      }
+      // every lane verifies its first two surviving candidates in parallel
+      uint64_t s0 = kNone, e0 = kNone, s1 = kNone, e1 = kNone;
+      uint32_t nv = 0;
+      uint32_t rest = bits;
+      while (rest && nv < 3) {
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const uint64_t s = candidate(pos + j, word_byte(v[u], j));
+        if (s == kNone || s < p) continue;  // p only grows: nothing before it can be accepted
+        const uint64_t e = R.end_from(a, s);
+        if (e == kNone) continue;
+        if (nv == 0) { s0 = s; e0 = e; }
+        else if (nv == 1) { s1 = s; e1 = e; }
+        nv++;
+      }
+      const bool crowded = nv >= 3 || (nv == 2 && rest != 0);
+      uint32_t active = __ballot_sync(0xffffffffu, nv != 0);
+      if (!__any_sync(0xffffffffu, crowded)) {
+        while (active) {
+          const int l = __ffs(active) - 1;
+          active &= active - 1;
+          const uint64_t as0 = __shfl_sync(0xffffffffu, s0, l), ae0 = __shfl_sync(0xffffffffu, e0, l);
+          const uint64_t as1 = __shfl_sync(0xffffffffu, s1, l), ae1 = __shfl_sync(0xffffffffu, e1, l);
+          accept(as0, ae0);
+          if (as1 != kNone) accept(as1, ae1);
+        }
+      } else {
+        // more than two matches start inside one 16-byte piece (e.g. `HH` on HHHH...): lane by lane, in order
+        active = __ballot_sync(0xffffffffu, bits != 0);
+        while (active) {
+          const int l = __ffs(active) - 1;
+          active &= active - 1;
+          uint32_t lb = __shfl_sync(0xffffffffu, bits, l);
+          const uint64_t lpos = __shfl_sync(0xffffffffu, pos, l);
+          while (lb) {  // uniform loop: every lane evaluates lane l's candidates (same addresses: broadcast loads)
+            const int j = __ffs(lb) - 1;
+            lb &= lb - 1;
+            const uint64_t q = lpos + j;
+            const uint64_t s = candidate(q, __ldg(a.text + q));
+            if (s == kNone || s < p) continue;
+            const uint64_t e = R.end_from(a, s);
+            if (e != kNone) accept(s, e);
+          }
+        }
+      }
+    }
+  }
+  c.p = p;
+  c.lm = lm;
+  if (total) c.chain = true;
+  *first_cand = fc;
+  return total;
+}
+
+template <int FAST>
+__global__ void __launch_bounds__(256) literal_scan(WalkArgs a, PfArgs pf, int mode) {
+  const auto R = RunnerSetup<FAST>::make(a);
+  __shared__ uint32_t sets[32];
+  if (threadIdx.x < 32) sets[threadIdx.x] = pf.sets[threadIdx.x >> 3][threadIdx.x & 7];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  if (mode == 2) {  // sequential pass: one warp, chunk after chunk with exact entry states
+    if (warp != 0) return;
+    Chain c;
+    c.p = a.in_p[a.seq_from];
+    c.lm = a.in_lm[a.seq_from];
+    c.chain = c.p != kSpec;
+    for (uint64_t k = a.seq_from; k < a.n_chunks; k++) {
+      const bool spec = !c.chain;
+      if (spec) { c.p = 0; c.lm = kNone; }
+      else if (lane == 0) { a.in_p[k] = c.p; a.in_lm[k] = c.lm; }
+      uint64_t fc = kNone;
+      const uint64_t total = pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+      if (spec && total == 0) { c.p = a.base + k * (uint64_t)a.chunk + 1; }
+      if (lane == 0) finish_chunk(a, k, c, total, fc, spec);
+      c.chain = true;
+    }
+    return;
+  }
+  const uint64_t work = mode == 1 ? (uint64_t)*a.n_dirty : a.n_chunks;
+  for (uint64_t idx = warp; idx < work; idx += n_warps) {
+    const uint64_t k = mode == 1 ? a.dirty_list[idx] : idx;
+    if (mode == 3 && (a.count[k] <= a.stage_cap)) continue;
+    Chain c;
+    c.p = a.in_p[k];
+    c.lm = a.in_lm[k];
+    c.chain = c.p != kSpec;
+    const bool spec = !c.chain;
+    if (spec) { c.p = 0; c.lm = kNone; }  // accept from the chunk's first candidate on
+    uint64_t fc = kNone;
+    if (mode == 3) {
+      pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.out, a.offset[k], a.cap);
+      continue;
+    }
+    const uint64_t total = pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    if (spec && total == 0) c.p = a.base + k * (uint64_t)a.chunk + 1;  // what a speculative walk without matches reports (never used: IDENT)
+    if (lane == 0) finish_chunk(a, k, c, total, fc, spec);
+  }
+}
+template __global__ void literal_scan<0>(WalkArgs, PfArgs, int);
+template __global__ void literal_scan<1>(WalkArgs, PfArgs, int);
+
+// compact_spans without the re-walk of overflowed chunks (literal_scan mode 3 does those)
+__global__ void __launch_bounds__(256) compact_staged(WalkArgs a) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const ulonglong2* stage = reinterpret_cast<const ulonglong2*>(a.stage);
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.out);
+  for (uint64_t g = warp0; g * 32 < a.n_chunks; g += n_warps) {
+    const uint64_t k = g * 32 + lane;
+    const uint64_t my_cnt = k < a.n_chunks ? a.count[k] : 0;
+    const uint64_t my_at = k < a.n_chunks ? a.offset[k] : 0;
+    const uint32_t my_skip = k < a.n_chunks ? a.skip[k] : 0;
+    uint32_t todo = __ballot_sync(0xffffffffu, my_cnt != 0 && my_cnt <= a.stage_cap);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint64_t cnt = __shfl_sync(0xffffffffu, my_cnt, j), at = __shfl_sync(0xffffffffu, my_at, j);
+      const uint32_t sk = __shfl_sync(0xffffffffu, my_skip, j);
+      for (uint64_t i = lane; i < cnt; i += 32)
+        if (at + i < a.cap) dst[at + i] = stage[(g * 32 + j) * (uint64_t)a.stage_cap + sk + i];
+    }
+  }
+}
+
 // FUSED: each lane also walks the find_iter chain over its own segment right after
 // scanning it (chunk == segment), while the segment's haystack bytes are still in L2 and
 // without a second kernel's bitmap round trip.  The walk is speculative exactly like

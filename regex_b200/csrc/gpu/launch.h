@@ -75,6 +75,21 @@ struct WalkArgs {
   int can_match_empty;
 };
 
+// Literal prefilter (kernels.cu "literal prefilter"): the byte to scan for and the byte sets a
+// match can have at its first offsets, derived from the anchored forward automaton on the host.
+struct PfArgs {
+  uint32_t o;           // offset of the scanned byte inside a match (< min match length)
+  uint32_t n_bytes;     // 1..4 byte values to scan for
+  uint32_t bcast[4];    // each replicated into the four bytes of a word
+  uint32_t n_sets;      // leading offsets 0..n_sets-1 of a match with a membership set (<= 4)
+  uint32_t sets[4][8];  // 256-bit sets
+};
+// mode 0: every chunk (one warp per chunk, grid-stride); 1: the dirty list; 2: sequential pass from
+// a.seq_from (one warp); 3: chunks that overflowed their staging slots, straight into a.out
+template <int FAST>
+__global__ void literal_scan(WalkArgs a, PfArgs pf, int mode);
+__global__ void compact_staged(WalkArgs a);
+
 struct BatchArgs {
   DfaView fwd;
   DfaView rev;
