@@ -7,17 +7,28 @@ this rank's resident haystack shard.
 
 Workload at N=1 = BASELINE.json configs[1]: sherlock-style patterns over 16 GiB of
 synthetic English text (lines of bench/src/data/sherlock.txt sampled with replacement,
-SURVEY.md §8d C2), headline pattern `[a-zA-Z]+ing`.  At N>1 every rank holds its own
+SURVEY.md 8d C2), headline pattern `[a-zA-Z]+ing`.  At N>1 every rank holds its own
 16 GiB shard of a 16*N GiB corpus (weak scaling, byte-range sharding); see
 regex_b200/sharded.py for the boundary exchange.
 
+Besides the contract's keys the line carries
+  parity       span-exact comparison with the oracle on windows of the haystack (first and last
+               256 MiB, random 16 MiB windows, both sides of every shard boundary)
+  e2e          the same search through rure_b200_find_all on pinned HOST memory, whole shard
+  cpu_baseline the oracle port of the reference's CPU engine on the whole shard, all host threads
+  rg           ripgrep (a descendant of the reference engine) on a <= 4 GiB slice, counts cross-checked
+  configs      the other BASELINE.json configs (C1, C3, C4, C5) at full size (N=1 only)
+  also         the other C2 patterns
+
 `--impl reference` times the CPU path (the oracle's restatement of the reference's lazy
 DFA pipeline -- the reference itself is Rust and cannot be built here) on the box's
-host cores over a bounded sample of the same corpus.
+host cores over the SAME corpus (one 16 GiB shard, generated with the same seed).
 """
 import argparse
+import ctypes
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -25,13 +36,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import corpus as C  # noqa: E402  (tools/corpus.py: the synthetic inputs)
 
 PATTERN = r"[a-zA-Z]+ing"
-ALSO = [r"Holmes|Watson", r"Sherlock|Holmes", r"Sher[a-z]+|Hol[a-z]+", r"(?i)Sherlock|Holmes|Watson", r"the\s+\w+"]
-SEED = 0x5EED0001
-GIB = 1 << 30
-# ncu --set full, scan_rev_fast<1> on 1 GiB of this corpus: 1.762 GB read + 0.223 GB written (profiles/r01_ncu_fused_scan.md)
+ALSO = [r"Holmes|Watson", r"Sherlock|Holmes", r"Sher[a-z]+|Hol[a-z]+", r"(?i)Sherlock|Holmes|Watson", r"the\s+\w+", r"\w+"]
+SEED = C.SEED
+GIB = C.GIB
+sherlock_lines, host_corpus, device_corpus = C.sherlock_lines, C.host_corpus, C.device_corpus
+# ncu --set full, scan_rev_fast<1> on 1 GiB of this corpus (profiles/): dram bytes read + written per haystack byte
 TRAFFIC_PER_BYTE = (1.762146e9 + 0.22295552e9) / (1 << 30)
+METRIC = "haystack GB/s scanned (find_iter, bit-exact spans)"
 
 
 def parse_args():
@@ -44,65 +60,12 @@ def parse_args():
     ap.add_argument("--pattern", default=PATTERN)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity windows beyond the shard edges, rg, the other configs and patterns")
+    ap.add_argument("--lines", type=int, default=100_000_000, help="C3 log lines")
     ap.add_argument("--seg", type=int, default=0, help="scan segment bytes (0 = automatic)")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--no-tensor-tma", action="store_true")
-    ap.add_argument("--also", action="store_true", help="time the other C2 patterns once each (extra keys)")
     return ap.parse_args()
-
-
-# ------------------------------------------------------------------ corpus ----
-def sherlock_lines():
-    text = open(os.path.join(ROOT, "tests", "golden", "sherlock.txt"), "rb").read()
-    lines = text.split(b"\n")[:-1]
-    return [l + b"\n" for l in lines]
-
-
-def host_corpus(n_bytes, seed=SEED):
-    """Same distribution as the device corpus, built on the host (CPU baseline sample)."""
-    import numpy as np
-    lines = sherlock_lines()
-    lens = np.array([len(l) for l in lines], dtype=np.int64)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    parts, total = [], 0
-    while total < n_bytes:
-        for i in rng.integers(0, len(lines), size=8192):
-            parts.append(lines[i])
-            total += int(lens[i])
-            if total >= n_bytes:
-                break
-    return b"".join(parts)[:n_bytes]
-
-
-def device_corpus(n_bytes, seed, device):
-    """Lines of sherlock.txt sampled with replacement, materialised directly in HBM."""
-    import numpy as np
-    import torch
-    lines = sherlock_lines()
-    lens = torch.tensor([len(l) for l in lines], dtype=torch.int64, device=device)
-    starts = torch.cumsum(lens, 0) - lens
-    flat = torch.frombuffer(bytearray(b"".join(lines)), dtype=torch.uint8).to(device)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    out = torch.empty(n_bytes, dtype=torch.uint8, device=device)
-    block = 64 << 20
-    mean = float(lens.float().mean())
-    pos = 0
-    while pos < n_bytes:
-        want = min(block, n_bytes - pos)
-        k = int(want / mean * 1.05) + 64
-        pick = torch.randint(0, len(lines), (k,), generator=gen, device=device)
-        l = lens[pick]
-        cum = torch.cumsum(l, 0)
-        have = int(cum[-1])
-        take = min(want, have)
-        idx = torch.arange(take, device=device, dtype=torch.int64)
-        line = torch.searchsorted(cum, idx, right=True)
-        src = starts[pick[line]] + (idx - (cum[line] - l[line]))
-        out[pos:pos + take] = flat[src]
-        pos += take
-        del idx, line, src, cum, l, pick
-    return out
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -144,41 +107,93 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons, "samples": len(sm)}
 
 
-# --------------------------------------------------------------- reference ----
-def cpu_reference(pattern, sample, threads, steps, warmup):
+# ---------------------------------------------------- the CPU legs (oracle) ----
+def _count_parallel_ptr(pattern, ptr, n, threads):
+    """oracle.count_parallel on a raw host buffer (a 16 GiB haystack is not copied into a bytes object)."""
+    from oracle import oracle as O
+    p = pattern.encode("utf-8")
+    return O.lib().oracle_count_parallel(p, len(p), O.FLAG_UNICODE, 0, ctypes.cast(ptr, ctypes.c_char_p), n, threads)
+
+
+def cpu_reference_ptr(pattern, ptr, n, threads, steps, warmup):
     from oracle import oracle as O
     O.build()
     for _ in range(warmup):
-        O.count_parallel(pattern, sample[: len(sample) // 8], threads)
+        _count_parallel_ptr(pattern, ptr, min(n, 1 << 30), threads)
     t0 = time.perf_counter()
     count = 0
     for _ in range(steps):
-        count = O.count_parallel(pattern, sample, threads)
+        count = _count_parallel_ptr(pattern, ptr, n, threads)
     dt = (time.perf_counter() - t0) / steps
-    return len(sample) / dt / 1e9, dt, count
+    return n / dt / 1e9, dt, count
+
+
+def oracle_spans(o, data):
+    """find_iter spans of `data` (bytes) as an int64 [k, 2] array."""
+    import numpy as np
+    from oracle import oracle as O
+    total = O.lib().oracle_find_iter(o._h, O.ENGINE_DFA, data, len(data), None, 0)
+    buf = np.empty((max(total, 1), 2), dtype=np.uint64)
+    O.lib().oracle_find_iter(o._h, O.ENGINE_DFA, data, len(data), buf.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t)), total)
+    return buf[:total].astype(np.int64)
 
 
 def run_reference(args):
+    """The reference's own CPU algorithm (oracle port; kind "port": no rustc in this image) on the
+    arm's config: the same 16 GiB shard (same generator and seed), every step scans all of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     threads = os.cpu_count() or 1
-    sample_bytes = 256 << 20
-    sample = host_corpus(sample_bytes)
-    gbs, dt, count = cpu_reference(args.pattern, sample, threads, max(1, args.steps), min(args.warmup, 1))
+    n = int(args.gib * GIB)
+    if torch.cuda.is_available():  # the same bytes the GPU arm scans (the generator runs on the device)
+        torch.cuda.set_device(0)
+        dev_text = device_corpus(n, SEED, torch.device("cuda", 0))
+        host = torch.empty(n, dtype=torch.uint8)
+        host.copy_(dev_text)
+        del dev_text
+        torch.cuda.empty_cache()
+        how = "generated by the GPU arm's generator with the same seed, copied to host memory before timing"
+    else:
+        host = torch.frombuffer(bytearray(host_corpus(n)), dtype=torch.uint8)
+        how = "host generator (no GPU visible)"
+    steps = max(1, min(args.steps, 5))
+    gbs, dt, count = cpu_reference_ptr(args.pattern, host.data_ptr(), n, threads, steps, min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": "haystack GB/s scanned (find_iter, bit-exact spans)", "value": round(gbs, 4),
-        "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 4),
+        "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}` over {args.gib:g} GiB/GPU synthetic English text "
-                               f"(reference arm: each step scans a bounded {sample_bytes >> 20} MiB sample of that corpus on the host cores)",
-                   "haystack_bytes_per_gpu": int(args.gib * GIB), "sample_bytes": sample_bytes},
+                               f"(reference arm: every step scans one whole {args.gib:g} GiB shard on the host cores; {how})",
+                   "haystack_bytes_per_gpu": n, "sample_bytes": n, "matches": count},
         "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_bytes >> 20} MiB of the C2 corpus, {threads} threads, byte ranges cut at newlines, oracle engine 'auto' "
-                                   f"(DfaSuffix where the reference selects it); matches={count}"},
+                         "sample": f"the whole {args.gib:g} GiB shard, {threads} threads, byte ranges cut at newlines, oracle engine 'auto' "
+                                   f"(DfaSuffix where the reference selects it, exec.rs:1176-1210); matches={count}"},
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------- parity windows ----
+def check_window(o, text, spans_dev, n_spans, pos_shift, a, b):
+    """Span-exact comparison on [a, b) of the buffer `text`: the oracle runs on the window cut at
+    line starts (no match of these patterns contains a newline) and must reproduce exactly the
+    GPU spans that lie inside it.  spans_dev holds buffer-relative positions + pos_shift."""
+    import numpy as np
+    import torch
+    nl = torch.nonzero(text[a:min(b, a + (1 << 16))] == 10)
+    a2 = a if a == 0 else a + int(nl[0]) + 1
+    tail = torch.nonzero(text[max(a2, b - (1 << 16)):b] == 10)
+    b2 = b if b == text.numel() else max(a2, b - (1 << 16)) + int(tail[-1]) + 1
+    host = text[a2:b2].cpu().numpy().tobytes()
+    exp = oracle_spans(o, host) + a2
+    starts = spans_dev[:n_spans, 0].contiguous()
+    lo = int(torch.searchsorted(starts, torch.tensor([a2 + pos_shift], device=starts.device))[0])
+    hi = int(torch.searchsorted(starts, torch.tensor([b2 + pos_shift], device=starts.device))[0])
+    got = spans_dev[lo:hi].cpu().numpy() - pos_shift
+    ok = got.shape == exp.shape and bool((got == exp).all())
+    return ok, int(exp.shape[0]), b2 - a2
 
 
 # -------------------------------------------------------------------- ours ----
@@ -272,25 +287,27 @@ def run_ours(args):
     ms_per_step = dev_s / args.steps * 1e3
     value = total_len / (dev_s / args.steps) / 1e9
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
     result = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         scan = sum(scan_ms) / len(scan_ms)
-        fused = bool(st["fused"])
+        path = {0: "scan_rev_bitmap (generic scan)", 1: "scan_rev_fast<scan only>", 2: "scan_rev_fast<fused scan+walk>", 3: "literal_scan (prefilter)"}[int(st["path"])]
+        emits = int(st["path"]) in (2, 3)
         # 1 byte read per haystack byte + 16 bytes written per emitted span; the start
         # bitmap, staging and stitch traffic are this design's overhead and earn no credit.  The fused
         # kernel (reverse scan + chain walk of each segment) emits the spans; without fusion the
         # dominant kernel is the scan alone and the spans belong to walk_chunks.
-        alg_bytes = n + (16 * n_local if fused else 0)
+        alg_bytes = n + (16 * n_local if emits else 0)
         achieved = alg_bytes / (scan / 1e3) / 1e9
         result = {
-            "metric": "haystack GB/s scanned (find_iter, bit-exact spans)", "value": round(value, 2), "unit": "GB/s",
+            "metric": METRIC, "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"C2 sherlock-style find_iter `{args.pattern}` over {args.gib:g} GiB/GPU synthetic English text "
@@ -302,72 +319,166 @@ def run_ours(args):
                        "boundary_fixup_rounds": rounds},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": TRAFFIC_PER_BYTE * n if fused and args.pattern == PATTERN else None,
-                         "traffic_source": "ncu --set full dram__bytes_read+write of scan_rev_fast<1> on a 1 GiB haystack (profiles/r01_ncu_fused_scan.md), scaled per byte",
-                         "kernel": "scan_rev_fast<fused scan+walk>" if fused else "scan_rev_fast<scan only>", "peak_source": peak_src,
+                         "traffic": TRAFFIC_PER_BYTE * n if int(st["path"]) == 2 and args.pattern == PATTERN else None,
+                         "traffic_source": "ncu --set full dram__bytes_read+write of scan_rev_fast<1> on a 1 GiB haystack (profiles/), scaled per byte",
+                         "kernel": path, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(scan, 4),
-                         "other_kernels_ms": round(sum(walk_ms) / len(walk_ms), 4)},
+                         "other_kernels_ms": round(sum(walk_ms) / len(walk_ms), 4),
+                         "step_frac": round((n + 16 * n_local) / (ms_per_step / 1e3) / 1e9 / peak, 4)},
             "clocks": clk.summary(),
-            "fixups": {k: st[k] for k in ("scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks")},
+            "fixups": {k: st[k] for k in ("scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks", "sequential_passes", "map_passes")},
         }
 
+    # ---- parity: span-exact windows against the oracle ----
+    from oracle import oracle as O
+    O.build()
+    o = O.OracleRegex(args.pattern)
+    win = (256 << 20) if world == 1 else (64 << 20)
+    win = min(win, n // 2)
+    lo_o, hi_o = geom.own_lo, geom.own_lo + n
+    windows = [("first", lo_o, lo_o + win), ("last", hi_o - win, hi_o)]
+    if world == 1 and not args.no_extras:
+        rng = np.random.Generator(np.random.PCG64(0x5EED))
+        w16 = min(16 << 20, n // 4)
+        for i in range(64 if n >= (4 << 30) else 8):
+            a = int(rng.integers(0, n - w16)) // 256 * 256
+            windows.append((f"random{i}", lo_o + a, lo_o + a + w16))
+    par = {"windows": 0, "spans": 0, "bytes": 0, "mismatches": []}
+    for name, a, b in windows:
+        ok, k, nb = check_window(o, text, engine.spans, n_local, 0, a, b)
+        par["windows"] += 1
+        par["spans"] += k
+        par["bytes"] += nb
+        if not ok:
+            par["mismatches"].append(f"rank{rank}:{name}")
+    pt = torch.tensor([par["windows"], par["spans"], par["bytes"], len(par["mismatches"])], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt)
+    assert int(pt[3]) == 0, ("span parity failed", par["mismatches"])
+    if rank == 0:
+        result["parity"] = {"windows": int(pt[0]), "spans_compared": int(pt[1]), "bytes_compared": int(pt[2]), "mismatches": 0,
+                            "what": "GPU spans == oracle find_iter spans on the first and last %d MiB of every shard (both sides of every shard "
+                                    "boundary)%s, windows cut at line starts" % (win >> 20, " and 64 random 16 MiB windows" if len(windows) > 2 else "")}
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    host = None
+    if not args.no_e2e or (rank == 0 and not args.no_cpu):
+        host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host.copy_(text[geom.own_lo:geom.own_lo + n])
+        torch.cuda.synchronize()
     if not args.no_e2e:
-        e2e_n = min(n, 4 * GIB)
-        lo = geom.own_lo
-        host = torch.empty(e2e_n, dtype=torch.uint8, pin_memory=True)
-        host.copy_(text[lo:lo + e2e_n])
-        cap = int(n_local * (e2e_n / n) * 1.1) + 4096
-        out = np.empty((cap, 2), dtype=np.uint64)
+        cap = n_local + 4096
+        out_t = torch.empty((cap, 2), dtype=torch.int64, pin_memory=True)  # the caller's result buffer, pinned like the haystack
+        out = out_t.numpy().view(np.uint64)
         tot = R.ctypes.c_size_t()
         for _ in range(2):
-            R.lib().rure_b200_find_all(re_._h, host.data_ptr(), e2e_n, out.ctypes.data, cap, R.byref(tot))
+            R.lib().rure_b200_find_all(re_._h, host.data_ptr(), n, out.ctypes.data, cap, R.byref(tot))
         barrier()
         k = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(k):
-            ok = R.lib().rure_b200_find_all(re_._h, host.data_ptr(), e2e_n, out.ctypes.data, cap, R.byref(tot))
+            ok = R.lib().rure_b200_find_all(re_._h, host.data_ptr(), n, out.ctypes.data, cap, R.byref(tot))
             assert ok
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if world == 1:
+            mine = engine.spans[:n_local].cpu().numpy().astype(np.uint64)
+            assert tot.value == n_local and (out[:n_local] == mine).all(), "e2e spans differ from the device-resident search"
         if rank == 0:
-            result["e2e"] = {"value": round(e2e_n * world / float(t[0]) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": e2e_n,
-                             "d2h_bytes_per_step": int(min(tot.value, cap) * 16 + 8), "haystack_bytes": e2e_n,
-                             "note": "rure_b200_find_all on pinned host memory per rank (independent haystacks); H2D of the haystack and "
-                                     "D2H of all spans inside the timed region; the library pipelines upload, search and "
-                                     "download in 64 MiB pieces"}
-        del host
+            result["e2e"] = {"value": round(n * world / float(t[0]) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
+                             "d2h_bytes_per_step": int(min(tot.value, cap) * 16 + 8), "haystack_bytes": n,
+                             "note": "rure_b200_find_all on pinned host memory, the whole shard per rank (at N>1: one independent haystack per rank, "
+                                     "max over ranks); H2D of the haystack and D2H of all spans inside the timed region; the library pipelines "
+                                     "upload, search and download in 64 MiB pieces; spans compared with the device-resident search"}
+        del out, out_t
 
     if rank == 0:
-        if args.also:
-            also = {}
-            spans = torch.empty((n_local * 2 + 4096, 2), dtype=torch.int64, device=dev)
-            local = text[geom.own_lo:geom.own_lo + n]
-            for pat in ALSO:
-                r2 = R.BytesRegex(pat)
-                r2.find_all_device(local)
-                c = r2.find_all_device(local, spans)
-                also[pat] = {"GB/s": round(n / (r2.last_stats()["total_ms"] / 1e3) / 1e9, 1), "matches": c}
-            result["also"] = also
+        threads = os.cpu_count() or 1
         if not args.no_cpu:
-            from oracle import oracle as O
-            sample_bytes = 128 << 20
-            sample = text[geom.own_lo:geom.own_lo + sample_bytes].cpu().numpy().tobytes()
-            last_nl = sample.rfind(b"\n") + 1
-            threads = os.cpu_count() or 1
-            gbs, dt, count = cpu_reference(args.pattern, sample[:last_nl], threads, 1, 1)
-            gpu_count = R.BytesRegex(args.pattern).find_all_device(text[geom.own_lo:geom.own_lo + last_nl].contiguous())
-            assert gpu_count == count, ("parity spot check failed", gpu_count, count)
+            gbs, dt, count = cpu_reference_ptr(args.pattern, host.data_ptr(), n, threads, 1, 1)
+            assert count == n_local, ("parity check failed: CPU count != GPU count", count, n_local)
             result["cpu_baseline"] = {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                                      "sample": f"first {last_nl >> 20} MiB of rank 0's shard, {threads} threads cut at newlines, oracle engine 'auto' "
+                                      "sample": f"rank 0's whole {args.gib:g} GiB shard, {threads} threads cut at newlines, oracle engine 'auto' "
                                                 f"(DfaSuffix as the reference selects for this pattern, exec.rs:1176-1210), count {count} == GPU count"}
+        if not args.no_extras and not args.no_cpu:
+            result["rg"] = rg_leg(args.pattern, host, n, re_, text, geom)
+    del host
+    if rank == 0 and world == 1 and not args.no_extras:
+        result["also"] = also_patterns(R, text, n, n_local, dev, peak)
+        result["configs"] = other_configs(args, text, dev)
+    if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def rg_leg(pattern, host, n, re_, text, geom):
+    """Independent data point: ripgrep, a descendant of the reference engine (lazy DFA +
+    SIMD literals, newer Unicode tables), single thread, on a <= 4 GiB slice; count cross-checked."""
+    rg = shutil.which("rg")
+    if not rg:
+        return {"unavailable": "rg not on PATH"}
+    import numpy as np
+    import torch
+    k = min(n, 4 * GIB)
+    arr = host[:k].numpy()
+    k = int(np.flatnonzero(arr[max(0, k - 65536):k] == 10)[-1]) + max(0, k - 65536) + 1  # cut at a line end
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > k + (1 << 30) else "/tmp"
+    path = os.path.join(tmpdir, f"rb200_rg_slice_{os.getpid()}.txt")
+    try:
+        arr[:k].tofile(path)
+        t0 = time.perf_counter()
+        out = subprocess.run([rg, "-U", "-a", "--count-matches", "-j1", "--no-config", "-e", pattern, path], capture_output=True, text=True, timeout=600)
+        dt = time.perf_counter() - t0
+        count = int(out.stdout.strip() or 0)
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+    gpu = re_.find_all_device(text[geom.own_lo:geom.own_lo + k].contiguous())
+    ver = subprocess.run([rg, "--version"], capture_output=True, text=True).stdout.split("\n")[0]
+    return {"value": round(k / dt / 1e9, 3), "unit": "GB/s", "threads": 1, "bytes": k, "count": count, "gpu_count_same_slice": gpu,
+            "counts_equal": count == gpu, "version": ver, "note": "rg -U -a --count-matches -j1 on a file in %s (page cache); wall clock of the process" % tmpdir}
+
+
+def also_patterns(R, text, n, n_local, dev, peak):
+    import torch
+    also = {}
+    spans = torch.empty((min(int(n / 3.5), 1 << 30) + 4096, 2), dtype=torch.int64, device=dev)  # `\w+` finds more; the rest is counted, not stored
+    for pat in ALSO:
+        r2 = R.BytesRegex(pat)
+        r2.set_stream(torch.cuda.current_stream().cuda_stream)
+        c = r2.find_all_device(text)
+        ms = []
+        for _ in range(3):
+            c = r2.find_all_device(text, spans)
+            ms.append(r2.last_stats()["total_ms"])
+        t = sorted(ms)[1]
+        also[pat] = {"GB/s": round(n / (t / 1e3) / 1e9, 1), "matches": c, "roofline_frac_step": round((n + 16 * min(c, spans.shape[0])) / (t / 1e3) / 1e9 / peak, 4),
+                     "path": int(r2.last_stats()["path"])}
+    del spans
+    return also
+
+
+def other_configs(args, text, dev):
+    """C1, C3, C4, C5 at the sizes BASELINE.json names (one GPU), each with a bounded oracle check;
+    the full-size parity tests are tests/test_gpu_configs.py."""
+    import torch
+    import bench_configs as BC
+    out = {}
+    for name, fn in (("C1", lambda: BC.c1(dev)), ("C4", lambda: BC.c4(dev, text)), ("C3", lambda: BC.c3(dev, args.lines)),
+                     ("C5", lambda: BC.c5(dev, args.gib))):
+        try:
+            t0 = time.perf_counter()
+            out[name] = fn()
+            out[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+        except Exception as e:  # a failed extra must not lose the headline line; it is reported as failed
+            out[name] = {"failed": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():

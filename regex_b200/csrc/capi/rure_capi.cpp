@@ -337,7 +337,7 @@ static bool set_option(Regex* r, const char* name, uint64_t value) {
   else if (k == "narrow_sets") t.narrow_sets = value != 0;
   else if (k == "max_stitch_rounds") t.max_stitch_rounds = (uint32_t)value;
   else if (k == "max_redo_rounds") t.max_redo_rounds = (uint32_t)value;
-  else if (k == "prefilter") t.prefilter = value != 0;
+  else if (k == "prefilter") t.prefilter = (int)value;
   else { g_last_error = "unknown option: " + k; return false; }
   return true;
 }

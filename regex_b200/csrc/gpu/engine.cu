@@ -332,7 +332,13 @@ static const uint16_t kByteFreq[256] = {
 // estimated frequency at some fixed offset o < min_len (the reference scans for its rarest
 // literal byte, src/literals.rs:466-489; here the bytes come from the automaton, so character
 // classes and alternations qualify as well: `Sher[a-z]+|Hol[a-z]+` scans for S and H).
-static constexpr uint32_t kPrefilterMaxFreq = 600;  // ~0.9 % of the haystack's bytes
+// Measured on the B200 (profiles/r02_prefilter.md): the word-wide byte tests cost ~2.3
+// instructions per haystack byte for two byte values, and every hit costs a queue push plus its
+// share of a verification round, against 5 instructions per byte for the shared-memory DFA scan.
+// `Holmes|Watson` over the C2 corpus (an H or W every 238 bytes, a match every 1.1 KB) runs at
+// 1.33 TB/s here and at 2.93 TB/s on the fused DFA path, so the automatic choice is conservative:
+static constexpr uint32_t kPrefilterMaxFreq = 600;   // structural limit (tuning.prefilter == 2): ~0.9 % of the bytes
+static constexpr uint32_t kPrefilterAutoFreq = 80;   // automatic (tuning.prefilter == 1): ~0.12 %, i.e. one rare byte
 static constexpr uint32_t kPrefilterState = 0xFFFEu; // what a prefilter shard reports as its boundary states
 bool Regex::plan_prefilter() {
   if (pf_state_) return pf_state_ > 0;
@@ -371,6 +377,7 @@ bool Regex::plan_prefilter() {
     for (int b = 0; b < 256; b++) if (allowed[dep][b]) a.sets[dep][b >> 5] |= 1u << (b & 31);
   pf_words_.resize(sizeof(PfArgs) / 4);
   std::memcpy(pf_words_.data(), &a, sizeof a);
+  pf_freq_ = best_f;
   pf_state_ = 1;
   return true;
 }
@@ -623,7 +630,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   const bool wfast = !wfixed && fwd->hot.n != 0 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
   // literal prefilter: no start bitmap at all -- literal_scan finds, verifies and chains the candidates
-  const bool use_pf = tuning.prefilter && !tuning.force_generic && ((uintptr_t)d_text & 15) == 0 && plan_prefilter();
+  const bool use_pf = tuning.prefilter && !tuning.force_generic && ((uintptr_t)d_text & 15) == 0 && plan_prefilter() &&
+                      (tuning.prefilter >= 2 || pf_freq_ <= kPrefilterAutoFreq);
   PfArgs pf{};
   if (use_pf) std::memcpy(&pf, pf_words_.data(), sizeof pf);
   const bool pf_fast = use_pf && fwd->hot.n != 0 && fwd->view.uniform_start;
@@ -694,27 +702,33 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     if (pf_fast) {
       wsmem = hot_bytes(fwd->hot.n) + 256;
       w.fwd_hot = fwd->hot;
-      RB_CUDA(allow_smem(literal_scan<1>, wsmem));
     } else {
       wsmem = smem_for(fwd->view);
       w.use_smem = wsmem != 0;
-      RB_CUDA(allow_smem(literal_scan<0>, wsmem));
     }
   }
-  auto launch_pf = [&](const WalkArgs& args, uint64_t chunks, int mode) {
+  auto launch_pf = [&](const WalkArgs& args, uint64_t chunks, int mode) -> cudaError_t {
     const uint32_t g = mode == 2 ? 1 : grid_for(chunks * 32, 256, 3);  // one warp per chunk
-    if (pf_fast) literal_scan<1><<<g, 256, wsmem, st>>>(args, pf, mode);
-    else literal_scan<0><<<g, 256, wsmem, st>>>(args, pf, mode);
+#define RB_PF(F, N)                                                                \
+    {                                                                              \
+      cudaError_t e__ = allow_smem(literal_scan<F, N>, wsmem);                     \
+      if (e__ != cudaSuccess) return e__;                                          \
+      literal_scan<F, N><<<g, 256, wsmem, st>>>(args, pf, mode);                   \
+      return cudaSuccess;                                                          \
+    }
+    if (pf_fast) switch (pf.n_bytes) { case 1: RB_PF(1, 1) case 2: RB_PF(1, 2) case 3: RB_PF(1, 3) default: RB_PF(1, 4) }
+    switch (pf.n_bytes) { case 1: RB_PF(0, 1) case 2: RB_PF(0, 2) case 3: RB_PF(0, 3) default: RB_PF(0, 4) }
+#undef RB_PF
   };
   auto launch_walk = [&](const WalkArgs& args, uint64_t work) {
-    if (use_pf) { launch_pf(args, work, 1); return; }
+    if (use_pf) { (void)launch_pf(args, work, 1); return; }
     const uint32_t g = grid_for(work, 256, 6);
     if (wkind == 2) walk_chunks<2><<<g, 256, 0, st>>>(args);
     else if (wkind == 1) walk_chunks<1><<<g, 256, wsmem, st>>>(args);
     else walk_chunks<0><<<g, 256, wsmem, st>>>(args);
   };
   if (use_pf) {
-    launch_pf(w, nc, 0);
+    RB_CUDA(launch_pf(w, nc, 0));
     RB_LAUNCH_CHECK("literal_scan");
     io->rev_guess = io->rev_entry != kNoState ? io->rev_entry : kPrefilterState;  // no reverse scan, nothing to guess
     io->rev_left = kPrefilterState;
@@ -770,7 +784,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
       if (++dirty_rounds > tuning.max_stitch_rounds) {
         // chains that do not meet again: one sequential pass from the leftmost such chunk
         wd.seq_from = hc[3];
-        if (use_pf) launch_pf(wd, 1, 2);
+        if (use_pf) (void)launch_pf(wd, 1, 2);
         else if (wkind == 2) walk_sequential<2><<<1, 256, 0, st>>>(wd);
         else if (wkind == 1) walk_sequential<1><<<1, 256, wsmem, st>>>(wd);
         else walk_sequential<0><<<1, 256, wsmem, st>>>(wd);
@@ -793,7 +807,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   if (w.cap > 0 && use_pf) {
     compact_staged<<<grid_for(nc, 256, 6), 256, 0, st>>>(w);
     RB_LAUNCH_CHECK("compact_staged");
-    launch_pf(w, nc, 3);  // chunks with more matches than staging slots: straight into the output
+    RB_CUDA(launch_pf(w, nc, 3));  // chunks with more matches than staging slots: straight into the output
     RB_LAUNCH_CHECK("literal_scan(overflow)");
   } else if (w.cap > 0) {
     const uint32_t g = grid_for(nc, 256, 6);

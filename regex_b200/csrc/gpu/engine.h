@@ -36,7 +36,8 @@ struct Tuning {
   uint32_t blocks_per_sm = 8;
   uint64_t wave0 = 32ull << 20;  // first wave of a forward search in bytes (x8 per wave); 0 = one wave
   bool narrow_sets = true;
-  bool prefilter = true;         // literal patterns with a rare byte: memchr-style candidate scan instead of the DFA scan       // RegexSet::matches: continue with the automaton of the still-unmatched patterns
+  int prefilter = 1;             // literal_scan instead of the DFA scan: 0 never, 1 when the scanned byte is estimated rare enough
+                                 // to win (one byte, <= ~0.12 % of the haystack), 2 whenever the pattern qualifies structurally       // RegexSet::matches: continue with the automaton of the still-unmatched patterns
   uint32_t max_stitch_rounds = 16;  // re-walk rounds before the stitch falls back to one sequential pass
   uint32_t max_redo_rounds = 3;     // scan redo rounds before segment entry states are solved by state-map composition
 };
@@ -138,7 +139,7 @@ class Regex {
   int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
-  bool plan_prefilter();  // fills pf_ (launch.h PfArgs) when the pattern has a rare byte at a fixed offset
+  bool plan_prefilter();  // fills pf_words_ (launch.h PfArgs) when every match has one of <= 4 bytes at a fixed offset
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
   int forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t limit, uint32_t entry, bool want_masks,
                     uint64_t* result_host, uint32_t* exit_state);
@@ -168,6 +169,7 @@ class Regex {
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};
   int pf_state_ = 0;               // 0 = not decided yet, 1 = prefilter applies, -1 = it does not
+  uint32_t pf_freq_ = 0;           // estimated frequency of the scanned bytes, parts per 65536
   std::vector<uint32_t> pf_words_; // PfArgs image (engine.cu)
 };
 

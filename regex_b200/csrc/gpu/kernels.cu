@@ -886,40 +886,73 @@ __device__ __forceinline__ uint32_t swar_eq(uint32_t w, uint32_t cc) {
   const uint32_t x = w ^ cc;
   return (x - 0x01010101u) & ~x & 0x80808080u;
 }
-__device__ __forceinline__ uint32_t swar_any(const PfArgs& pf, uint32_t w) {
-  uint32_t t = swar_eq(w, pf.bcast[0]);
-  if (pf.n_bytes > 1) t |= swar_eq(w, pf.bcast[1]);
-  if (pf.n_bytes > 2) t |= swar_eq(w, pf.bcast[2]);
-  if (pf.n_bytes > 3) t |= swar_eq(w, pf.bcast[3]);
+template <int NB>
+__device__ __forceinline__ uint32_t swar_any(const uint32_t (&cc)[4], uint32_t w) {
+  uint32_t t = swar_eq(w, cc[0]);
+  if (NB > 1) t |= swar_eq(w, cc[1]);
+  if (NB > 2) t |= swar_eq(w, cc[2]);
+  if (NB > 3) t |= swar_eq(w, cc[3]);
   return t;
 }
 __device__ __forceinline__ uint32_t flags_to_bits(uint32_t t) {  // bits 7,15,23,31 -> bits 0..3
   return (((t >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
+// The verifier, out of line: one copy of the automaton loop however many call sites, and the
+// streaming loop stays small (the first version inlined it three times and starved on
+// instruction fetch: ncu "no instruction" 7.9 stalls per issue).
 template <typename Runner>
-__device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArgs& pf, const uint32_t* sets, const Runner& R, uint64_t k,
-                                                  Chain& c, uint64_t* first_cand, uint64_t* dst, uint64_t w_at, uint64_t limit_out) {
+__device__ __noinline__ uint64_t pf_verify(const WalkArgs* a, const Runner* R, uint64_t s) { return R->end_from(*a, s); }
+
+// Is a match possible with its scanned byte at q?  Tests the bytes at the first offsets of the
+// would-be match against the sets the automaton allows there (the set at offset o holds
+// exactly the scanned bytes).  Returns the candidate start or kNone.
+__device__ __forceinline__ uint64_t pf_candidate(const WalkArgs& a, const PfArgs& pf, const uint32_t* sets, uint64_t q) {
+  if (q < pf.o) return kNone;
+  const uint64_t s = q - pf.o;
+  if (s + 4 > a.n) {  // the last bytes of the buffer: byte loads
+    for (uint32_t d = 0; d < pf.n_sets; d++) {
+      if (s + d >= a.n) return a.text_continues ? s : kNone;  // a shard's halo ends here: let the automaton report it
+      const uint32_t b = a.text[s + d];
+      if (!((sets[d * 8 + (b >> 5)] >> (b & 31)) & 1u)) return kNone;
+    }
+    return s;
+  }
+  // four bytes at s from two aligned words: one memory round trip
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a.text + s) & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a.text + s) & 3) * 8;
+  const uint32_t w0 = __ldg(wp), w1 = sh ? __ldg(wp + 1) : 0u;
+  const uint32_t w = __funnelshift_r(w0, w1, sh);
+  bool ok = true;
+#pragma unroll
+  for (uint32_t d = 0; d < 4; d++) {
+    const uint32_t b = (w >> (8 * d)) & 0xFFu;
+    if (d < pf.n_sets) ok = ok && ((sets[d * 8 + (b >> 5)] >> (b & 31)) & 1u);
+  }
+  return ok ? s : kNone;
+}
+
+constexpr uint32_t kPfSlots = 6;  // queued hits per lane between two flushes
+constexpr uint32_t kPfWarpSmem = kPfSlots * 32 * 2 + kPfSlots * 32 * 4;  // u16 positions + u32 match lengths
+
+// The chain over chunk k.  Hits are only QUEUED while the chunk streams by (a two-byte push by
+// the lane that saw the byte: no warp-wide step per hit); at the end of the chunk every lane
+// verifies its own queue -- fingerprint, then the anchored automaton -- with all lanes that
+// have work active at once, and the warp then takes the verified matches in position order
+// (one warp-wide minimum per match) and applies the find_iter rule to them.
+template <int NB, typename Runner>
+__device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArgs& pf, const uint32_t* sets, unsigned char* warp_smem,
+                                                  const Runner& R, uint64_t k, Chain& c, uint64_t* first_cand, uint64_t* dst,
+                                                  uint64_t w_at, uint64_t limit_out) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
   const uint64_t ce = min(cb + a.chunk, a.limit);
   const uint64_t q_hi = min(ce, a.n);       // scanned bytes [cb, q_hi)
+  uint16_t* qpos = reinterpret_cast<uint16_t*>(warp_smem);                         // [slot][lane]: q - cb
+  uint32_t* qlen = reinterpret_cast<uint32_t*>(warp_smem + kPfSlots * 32 * 2);     // [slot][lane]: match length, 0 = none
   uint64_t total = 0, fc = kNone;
   uint64_t p = c.p, lm = c.lm;               // warp-uniform iterator state
-  // candidate at scanned byte q: confirm the byte and the fingerprint; returns the start or kNone
-  auto candidate = [&](uint64_t q, uint32_t byte) -> uint64_t {
-    bool is = false;
-    for (uint32_t i = 0; i < pf.n_bytes; i++) is = is || byte == (pf.bcast[i] & 0xFFu);
-    if (!is || q < pf.o) return kNone;
-    const uint64_t s = q - pf.o;
-    for (uint32_t d = 0; d < pf.n_sets; d++) {
-      if (d == pf.o) continue;
-      if (s + d >= a.n) return a.text_continues ? s : kNone;  // a shard's halo ends here: let the automaton report it
-      const uint32_t b = __ldg(a.text + s + d);
-      if (!((sets[d * 8 + (b >> 5)] >> (b & 31)) & 1u)) return kNone;
-    }
-    return s;
-  };
+  uint32_t cnt = 0;                          // queued hits of this lane
   auto accept = [&](uint64_t s, uint64_t e) {  // uniform arguments
     if (s < p) return;
     if (fc == kNone) fc = s;
@@ -930,79 +963,112 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
     total++;
     p = lm = e;
   };
-  for (uint64_t off = cb; off < q_hi; off += 2048) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint64_t pos = off + u * 512 + lane * 16;
-      if (pos + 16 <= a.n) {
-        v[u] = ldg128_stream(a.text + pos);
-      } else {  // the last bytes of the buffer
-        uint32_t w[4] = {0, 0, 0, 0};
-        for (int j = 0; j < 16; j++)
-          if (pos + j < a.n) w[j >> 2] |= (uint32_t)a.text[pos + j] << (8 * (j & 3));
-        v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+  auto flush = [&]() {
+    uint32_t maxc = cnt;
+    for (int o = 16; o; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+    if (maxc == 0) return;
+    for (uint32_t r = 0; r < maxc; r++) {  // round r: every lane with an r-th hit verifies it
+      if (r < cnt) {
+        const uint64_t q = cb + qpos[r * 32 + lane];
+        const uint64_t s = pf_candidate(a, pf, sets, q);  // includes the byte at q itself (the set at offset o)
+        uint32_t len = 0;
+        if (s != kNone && s >= p) {
+          const uint64_t e = pf_verify(&a, &R, s);
+          if (e != kNone) len = (uint32_t)min(e - s, (uint64_t)0xFFFFFFFFu);
+        }
+        qlen[r * 32 + lane] = len;
       }
     }
+    __syncwarp();
+    // verified matches in position order: each lane offers its first pending one
+    uint32_t cur = 0;
+    for (;;) {
+      while (cur < cnt && qlen[cur * 32 + lane] == 0) cur++;
+      const uint32_t key = cur < cnt ? (uint32_t)qpos[cur * 32 + lane] : 0xFFFFFFFFu;
+      const uint32_t m = __reduce_min_sync(0xffffffffu, key);
+      if (m == 0xFFFFFFFFu) break;
+      const int owner = __ffs(__ballot_sync(0xffffffffu, key == m)) - 1;
+      const uint32_t len = __shfl_sync(0xffffffffu, cur < cnt ? qlen[cur * 32 + lane] : 0u, owner);
+      const uint64_t s = cb + m - pf.o;
+      accept(s, len == 0xFFFFFFFFu ? pf_verify(&a, &R, s) : s + len);  // a match of 4 GiB or more: ask again for its end
+      if ((int)lane == owner) cur++;
+    }
+    cnt = 0;
+    __syncwarp();
+  };
+  const uint32_t cc[4] = {pf.bcast[0], pf.bcast[1], pf.bcast[2], pf.bcast[3]};
+  for (uint64_t off = cb; off < q_hi; off += 2048) {
+    uint4 v[4];
+    const bool whole = off + 2048 <= q_hi;  // the common piece: every byte inside the chunk and the buffer
+    const uint8_t* src = a.text + off + lane * 16;
+    if (whole) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = ldg128(src + u * 512);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint64_t pos = off + u * 512 + lane * 16;
+        if (pos + 16 <= a.n) {
+          v[u] = ldg128(a.text + pos);
+        } else {  // the last bytes of the buffer
+          uint32_t w[4] = {0, 0, 0, 0};
+          for (int j = 0; j < 16; j++)
+            if (pos + j < a.n) w[j >> 2] |= (uint32_t)a.text[pos + j] << (8 * (j & 3));
+          v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    const uint32_t cnt_before = cnt;
+    const uint32_t rel0 = (uint32_t)(off - cb) + lane * 16;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const uint64_t pos = off + u * 512 + lane * 16;
-      const uint32_t t0 = swar_any(pf, v[u].x), t1 = swar_any(pf, v[u].y), t2 = swar_any(pf, v[u].z), t3 = swar_any(pf, v[u].w);
-      const bool mine = (t0 | t1 | t2 | t3) != 0 && pos < q_hi;
-      if (!__any_sync(0xffffffffu, mine)) continue;
-      // ---- rare path: some lane of the warp saw one of the bytes ----
-      uint32_t bits = 0;
-      if (mine) {
-        bits = flags_to_bits(t0) | (flags_to_bits(t1) << 4) | (flags_to_bits(t2) << 8) | (flags_to_bits(t3) << 12);
-        if (pos + 16 > q_hi) bits &= (1u << (uint32_t)(q_hi - pos)) - 1u;
-      }
-      // every lane verifies its first two surviving candidates in parallel
-      uint64_t s0 = kNone, e0 = kNone, s1 = kNone, e1 = kNone;
-      uint32_t nv = 0;
-      uint32_t rest = bits;
-      while (rest && nv < 3) {
-        const int j = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const uint64_t s = candidate(pos + j, word_byte(v[u], j));
-        if (s == kNone || s < p) continue;  // p only grows: nothing before it can be accepted
-        const uint64_t e = R.end_from(a, s);
-        if (e == kNone) continue;
-        if (nv == 0) { s0 = s; e0 = e; }
-        else if (nv == 1) { s1 = s; e1 = e; }
-        nv++;
-      }
-      const bool crowded = nv >= 3 || (nv == 2 && rest != 0);
-      uint32_t active = __ballot_sync(0xffffffffu, nv != 0);
-      if (!__any_sync(0xffffffffu, crowded)) {
-        while (active) {
-          const int l = __ffs(active) - 1;
-          active &= active - 1;
-          const uint64_t as0 = __shfl_sync(0xffffffffu, s0, l), ae0 = __shfl_sync(0xffffffffu, e0, l);
-          const uint64_t as1 = __shfl_sync(0xffffffffu, s1, l), ae1 = __shfl_sync(0xffffffffu, e1, l);
-          accept(as0, ae0);
-          if (as1 != kNone) accept(as1, ae1);
+      const uint32_t t0 = swar_any<NB>(cc, v[u].x), t1 = swar_any<NB>(cc, v[u].y), t2 = swar_any<NB>(cc, v[u].z), t3 = swar_any<NB>(cc, v[u].w);
+      if ((t0 | t1 | t2 | t3) != 0) {  // this lane only: queue the flagged bytes (a flag above a true hit may be spurious: flush() looks again)
+        uint32_t bits = flags_to_bits(t0) | (flags_to_bits(t1) << 4) | (flags_to_bits(t2) << 8) | (flags_to_bits(t3) << 12);
+        const uint32_t rel = rel0 + u * 512;
+        if (!whole) {
+          const uint64_t pos = cb + rel;
+          bits = pos >= q_hi ? 0u : (pos + 16 > q_hi ? bits & ((1u << (uint32_t)(q_hi - pos)) - 1u) : bits);
         }
-      } else {
-        // more than two matches start inside one 16-byte piece (e.g. `HH` on HHHH...): lane by lane, in order
-        active = __ballot_sync(0xffffffffu, bits != 0);
-        while (active) {
-          const int l = __ffs(active) - 1;
-          active &= active - 1;
-          uint32_t lb = __shfl_sync(0xffffffffu, bits, l);
+        while (bits) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (cnt < kPfSlots) qpos[cnt * 32 + lane] = (uint16_t)(rel + j);
+          cnt++;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, cnt > kPfSlots)) {
+      // a lane met more of the bytes than it can queue (a haystack full of them): verify what was
+      // queued before this piece, then take this piece lane by lane, in order
+      cnt = cnt_before;
+      flush();
+#pragma unroll 1
+      for (int u = 0; u < 4; u++) {
+        const uint64_t pos = off + u * 512 + lane * 16;
+        uint32_t todo = __ballot_sync(0xffffffffu, pos < q_hi);
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
           const uint64_t lpos = __shfl_sync(0xffffffffu, pos, l);
-          while (lb) {  // uniform loop: every lane evaluates lane l's candidates (same addresses: broadcast loads)
-            const int j = __ffs(lb) - 1;
-            lb &= lb - 1;
+          for (uint32_t j = 0; j < 16 && lpos + j < q_hi; j++) {  // uniform: every lane evaluates lane l's bytes (broadcast loads)
             const uint64_t q = lpos + j;
-            const uint64_t s = candidate(q, __ldg(a.text + q));
+            const uint32_t byte = __ldg(a.text + q);
+            bool is = false;
+            for (uint32_t i = 0; i < pf.n_bytes; i++) is = is || byte == (pf.bcast[i] & 0xFFu);
+            if (!is) continue;
+            const uint64_t s = pf_candidate(a, pf, sets, q);
             if (s == kNone || s < p) continue;
-            const uint64_t e = R.end_from(a, s);
+            const uint64_t e = pf_verify(&a, &R, s);
             if (e != kNone) accept(s, e);
           }
         }
       }
+    } else if (__any_sync(0xffffffffu, cnt + 2 > kPfSlots)) {
+      flush();  // little room left: empty the queues before the next piece
     }
   }
+  flush();
   c.p = p;
   c.lm = lm;
   if (total) c.chain = true;
@@ -1010,13 +1076,15 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
   return total;
 }
 
-template <int FAST>
-__global__ void __launch_bounds__(256) literal_scan(WalkArgs a, PfArgs pf, int mode) {
+template <int FAST, int NB>
+__global__ void __launch_bounds__(256, 3) literal_scan(const __grid_constant__ WalkArgs a, const __grid_constant__ PfArgs pf, int mode) {
   const auto R = RunnerSetup<FAST>::make(a);
   __shared__ uint32_t sets[32];
+  __shared__ __align__(16) unsigned char queues[8 * kPfWarpSmem];  // blockDim.x == 256
   if (threadIdx.x < 32) sets[threadIdx.x] = pf.sets[threadIdx.x >> 3][threadIdx.x & 7];
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
+  unsigned char* wq = queues + (threadIdx.x >> 5) * kPfWarpSmem;
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   if (mode == 2) {  // sequential pass: one warp, chunk after chunk with exact entry states
@@ -1030,7 +1098,7 @@ __global__ void __launch_bounds__(256) literal_scan(WalkArgs a, PfArgs pf, int m
       if (spec) { c.p = 0; c.lm = kNone; }
       else if (lane == 0) { a.in_p[k] = c.p; a.in_lm[k] = c.lm; }
       uint64_t fc = kNone;
-      const uint64_t total = pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+      const uint64_t total = pf_walk_chunk<NB>(a, pf, sets, wq, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
       if (spec && total == 0) { c.p = a.base + k * (uint64_t)a.chunk + 1; }
       if (lane == 0) finish_chunk(a, k, c, total, fc, spec);
       c.chain = true;
@@ -1049,16 +1117,18 @@ __global__ void __launch_bounds__(256) literal_scan(WalkArgs a, PfArgs pf, int m
     if (spec) { c.p = 0; c.lm = kNone; }  // accept from the chunk's first candidate on
     uint64_t fc = kNone;
     if (mode == 3) {
-      pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.out, a.offset[k], a.cap);
+      pf_walk_chunk<NB>(a, pf, sets, wq, R, k, c, &fc, a.out, a.offset[k], a.cap);
       continue;
     }
-    const uint64_t total = pf_walk_chunk(a, pf, sets, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    const uint64_t total = pf_walk_chunk<NB>(a, pf, sets, wq, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
     if (spec && total == 0) c.p = a.base + k * (uint64_t)a.chunk + 1;  // what a speculative walk without matches reports (never used: IDENT)
     if (lane == 0) finish_chunk(a, k, c, total, fc, spec);
   }
 }
-template __global__ void literal_scan<0>(WalkArgs, PfArgs, int);
-template __global__ void literal_scan<1>(WalkArgs, PfArgs, int);
+#define RB_INSTANTIATE_LITERAL_SCAN(F, N) \
+  template __global__ void literal_scan<F, N>(const __grid_constant__ WalkArgs, const __grid_constant__ PfArgs, int);
+RB_INSTANTIATE_LITERAL_SCAN(0, 1) RB_INSTANTIATE_LITERAL_SCAN(0, 2) RB_INSTANTIATE_LITERAL_SCAN(0, 3) RB_INSTANTIATE_LITERAL_SCAN(0, 4)
+RB_INSTANTIATE_LITERAL_SCAN(1, 1) RB_INSTANTIATE_LITERAL_SCAN(1, 2) RB_INSTANTIATE_LITERAL_SCAN(1, 3) RB_INSTANTIATE_LITERAL_SCAN(1, 4)
 
 // compact_spans without the re-walk of overflowed chunks (literal_scan mode 3 does those)
 __global__ void __launch_bounds__(256) compact_staged(WalkArgs a) {

@@ -86,8 +86,8 @@ struct PfArgs {
 };
 // mode 0: every chunk (one warp per chunk, grid-stride); 1: the dirty list; 2: sequential pass from
 // a.seq_from (one warp); 3: chunks that overflowed their staging slots, straight into a.out
-template <int FAST>
-__global__ void literal_scan(WalkArgs a, PfArgs pf, int mode);
+template <int FAST, int NB>  // NB = PfArgs::n_bytes
+__global__ void literal_scan(const __grid_constant__ WalkArgs a, const __grid_constant__ PfArgs pf, int mode);
 __global__ void compact_staged(WalkArgs a);
 
 struct BatchArgs {

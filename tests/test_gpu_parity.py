@@ -496,7 +496,7 @@ def test_pipelined_host_find_all(monkeypatch):
 
 
 # ------------------------------------------- look-arounds at every kind of boundary ----
-def _run_gpu_shards(pat, text, d_text, world, exp_len, halo=256, tuning=None):
+def _run_gpu_shards(pat, text, d_text, world, exp_len, halo=256, tuning=None, options=None):
     """Byte-range shards of `text` through one GPU (one thread per shard, in-process collectives)."""
     import threading
     from regex_b200 import sharded
@@ -508,6 +508,8 @@ def _run_gpu_shards(pat, text, d_text, world, exp_len, halo=256, tuning=None):
             re_ = R.BytesRegex(pat)
             if tuning:
                 re_.set_tuning(**tuning)
+            for k, v in (options or {}).items():
+                re_.set_option(k, v)
             info = re_.pattern_info()
             geom = sharded.plan(len(text), world, rank, halo=halo)
             buf = d_text[geom.buf_lo:geom.buf_hi].clone()

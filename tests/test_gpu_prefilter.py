@@ -19,19 +19,29 @@ def _spans(a):
     return [tuple(int(v) for v in r) for r in np.asarray(a).reshape(-1, 2).tolist()]
 
 
+def _forced(r):
+    r.set_option("prefilter", 2)  # whenever the pattern qualifies structurally (automatic mode wants ONE rare byte)
+    return r
+
+
 def test_prefilter_is_chosen_for_rare_byte_patterns_only():
     text = sherlock_text()[:200000]
     for pat in ELIGIBLE:
-        r = R.BytesRegex(pat)
+        r = _forced(R.BytesRegex(pat))
         r.find_all(text)
         assert r.last_stats()["path"] == 3, pat
         r.set_option("prefilter", 0)
         r.find_all(text)
         assert r.last_stats()["path"] != 3, pat
     for pat in NOT_ELIGIBLE:
-        r = R.BytesRegex(pat)
+        r = _forced(R.BytesRegex(pat))
         r.find_all(text)
         assert r.last_stats()["path"] != 3, pat
+    # automatic mode: one byte of small estimated frequency
+    for pat, auto in ((r"Qu[a-z]+", True), (r"@\w+", True), (r"Zz+|Xx", False), (r"Holmes|Watson", False), (r"Watson", False)):
+        r = R.BytesRegex(pat)
+        assert _spans(r.find_all(text)) == O.OracleRegex(pat).find_iter(text)
+        assert (r.last_stats()["path"] == 3) == auto, pat
 
 
 @pytest.mark.parametrize("utf8", [False, True])
@@ -40,7 +50,7 @@ def test_prefilter_equals_dfa_path_and_oracle(utf8):
     cls = R.Regex if utf8 else R.BytesRegex
     for pat in ELIGIBLE:
         exp = O.OracleRegex(pat, only_utf8=utf8).find_iter(text)
-        r = cls(pat)
+        r = _forced(cls(pat))
         got = _spans(r.find_all(text))
         assert r.last_stats()["path"] == 3
         assert got == exp, (pat, got[:4], exp[:4])
@@ -49,7 +59,7 @@ def test_prefilter_equals_dfa_path_and_oracle(utf8):
         assert _spans(g.find_all(text)) == exp, pat
         for cut in (0, 1, 15, 16, 17, 511, 512, 2047, 2048, 2049, 8191, 8192, 8193, 20000):  # ragged ends, chunk edges
             assert _spans(r.find_all(text[:cut])) == O.OracleRegex(pat, only_utf8=utf8).find_iter(text[:cut]), (pat, cut)
-        for start in (1, 7, 600, 8190):
+        for start in (3, 7, 600, 8190):
             assert r.find_at(text, start) == O.OracleRegex(pat, only_utf8=utf8).find_at(text, start), (pat, start)
 
 
@@ -67,7 +77,7 @@ def test_prefilter_matches_at_every_alignment_and_chunk_edge():
                 buf[pos:pos + len(w)] = w
         text = bytes(buf)
         exp = O.OracleRegex(pat).find_iter(text)
-        r = R.BytesRegex(pat)
+        r = _forced(R.BytesRegex(pat))
         assert _spans(r.find_all(text)) == exp, pat
         assert r.last_stats()["path"] == 3
 
@@ -79,7 +89,7 @@ def test_prefilter_dense_and_overlapping_candidates():
              (r"Hx*", b"ab" + b"H" + b"x" * 40000 + b" H Hxx " + b"y" * 9000 + b"Hx"), (r"Ho+|Wo", b"Hooo Wo " * 9000 + b"H" + b"o" * 20000)]
     for pat, text in cases:
         exp = O.OracleRegex(pat).find_iter(text)
-        r = R.BytesRegex(pat)
+        r = _forced(R.BytesRegex(pat))
         got = _spans(r.find_all(text))
         assert r.last_stats()["path"] == 3, pat
         assert got == exp, (pat, got[:5], exp[:5], len(got), len(exp))
@@ -94,7 +104,7 @@ def test_prefilter_shards(world):
     d = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
     for pat in (r"Holmes|Watson", r"Sher[a-z]+|Hol[a-z]+"):
         exp = O.OracleRegex(pat).find_iter(text)
-        assert _run_gpu_shards(pat, text, d, world, len(exp), halo=4096) == exp, pat
+        assert _run_gpu_shards(pat, text, d, world, len(exp), halo=4096, options={"prefilter": 2}) == exp, pat
 
 
 def test_prefilter_large_haystack_and_pipelined_host_path():
@@ -104,7 +114,7 @@ def test_prefilter_large_haystack_and_pipelined_host_path():
     d = torch.frombuffer(bytearray(base), dtype=torch.uint8).cuda().repeat(reps)
     for pat in (r"Holmes|Watson", r"Sherlock|Holmes"):
         base_spans = O.OracleRegex(pat).find_iter(base)
-        r = R.BytesRegex(pat)
+        r = _forced(R.BytesRegex(pat))
         out = torch.empty((len(base_spans) * reps + 4096, 2), dtype=torch.int64, device="cuda")
         total = r.find_all_device(d, out)
         assert r.last_stats()["path"] == 3
@@ -119,7 +129,7 @@ def test_prefilter_large_haystack_and_pipelined_host_path():
         assert r.find_all_device(d) == total  # count-only mode
     # host haystack through the pipelined upload (pieces are shards)
     host = base * 10
-    r = R.BytesRegex(r"Holmes|Watson")
+    r = _forced(R.BytesRegex(r"Holmes|Watson"))
     got = r.find_all(host)
     one = np.array(O.OracleRegex(r"Holmes|Watson").find_iter(base + base[:64]), dtype=np.int64).reshape(-1, 2)
     g = R.BytesRegex(r"Holmes|Watson")
