@@ -132,6 +132,7 @@ void rure_b200_set_tuning(rure *re, uint32_t seg, uint32_t chunk, uint32_t warm,
 /* Launch this object's kernels on a caller-owned cudaStream_t (e.g. torch's current
  * stream) instead of its private stream; pass the stream handle as a pointer value. */
 void rure_b200_set_stream(rure *re, void *cuda_stream);
+void rure_b200_set_set_stream(rure_set *set, void *cuda_stream);
 /* Tests: route scans through the generic kernel even when the fast one applies. */
 void rure_b200_force_generic(rure *re, int yes);
 /* Walk each segment's find_iter chain inside the fast scan kernel (default on). */

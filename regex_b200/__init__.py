@@ -95,6 +95,7 @@ def _load():
         "rure_b200_set_tuning": (None, [vp, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32]),
         "rure_b200_force_generic": (None, [vp, c_int]),
         "rure_b200_set_stream": (None, [vp, vp]),
+        "rure_b200_set_set_stream": (None, [vp, vp]),
         "rure_b200_set_fuse": (None, [vp, c_int]),
         "rure_b200_set_tensor_tma": (None, [vp, c_int]),
         "rure_b200_dfa_export": (c_bool, [vp, c_int, POINTER(c_uint32), vp, vp, vp, vp]),
@@ -445,6 +446,10 @@ class _SetBase:
         if not _lib.rure_b200_set_matches_device(self._h, d_text.data_ptr(), d_text.numel(), start, out):
             raise Error(_last_error())
         return list(out)
+
+    def set_stream(self, cuda_stream):
+        """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _lib.rure_b200_set_set_stream(self._h, cuda_stream)
 
     def matches_device(self, d_text, start=0):
         """RegexSet::matches over a device-resident haystack: indices of the matching patterns."""

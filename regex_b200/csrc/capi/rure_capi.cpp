@@ -352,6 +352,7 @@ void rure_b200_set_tuning(rure* re, uint32_t seg, uint32_t chunk, uint32_t warm,
   if (blocks_per_sm) t.blocks_per_sm = blocks_per_sm;
 }
 void rure_b200_set_stream(rure* re, void* cuda_stream) { re->re->set_stream(cuda_stream); }
+void rure_b200_set_set_stream(rure_set* set, void* cuda_stream) { set->re->set_stream(cuda_stream); }
 void rure_b200_force_generic(rure* re, int yes) { re->re->tuning.force_generic = yes != 0; }
 void rure_b200_set_fuse(rure* re, int yes) { re->re->tuning.fuse = yes != 0; }
 void rure_b200_set_tensor_tma(rure* re, int yes) { re->re->tuning.tensor_tma = yes != 0; }
