@@ -360,6 +360,21 @@ def run_ours(args):
                             "what": "GPU spans == oracle find_iter spans on the first and last %d MiB of every shard (both sides of every shard "
                                     "boundary)%s, windows cut at line starts" % (win >> 20, " and 64 random 16 MiB windows" if len(windows) > 2 else "")}
 
+    # ---- N > 1: all spans in one buffer on rank 0 (global positions), checked and timed ----
+    if world > 1:
+        counts = sharded.find_all_sharded.last_counts
+        barrier()
+        t0 = time.perf_counter()
+        allspans = sharded.gather_spans(engine.spans, n_local, counts, geom.buf_lo, rank, world)
+        barrier()
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            assert allspans.shape[0] == grand_total
+            assert bool((allspans[1:, 0] >= allspans[:-1, 1]).all()) and bool((allspans[:, 0] < allspans[:, 1]).all())
+            result["span_gather"] = {"ms": round(gather_ms, 2), "spans": int(grand_total), "bytes": int(grand_total) * 16,
+                                     "note": "NCCL point-to-point gather of every rank's spans into one ordered buffer on rank 0 (outside the timed steps)"}
+        del allspans
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     host = None
     if not args.no_e2e or (rank == 0 and not args.no_cpu):

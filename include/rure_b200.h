@@ -105,6 +105,28 @@ typedef struct rure_b200_shard {
 bool rure_b200_find_all_shard_device(rure *re, const uint8_t *d_buffer, size_t n_buffer,
                                      rure_b200_shard *io, rure_match *d_out, size_t cap);
 
+/* is_match / shortest_match / RegexSet::matches over one shard (positions [own_lo, own_hi) of the
+ * buffer; the last shard also takes the end-of-text step).  The forward automaton's state flows
+ * left to right: entry_state is the left neighbour's exact exit_state, or RURE_B200_NO_STATE to
+ * guess it from the left context; regex_b200/sharded.py (forward_sharded) compares entry_used
+ * with the neighbour's exit_state and searches again on a mismatch.  Results: first_end = end of
+ * the first match that ends in this shard (buffer-relative; shortest_match = min over ranks),
+ * masks = patterns that match inside it (RegexSet::matches = OR over ranks; 4 words = 256 patterns). */
+typedef struct rure_b200_fwd_shard {
+  /* in */
+  uint64_t own_lo, own_hi;
+  int32_t is_first, is_last;
+  uint32_t entry_state;
+  /* out */
+  uint32_t entry_used, exit_state, found;
+  uint64_t first_end;
+  uint64_t masks[4];
+} rure_b200_fwd_shard;
+bool rure_b200_shortest_match_shard_device(rure *re, const uint8_t *d_buffer, size_t n_buffer,
+                                           rure_b200_fwd_shard *io);
+bool rure_b200_set_matches_shard_device(rure_set *set, const uint8_t *d_buffer, size_t n_buffer,
+                                        rure_b200_fwd_shard *io);
+
 /* ---- diagnostics ----------------------------------------------------------- */
 const char *rure_b200_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */

@@ -41,6 +41,20 @@ class _Shard(ctypes.Structure):  # include/rure_b200.h: rure_b200_shard
                 ("n_matches", c_uint64), ("halo_overflow", c_uint32), ("chain_clamped", c_uint32)]
 
 
+class _FwdShard(ctypes.Structure):  # include/rure_b200.h: rure_b200_fwd_shard
+    _fields_ = [("own_lo", c_uint64), ("own_hi", c_uint64), ("is_first", ctypes.c_int32), ("is_last", ctypes.c_int32),
+                ("entry_state", c_uint32), ("entry_used", c_uint32), ("exit_state", c_uint32), ("found", c_uint32),
+                ("first_end", c_uint64), ("masks", c_uint64 * 4)]
+
+
+def _forward_shard(fn, handle, d_buffer, io):
+    sh = _FwdShard(own_lo=io["own_lo"], own_hi=io["own_hi"], is_first=int(io["is_first"]), is_last=int(io["is_last"]),
+                   entry_state=io["entry_state"])
+    if not fn(handle, d_buffer.data_ptr(), d_buffer.numel(), byref(sh)):
+        raise Error(_last_error())
+    return dict(entry_used=sh.entry_used, exit_state=sh.exit_state, found=bool(sh.found), first_end=sh.first_end, masks=list(sh.masks))
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -81,6 +95,8 @@ def _load():
         "rure_b200_find_all_device": (c_bool, [vp, vp, sz, sz, vp, sz, POINTER(sz)]),
         "rure_b200_find_all_shard_device": (c_bool, [vp, vp, sz, POINTER(_Shard), vp, sz]),
         "rure_b200_shortest_match_device": (c_bool, [vp, vp, sz, sz, POINTER(c_bool), POINTER(sz)]),
+        "rure_b200_shortest_match_shard_device": (c_bool, [vp, vp, sz, POINTER(_FwdShard)]),
+        "rure_b200_set_matches_shard_device": (c_bool, [vp, vp, sz, POINTER(_FwdShard)]),
         "rure_b200_set_matches_device": (c_bool, [vp, vp, sz, sz, POINTER(c_uint64)]),
         "rure_b200_is_match_batch_device": (c_bool, [vp, vp, vp, sz, vp]),
         "rure_b200_find_batch_device": (c_bool, [vp, vp, vp, sz, vp, vp]),
@@ -300,6 +316,10 @@ class _Compiled:
             raise Error(_last_error())
         return dict(rev_guess=sh.rev_guess, rev_left=sh.rev_left, exit_p=sh.exit_p, exit_lm=sh.exit_lm, n_matches=sh.n_matches)
 
+    def forward_shard_device(self, d_buffer, io):
+        """is_match / shortest_match over one shard (regex_b200/sharded.py: forward_sharded)."""
+        return _forward_shard(_lib.rure_b200_shortest_match_shard_device, self._h, d_buffer, io)
+
     def shortest_match_device(self, d_text, start=0):
         found, end = c_bool(), c_size_t()
         if not _lib.rure_b200_shortest_match_device(self._h, d_text.data_ptr(), d_text.numel(), start, byref(found), byref(end)):
@@ -450,6 +470,10 @@ class _SetBase:
     def set_stream(self, cuda_stream):
         """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         _lib.rure_b200_set_set_stream(self._h, cuda_stream)
+
+    def forward_shard_device(self, d_buffer, io):
+        """RegexSet::matches over one shard (regex_b200/sharded.py: forward_sharded)."""
+        return _forward_shard(_lib.rure_b200_set_matches_shard_device, self._h, d_buffer, io)
 
     def matches_device(self, d_text, start=0):
         """RegexSet::matches over a device-resident haystack: indices of the matching patterns."""

@@ -311,6 +311,26 @@ bool rure_b200_find_all_shard_device(rure* re, const uint8_t* d_buffer, size_t n
   return r;
 }
 
+static bool forward_shard(Regex* r, const uint8_t* d_buffer, size_t n_buffer, rure_b200_fwd_shard* io, bool want_masks) {
+  bool found = false;
+  uint64_t first = ~0ull;
+  uint32_t used = io->entry_state, exit_state = io->entry_state;
+  for (auto& m : io->masks) m = 0;
+  bool r_ok = ok(r, r->forward_shard_device(d_buffer, n_buffer, io->own_lo, io->own_hi, io->is_first != 0, io->is_last != 0, io->entry_state,
+                                           want_masks, &found, &first, io->masks, &used, &exit_state));
+  io->found = found ? 1 : 0;
+  io->first_end = first;
+  io->entry_used = used;
+  io->exit_state = exit_state;
+  return r_ok;
+}
+bool rure_b200_shortest_match_shard_device(rure* re, const uint8_t* d_buffer, size_t n_buffer, rure_b200_fwd_shard* io) {
+  return forward_shard(re->re, d_buffer, n_buffer, io, false);
+}
+bool rure_b200_set_matches_shard_device(rure_set* set, const uint8_t* d_buffer, size_t n_buffer, rure_b200_fwd_shard* io) {
+  return forward_shard(set->re, d_buffer, n_buffer, io, true);
+}
+
 const char* rure_b200_last_error(void) { return g_last_error.c_str(); }
 uint64_t rure_b200_kernel_launches(void) { return rbgpu::kernel_launches(); }
 void rure_b200_last_stats(rure* re, double* out8) {

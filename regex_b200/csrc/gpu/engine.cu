@@ -978,17 +978,23 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
 //     of the product automaton of all of them.  That automaton knows nothing about the bytes
 //     already passed, so it scans from `start` again; narrowing happens after the first two
 //     waves only, which bounds the repeated work to 1/8 of the haystack.
-int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host) {
+// end: positions [start, end) are searched (n + 1 = to the end of the text, the default); entry:
+// exact automaton state at `start` (a shard, kNoEntry = a fresh search); *exit_state: the exact
+// state after the last position (what the right-hand shard must be entered with).
+int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host, uint64_t end,
+                          uint32_t entry, uint32_t* exit_out) {
   result_host[0] = kNone;
   for (uint32_t w = 0; w < kMaxMaskWords; w++) result_host[1 + w] = 0;
   const uint32_t n_pat = (uint32_t)patterns_.size();
   uint64_t wave = tuning.wave0 ? (tuning.wave0 + 4095) / 4096 * 4096 : 0;
   uint64_t lo = start;
-  uint32_t entry = kNoEntry;
+  end = std::min(end, n + 1);
+  const bool whole = end == n + 1 && entry == kNoEntry;  // narrowing restarts the search at `start` with a fresh automaton
+  if (exit_out) *exit_out = entry == kNoEntry ? kNoState : entry;
   stats.scan_redo_rounds = stats.scan_redo_segments = stats.map_passes = stats.waves = 0;
   for (uint32_t wi = 0;; wi++) {
-    uint64_t limit = n + 1;
-    if (wave && n + 1 - lo > 2 * wave) limit = (lo + wave) / 4096 * 4096;
+    uint64_t limit = end;
+    if (wave && end - lo > 2 * wave) limit = (lo + wave) / 4096 * 4096;
     uint64_t r[1 + kMaxMaskWords];
     uint32_t exit_state = 0;
     if (int rc = forward_range(d_text, n, lo, limit, entry, want_masks, r, &exit_state)) return rc;
@@ -999,7 +1005,8 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
       fresh = fresh || (r[1 + w] & ~result_host[1 + w]);
       result_host[1 + w] |= r[1 + w];
     }
-    if (limit == n + 1) break;
+    if (exit_out) *exit_out = exit_state;
+    if (limit == end) break;
     if (!want_masks && result_host[0] != kNone) break;
     if (exit_state == 0) break;  // dead state: an anchored search that can no longer match
     if (want_masks) {
@@ -1007,7 +1014,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
       for (uint32_t i = 0; i < n_pat; i++)
         if (!((result_host[1 + i / 64] >> (i % 64)) & 1)) open.push_back(i);
       if (open.empty()) break;
-      if (tuning.narrow_sets && wi < 2 && fresh && open.size() < n_pat) {
+      if (tuning.narrow_sets && whole && wi < 2 && fresh && open.size() < n_pat) {
         Regex* sub = nullptr;
         if (int rc = subset(open, &sub)) return rc;
         uint64_t sr[1 + kMaxMaskWords];
@@ -1067,6 +1074,50 @@ int Regex::set_matches_device(const uint8_t* d_text, uint64_t n, uint64_t start,
   uint64_t res[1 + kMaxMaskWords];
   if (int rc = forward_reduce(d_text, n, start, true, res)) return rc;
   for (uint32_t w = 0; w < mw; w++) { masks[w] = res[1 + w]; if (res[1 + w]) *any = true; }
+  return 0;
+}
+
+// One byte-range shard of a forward search (is_match / shortest_match / RegexSet::matches over a
+// sharded haystack).  The automaton state flows left to right: a shard that is not
+// told its entry state guesses it by running the automaton over the left context in front of
+// own_lo (host side, <= 256 bytes) from the start state that belongs to that position; the
+// ranks compare each guess with the left neighbour's exact exit state and search again when
+// they differ (regex_b200/sharded.py: forward_sharded).
+int Regex::forward_shard_device(const uint8_t* d_text, uint64_t n, uint64_t own_lo, uint64_t own_hi, bool is_first, bool is_last, uint32_t entry,
+                                bool want_masks, bool* found, uint64_t* first_end, uint64_t* masks, uint32_t* entry_used,
+                                uint32_t* exit_state) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *found = false;
+  *first_end = kNone;
+  const uint32_t mw = (uint32_t)std::max<size_t>(1, (patterns_.size() + 63) / 64);
+  for (uint32_t w = 0; w < mw; w++) masks[w] = 0;
+  *entry_used = *exit_state = entry;
+  if (patterns_.empty()) return 0;
+  if (own_lo > own_hi || own_hi > n) return fail("bad shard geometry");
+  DeviceDfa* fwd;
+  if (int rc = ensure(kFwdUnanchoredAll, &fwd)) return rc;
+  if (entry == kNoEntry && own_lo > 0) {
+    rb::Error err;
+    const rb::Dfa* h = host_dfa(kFwdUnanchoredAll, &err);
+    if (!h) return fail(err.msg);
+    // run the automaton over the last <= 255 bytes in front of own_lo; its start state takes the
+    // flags of a position inside a long text (dfa.rs:1415-1434), so one more byte is looked at
+    uint64_t from = own_lo > 255 ? own_lo - 255 : 0;
+    if (from == 0 && !is_first) from = 1;            // buffer byte 0 is not the start of the haystack
+    const uint64_t copy_lo = from ? from - 1 : 0;
+    const uint64_t copy_n = std::min<uint64_t>(n, own_lo + 1) - copy_lo;
+    std::vector<uint8_t> left(copy_n + 1, 0);
+    RB_CUDA(d2h(left.data(), d_text + copy_lo, copy_n));
+    uint32_t st = h->start[rb::start_flag_index_forward(left.data(), copy_n, from - copy_lo) & 127];
+    for (uint64_t i = from; i < own_lo; i++) st = h->next((uint16_t)st, left[i - copy_lo]);
+    entry = st;
+  }
+  *entry_used = entry;
+  uint64_t res[1 + kMaxMaskWords];
+  const uint64_t end = is_last ? n + 1 : own_hi;
+  if (int rc = forward_reduce(d_text, n, own_lo, want_masks, res, end, entry, exit_state)) return rc;
+  if (res[0] != kNone) { *found = true; *first_end = res[0]; }
+  for (uint32_t w = 0; w < mw; w++) { masks[w] = res[1 + w]; if (want_masks && res[1 + w]) *found = true; }
   return 0;
 }
 

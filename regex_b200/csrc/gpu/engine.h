@@ -102,6 +102,10 @@ class Regex {
   // RegexSet::matches (re_set.rs:184-213): masks = ceil(n_patterns/64) words (host).
   int set_matches_device(const uint8_t* d_text, uint64_t n, uint64_t start, bool* any, uint64_t* masks);
 
+  // one shard of a forward search over a sharded haystack (see engine.cu)
+  int forward_shard_device(const uint8_t* d_text, uint64_t n, uint64_t own_lo, uint64_t own_hi, bool is_first, bool is_last, uint32_t entry,
+                           bool want_masks, bool* found, uint64_t* first_end, uint64_t* masks, uint32_t* entry_used, uint32_t* exit_state);
+
   // ---- batched records, device-resident text + offsets[n_rec+1] --------------
   int is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits);
   int find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_spans, uint32_t* d_bits);
@@ -140,7 +144,8 @@ class Regex {
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
   bool plan_prefilter();  // fills pf_words_ (launch.h PfArgs) when every match has one of <= 4 bytes at a fixed offset
-  int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host);
+  int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host, uint64_t end = ~0ull,
+                     uint32_t entry = 0xFFFFFFFFu, uint32_t* exit_out = nullptr);
   int forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint64_t limit, uint32_t entry, bool want_masks,
                     uint64_t* result_host, uint32_t* exit_state);
   int subset(const std::vector<uint32_t>& members, Regex** out);

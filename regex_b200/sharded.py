@@ -219,6 +219,7 @@ def find_all_sharded(engine, geom, comm, can_match_empty, has_looks, start=0):
             continue
         # ---- 3. counts -> global offsets ------------------------------------------------
         counts = [v[4] for v in allv]
+        find_all_sharded.last_counts = counts  # per-rank counts (gather_spans wants them)
         return counts[me], sum(counts[:me]), sum(counts), rounds
 
 
@@ -238,3 +239,75 @@ class GpuShardEngine:
     def run(self, io):
         self.last = self.regex.find_all_shard_device(self.d_buffer, io, self.spans)
         return self.last
+
+
+def forward_sharded(run, geom, comm):
+    """is_match / shortest_match / RegexSet::matches over a byte-range sharded haystack.
+
+    `run(io) -> dict` searches this rank's shard (Regex.forward_shard_device /
+    RegexSet.forward_shard_device, or the CPU stand-in of the tests) with
+    io = {own_lo, own_hi, is_first, is_last, entry_state}.  The forward automaton's state flows
+    left to right: every rank first guesses its entry state from its left context; ONE all_gather
+    per round carries (entry used, exit state, found, first match end, four mask words); a rank
+    whose guess differs from its left neighbour's exit state searches again with the exact
+    state.  Returns (first_end or None, mask words OR-ed over the ranks, rounds): shortest_match
+    is the smallest first_end, is_match is `first_end is not None`, RegexSet::matches is the
+    mask (all-gather + OR; NCCL has no bitwise-OR reduction)."""
+    world, me = geom.world, geom.rank
+    owns_bytes = not (geom.a >= geom.b and not geom.is_first)
+    io = dict(own_lo=geom.own_lo, own_hi=geom.own_hi, is_first=geom.is_first, is_last=geom.is_last, entry_state=NO_STATE)
+    res = run(io) if owns_bytes else None
+    rounds = 0
+    while True:
+        if res is None:
+            mine = [NO_STATE, NO_STATE, 0, NONE, 0, 0, 0, 0, 0]
+        else:
+            fe = res["first_end"] + geom.buf_lo if res["found"] and res["first_end"] != NONE else NONE
+            mine = [res["entry_used"], res["exit_state"], int(res["found"]), fe] + list(res["masks"]) + [1]
+        allv = comm.all_gather(mine)
+        redo = {}
+        prev_exit = None  # exact exit state of the nearest rank to the left that searched
+        for g in range(world):
+            if not allv[g][8]:
+                continue
+            if prev_exit is not None and allv[g][0] != prev_exit:
+                redo[g] = prev_exit
+                break  # everything to the right depends on this rank's new exit state
+            prev_exit = allv[g][1]
+        if redo:
+            if me in redo:
+                io["entry_state"] = redo[me]
+                res = run(io)
+            rounds += 1
+            continue
+        ends = [v[3] for v in allv if v[8] and v[2] and v[3] != NONE]
+        masks = [0, 0, 0, 0]
+        for v in allv:
+            if v[8]:
+                for w in range(4):
+                    masks[w] |= v[4 + w]
+        return (min(ends) if ends else None), masks, rounds
+
+
+def gather_spans(spans_local, n_local, counts, buf_lo, rank, world, dst_rank=0):
+    """All ranks' spans in one buffer on `dst_rank`, in haystack order with global positions
+    ("spans gathered to GPU 0 ... only if the caller wants a single buffer").
+    spans_local: (cap, 2) int64 CUDA tensor of buffer-relative spans; counts: per-rank match
+    counts from find_all_sharded.  NCCL point-to-point; returns the (total, 2) tensor on dst_rank,
+    None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    mine = (spans_local[:n_local] + buf_lo).contiguous()
+    if world == 1:
+        return mine
+    if rank == dst_rank:
+        out = torch.empty((sum(counts), 2), dtype=torch.int64, device=spans_local.device)
+        offs = [sum(counts[:g]) for g in range(world)]
+        out[offs[rank]:offs[rank] + counts[rank]] = mine
+        reqs = [dist.irecv(out[offs[g]:offs[g] + counts[g]], src=g) for g in range(world) if g != dst_rank and counts[g]]
+        for r in reqs:
+            r.wait()
+        return out
+    if n_local:
+        dist.send(mine, dst=dst_rank)
+    return None

@@ -112,3 +112,41 @@ class SimShardEngine:
             if st == 0:
                 return last
             q += 1
+
+
+class SimFwdShard:
+    """CPU stand-in for rure_b200_shortest_match_shard_device / rure_b200_set_matches_shard_device:
+    the forward all-match automaton over the shard's own bytes, entry state guessed from the left
+    context unless given (same rule as Regex::forward_shard_device)."""
+
+    def __init__(self, regex, buf, weak_guess=False):
+        self.sim = Sim(regex)
+        self.buf = buf
+        self.weak_guess = weak_guess  # guess from a single context byte: wrong more often (tests)
+
+    def run(self, io):
+        s, t, n = self.sim, self.buf, len(self.buf)
+        d = s.d(R.DFA_FWD_UNANCHORED_ALL)
+        lo, hi = io["own_lo"], io["own_hi"]
+        st = io["entry_state"]
+        if st == NO_STATE:
+            if lo == 0:
+                st = int(d["start"][flags_forward(t, 0)])
+            else:
+                frm = max(lo - (1 if self.weak_guess else 255), 0)
+                if frm == 0 and not io["is_first"]:
+                    frm = 1
+                st = int(d["start"][flags_forward(t, frm)]) if frm > 0 or io["is_first"] else None
+                for i in range(frm, lo):
+                    st = s.step(d, st, t[i])
+        used = st
+        first, masks = None, [0, 0, 0, 0]
+        end = n + 1 if io["is_last"] else hi
+        for q in range(lo, end):
+            st = s.step(d, st, t[q]) if q < n else s.eof(d, st)
+            if st >= d["match_lo"]:
+                if first is None:
+                    first = q
+                for w in range(d["masks"].shape[1]):
+                    masks[w] |= int(d["masks"][st, w])
+        return dict(entry_used=used, exit_state=st, found=first is not None, first_end=first if first is not None else NONE, masks=masks)

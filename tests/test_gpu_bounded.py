@@ -145,3 +145,48 @@ def test_regex_set_narrowing_equals_the_product_automaton():
     s = R.BytesRegexSet([r"\w+", r"Holmes", r"\s"])
     s.set_option("wave0", 1 << 20)
     assert s.matches_device(d) == [0, 1, 2] and s.last_stats()["waves"] == 1
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_forward_searches_on_the_gpu(world):
+    """is_match / shortest_match / RegexSet::matches over byte-range shards driven through one GPU
+    (one thread per shard, in-process collectives): first-end min and mask OR must equal the
+    whole-haystack answers; sticky automata need the exact-state exchange."""
+    import threading
+    import torch
+    from regex_b200 import sharded
+    text = tiled_corpus(3 << 20) + b" NEEDLE " + tiled_corpus(1 << 20, seed=9)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+
+    def run(make, fn_expected):
+        comm = sharded.ThreadComm(world)
+        out, errs = [None] * world, []
+
+        def work(rank):
+            try:
+                re_ = make()
+                re_.set_option("wave0", 1 << 18)
+                geom = sharded.plan(len(text), world, rank, halo=256)
+                buf = d_text[geom.buf_lo:geom.buf_hi].clone()
+                out[rank] = sharded.forward_sharded(lambda io: re_.forward_shard_device(buf, io), geom, comm.view(rank))
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+                comm._barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+            assert not t.is_alive()
+        assert not errs, errs
+        assert all(o[:2] == out[0][:2] for o in out)
+        return out[0]
+
+    for pat in (r"NEEDLE", r"Holmes", r"qqqqqqqq", r"(?s)Sherlock.*NEEDLE", r"(?m)^NEEDLE", r"E \w+\s"):
+        first, _, _ = run(lambda: R.BytesRegex(pat), None)
+        assert first == O.OracleRegex(pat).shortest_match_at(text), pat
+    pats = [r"\w+", r"NEEDLE", r"qqqqqq", r"(?s)NEEDLE.*Watson", r"(?s)Watson.*NEEDLE", r"\d{7}", r"(?i)needle "]
+    _, masks, _ = run(lambda: R.BytesRegexSet(pats), None)
+    exp = [i for i, p in enumerate(pats) if pyre.search(p.encode(), text) is not None]
+    assert [i for i in range(len(pats)) if (masks[0] >> i) & 1] == exp

@@ -22,6 +22,9 @@ CASES = [
 ]
 
 
+FWD_CASES = [r"Holmes", r"(?s)the.*Watson", r"zzzz", r"(?m)^\w+$", [r"\w+", r"Holmes", r"zq", r"(?s)a.*z"]]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -55,8 +58,17 @@ def _worker(rank, world, port, text, q):
                 assert off == len(merged)
                 merged += sp
             results.append((pat, merged, total, max(g[2] for g in gathered)))
+    # forward searches over the same collectives: shortest_match (first-end min) and RegexSet::matches (mask OR)
+    from shard_sim import SimFwdShard
+    fwd = []
+    geom = sharded.plan(len(text), world, rank, halo=512, left_ctx=256)
+    for pat in FWD_CASES:
+        re_ = R.BytesRegexSet(pat) if isinstance(pat, list) else R.BytesRegex(pat)
+        eng = SimFwdShard(re_, text[geom.buf_lo:geom.buf_hi], weak_guess=True)
+        first, masks, rounds = sharded.forward_sharded(eng.run, geom, comm)
+        fwd.append((first, masks[0], rounds))
     if rank == 0:
-        q.put(results)
+        q.put((results, fwd))
     dist.destroy_process_group()
 
 
@@ -69,7 +81,7 @@ def test_sharded_protocol_matches_oracle(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, text, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = q.get(timeout=240)
+    results, fwd = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -81,6 +93,11 @@ def test_sharded_protocol_matches_oracle(world):
         assert total == len(exp)
         saw_fixup = saw_fixup or rounds > 0
     assert saw_fixup, "no case exercised a boundary fix-up; the test lost its teeth"
+    for pat, (first, mask, _) in zip(FWD_CASES, fwd):
+        if isinstance(pat, list):
+            assert [i for i in range(len(pat)) if (mask >> i) & 1] == list(O.OracleRegex(pat).set_matches(text)), pat
+        else:
+            assert first == O.OracleRegex(pat).shortest_match_at(text), pat
 
 
 def test_plan_covers_haystack_exactly():
@@ -213,3 +230,75 @@ def test_sharded_protocol_slice_rule_at_a_speculative_boundary():
     for seed in range(40):
         text = xorshift_bytes(seed, 948, b"abc \n")
         assert _run_threads(pat, text, 3) == O.OracleRegex(pat).find_iter(text), seed
+
+
+def _run_forward_threads(make_regex, text, world, weak=True):
+    import sys
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_sim import SimFwdShard
+    comm = sharded.ThreadComm(world)
+    out, errs = [None] * world, []
+
+    def work(rank):
+        try:
+            geom = sharded.plan(len(text), world, rank, halo=256)
+            eng = SimFwdShard(make_regex(), text[geom.buf_lo:geom.buf_hi], weak_guess=weak)
+            out[rank] = sharded.forward_sharded(eng.run, geom, comm.view(rank))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            comm._barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+        assert not th.is_alive()
+    if errs:
+        real = [e for e in errs if "BrokenBarrier" not in type(e).__name__]
+        raise real[0] if real else errs[0]
+    assert all(o[:2] == out[0][:2] for o in out)  # every rank reaches the same answer
+    return out[0]
+
+
+def test_sharded_shortest_match_and_set_matches():
+    """is_match / shortest_match / RegexSet::matches over 2-4 shards (mask all-gather + OR, first-end
+    min) against the oracle, with weak entry-state guesses so that the exact-state
+    exchange is exercised."""
+    import numpy as np
+    from helpers import xorshift_bytes
+    from test_fuzz_tables_vs_oracle import _pattern
+    rng = np.random.Generator(np.random.PCG64(0xF0D))
+    base = sherlock_text()[4000:7000]
+    fixed = [(r"(?s)wat.*son", base), (r"Holmes", base), (r"zzzz", base), (r"(?m)^The$", base), (r"\d{4}", base),
+             (r"(?-u:\b)s\w+e(?-u:\b)", base), (r"a$", b"x" * 700 + b"a"), (r"^x", b"x" * 600), (r"", b"q" * 600)]
+    cases = saw_redo = 0
+    for it in range(140):
+        if it < len(fixed):
+            pat, text = fixed[it]
+        else:
+            pat = _pattern(rng)
+            text = xorshift_bytes(int(rng.integers(0, 1000)), int(rng.integers(300, 1200)), b"abc \n" if rng.random() < 0.7 else b"ab1 _\n\xc3\xa9")
+        try:
+            R.BytesRegex(pat)
+        except R.Error:
+            continue
+        world = int(rng.integers(2, 5))
+        first, _, rounds = _run_forward_threads(lambda: R.BytesRegex(pat), text, world)
+        assert first == O.OracleRegex(pat).shortest_match_at(text), (pat, world)
+        saw_redo += rounds > 0
+        cases += 1
+    for it in range(40):
+        pats = [_pattern(rng) for _ in range(int(rng.integers(2, 6)))] + ["Holmes", "(?s)a.*b"]
+        try:
+            R.BytesRegexSet(pats)
+        except R.Error:
+            continue
+        text = xorshift_bytes(it, int(rng.integers(300, 1200)), b"abc \n") + (b"Holmes" if it % 2 else b"")
+        _, masks, rounds = _run_forward_threads(lambda: R.BytesRegexSet(pats), text, int(rng.integers(2, 5)))
+        got = [i for i in range(len(pats)) if (masks[i // 64] >> (i % 64)) & 1]
+        assert got == list(O.OracleRegex(pats).set_matches(text)), pats
+        saw_redo += rounds > 0
+        cases += 1
+    assert cases > 120 and saw_redo > 5, (cases, saw_redo)
