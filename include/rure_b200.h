@@ -37,6 +37,18 @@ rure_set *rure_b200_compile_set_str(const uint8_t **patterns, const size_t *patt
                                     size_t patterns_count, uint32_t flags, rure_options *options,
                                     rure_error *error);
 
+/* ---- the scalar searches of rure.h with an error path ----------------------
+ * rure_is_match / rure_shortest_match / rure_find / rure_set_is_match cannot report a run-time
+ * failure (the reference's never fail) and abort when the GPU search cannot run; these return
+ * false then and set rure_b200_last_error().  Results go to *matched / *found / *end / *match. */
+bool rure_b200_is_match(rure *re, const uint8_t *haystack, size_t length, size_t start, bool *matched);
+bool rure_b200_shortest_match(rure *re, const uint8_t *haystack, size_t length, size_t start,
+                              bool *found, size_t *end);
+bool rure_b200_find(rure *re, const uint8_t *haystack, size_t length, size_t start, bool *found,
+                    rure_match *match);
+bool rure_b200_set_is_match(rure_set *set, const uint8_t *haystack, size_t length, size_t start,
+                            bool *matched);
+
 /* ---- single haystack ------------------------------------------------------ */
 /* Host haystack.  Large haystacks (>= 128 MiB) are uploaded in 64 MiB pieces and each piece
  * is searched while later pieces are still in flight, spans travelling back meanwhile; the

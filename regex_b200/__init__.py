@@ -86,6 +86,10 @@ def _load():
         "rure_error_new": (vp, []),
         "rure_error_free": (None, [vp]),
         "rure_error_message": (c_char_p, [vp]),
+        "rure_b200_is_match": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool)]),
+        "rure_b200_shortest_match": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool), POINTER(sz)]),
+        "rure_b200_find": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool), POINTER(_Match)]),
+        "rure_b200_set_is_match": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool)]),
         "rure_b200_find_all": (c_bool, [vp, u8p, sz, vp, sz, POINTER(sz)]),
         "rure_b200_count_all": (c_bool, [vp, u8p, sz, POINTER(sz)]),
         "rure_b200_set_matches_mask": (c_bool, [vp, u8p, sz, sz, POINTER(c_uint64)]),
@@ -229,23 +233,30 @@ class _Compiled:
 
     def is_match_at(self, text, start):
         p, n, keep = _buf(text)
-        return bool(_lib.rure_is_match(self._h, p, n, start))
+        out = c_bool()
+        if not _lib.rure_b200_is_match(self._h, p, n, start, byref(out)):  # the error-reporting twin of rure_is_match
+            raise Error(_last_error())
+        return bool(out.value)
 
     def shortest_match(self, text):
         return self.shortest_match_at(text, 0)
 
     def shortest_match_at(self, text, start):
         p, n, keep = _buf(text)
-        end = c_size_t()
-        return end.value if _lib.rure_shortest_match(self._h, p, n, start, byref(end)) else None
+        end, found = c_size_t(), c_bool()
+        if not _lib.rure_b200_shortest_match(self._h, p, n, start, byref(found), byref(end)):
+            raise Error(_last_error())
+        return end.value if found.value else None
 
     def find(self, text):
         return self.find_at(text, 0)
 
     def find_at(self, text, start):
         p, n, keep = _buf(text)
-        m = _Match()
-        return (m.start, m.end) if _lib.rure_find(self._h, p, n, start, byref(m)) else None
+        m, found = _Match(), c_bool()
+        if not _lib.rure_b200_find(self._h, p, n, start, byref(found), byref(m)):
+            raise Error(_last_error())
+        return (m.start, m.end) if found.value else None
 
     def find_iter(self, text):
         """All non-overlapping leftmost-first matches as a list of (start, end)."""
@@ -435,14 +446,16 @@ class _SetBase:
 
     def is_match(self, text, start=0):
         p, n, keep = _buf(text)
-        return bool(_lib.rure_set_is_match(self._h, p, n, start))
+        out = c_bool()
+        if not _lib.rure_b200_set_is_match(self._h, p, n, start, byref(out)):
+            raise Error(_last_error())
+        return bool(out.value)
 
     def matches(self, text, start=0):
         """Indices of the patterns that match somewhere in text (re_set.rs:184-191)."""
         p, n, keep = _buf(text)
-        out = (c_bool * max(1, len(self)))()
-        _lib.rure_set_matches(self._h, p, n, start, out)
-        return [i for i in range(len(self)) if out[i]]
+        words = self.matches_mask(text, start)  # rure_b200_set_matches_mask reports failures; rure_set_matches aborts
+        return [i for i in range(len(self)) if (words[i // 64] >> (i % 64)) & 1]
 
     def matches_mask(self, text, start=0):
         p, n, keep = _buf(text)

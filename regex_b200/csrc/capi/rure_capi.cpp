@@ -246,6 +246,30 @@ rure_error* rure_error_new(void) { return new rure_error(); }
 void rure_error_free(rure_error* e) { delete e; }
 const char* rure_error_message(rure_error* e) { return e->msg.c_str(); }
 
+// ---------------------------------------- scalar searches that report failures --
+// The reference's scalar entry points cannot fail at run time, so rure_is_match & co abort when
+// the GPU search cannot run (no device, out of memory).  Hosts that prefer an error code use these.
+bool rure_b200_is_match(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* matched) {
+  uint64_t end = 0;
+  return ok(re->re, re->re->shortest_match_host(haystack, length, start, matched, &end));
+}
+bool rure_b200_shortest_match(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, size_t* end) {
+  uint64_t e = 0;
+  const bool r = ok(re->re, re->re->shortest_match_host(haystack, length, start, found, &e));
+  if (r && *found && end) *end = e;
+  return r;
+}
+bool rure_b200_find(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, rure_match* match) {
+  uint64_t s = 0, e = 0;
+  const bool r = ok(re->re, re->re->find_at_host(haystack, length, start, found, &s, &e));
+  if (r && *found && match) { match->start = s; match->end = e; }
+  return r;
+}
+bool rure_b200_set_is_match(rure_set* set, const uint8_t* haystack, size_t length, size_t start, bool* matched) {
+  uint64_t end = 0;
+  return ok(set->re, set->re->shortest_match_host(haystack, length, start, matched, &end));
+}
+
 // ------------------------------------------------------------ bulk extension --
 bool rure_b200_find_all(rure* re, const uint8_t* haystack, size_t length, rure_match* out, size_t cap, size_t* n_total) {
   uint64_t total = 0;

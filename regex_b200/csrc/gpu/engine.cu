@@ -997,6 +997,13 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
     if (wave && end - lo > 2 * wave) limit = (lo + wave) / 4096 * 4096;
     uint64_t r[1 + kMaxMaskWords];
     uint32_t exit_state = 0;
+    if (lazy_) {  // host haystack: bring in what this wave reads (plus a little for the flags at its end)
+      const uint64_t want = std::min(lazy_->n, limit + 64);
+      if (want > lazy_->done) {
+        RB_CUDA(cudaMemcpyAsync(lazy_->dst + lazy_->done, lazy_->src + lazy_->done, want - lazy_->done, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+        lazy_->done = want;
+      }
+    }
     if (int rc = forward_range(d_text, n, lo, limit, entry, want_masks, r, &exit_state)) return rc;
     stats.waves++;
     result_host[0] = std::min(result_host[0], r[0]);
@@ -1020,8 +1027,11 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
         uint64_t sr[1 + kMaxMaskWords];
         sub->tuning.wave0 = tuning.wave0;
         sub->set_stream(stream_);
+        sub->lazy_ = lazy_;
         std::lock_guard<std::recursive_mutex> lock(sub->mu_);
-        if (int rc = sub->forward_reduce(d_text, n, start, true, sr)) return fail(sub->last_error());
+        const int src = sub->forward_reduce(d_text, n, start, true, sr);
+        sub->lazy_ = nullptr;
+        if (src) return fail(sub->last_error());
         stats.waves += sub->stats.waves;
         for (uint32_t j = 0; j < open.size(); j++)
           if ((sr[1 + j / 64] >> (j % 64)) & 1) result_host[1 + open[j] / 64] |= 1ull << (open[j] % 64);
@@ -1359,26 +1369,90 @@ int Regex::find_all_host(const uint8_t* text, uint64_t n, uint64_t start, uint64
   if (d_out && k) RB_CUDA(d2h(out, d_out, k * 16));
   return 0;
 }
+// find_at on a host haystack (rure_find): the reference's cost is the distance to the next match
+// (src/exec.rs:473-514), so the haystack is uploaded and searched in windows that grow from
+// 64 KiB (x8 each) starting at `start`, every window as a byte-range shard entered with the
+// exact iterator state of the one before, and the search stops at the first span.  A C loop
+// `while (rure_find(re, h, n, pos, &m)) pos = m.end;` therefore moves each byte over PCIe
+// about once per match near it instead of once per call.
 int Regex::find_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* s, uint64_t* e) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
-  int rc;
-  const uint8_t* d = upload_text(text, n, &rc);
-  if (rc) return rc;
-  return find_at_device(d, n, start, found, s, e);
+  *found = false;
+  if (start > n) return 0;
+  if (int rc = init_device()) return rc;
+  if (is_set_) return fail("find requires exactly one pattern (RegexSet cannot be used with find, exec.rs:510-512)");
+  uint8_t* d = (uint8_t*)text_.ensure(n + 64);
+  uint64_t* d_out = (uint64_t*)out_.ensure(16);
+  if (!d || !d_out) return fail("out of device memory (haystack)");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const uint64_t buf_lo = start > 256 ? (start - 256) & ~255ull : 0;  // 256 bytes of left context for look-behind
+  uint64_t resident = buf_lo;                                         // bytes [buf_lo, resident) are on the device
+  uint64_t own_lo = start ? ((start - 1) & ~255ull) : 0;              // bit i <-> position i + 1
+  uint64_t win = 64 << 10, halo = 64 << 10;
+  uint64_t p = start, lm = kNone;
+  for (;;) {
+    uint64_t own_hi = std::min<uint64_t>(n, (own_lo + win + 255) & ~(uint64_t)255);
+    if (n - own_hi < 4096) own_hi = n;
+    const uint64_t hi = std::min(n, own_hi + halo);
+    if (hi == n) own_hi = n;  // the buffer ends with the text: the last window owns everything up to it
+    if (hi > resident) {
+      RB_CUDA(cudaMemcpyAsync(d + resident, text + resident, hi - resident, cudaMemcpyHostToDevice, st));
+      resident = hi;
+    }
+    ShardIO io;
+    io.own_lo = own_lo - buf_lo;
+    io.own_hi = own_hi - buf_lo;
+    io.is_first = buf_lo == 0;
+    io.is_last = hi == n;
+    io.chain_p = p - buf_lo;
+    io.chain_lm = lm == kNone ? kNone : lm - buf_lo;
+    const int rc = find_all_shard_device(d + buf_lo, hi - buf_lo, &io, d_out, 1);
+    if (rc) {
+      if (!io.halo_overflow) return rc;
+      if (hi == n) return rc;
+      halo *= 8;  // a match longer than the halo: look further
+      continue;
+    }
+    if (io.n_matches) {
+      uint64_t h[2];
+      RB_CUDA(d2h(h, d_out, 16));
+      *found = true;
+      *s = h[0] + buf_lo;
+      *e = h[1] + buf_lo;
+      return 0;
+    }
+    if (own_hi == n || io.exit_p == kNone) return 0;
+    p = io.exit_p + buf_lo;
+    lm = io.exit_lm == kNone ? kNone : io.exit_lm + buf_lo;
+    own_lo = own_hi;
+    win *= 8;
+  }
 }
+// is_match / shortest_match / set matches on a host haystack: the waves of forward_reduce upload
+// what they are about to read, so an early exit also ends the transfer (dfa.rs:658-667).
 int Regex::shortest_match_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* end) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
-  int rc;
-  const uint8_t* d = upload_text(text, n, &rc);
-  if (rc) return rc;
-  return shortest_match_device(d, n, start, found, end);
+  *found = false;
+  if (int rc = init_device()) return rc;
+  uint8_t* d = (uint8_t*)text_.ensure(n + 64);
+  if (!d) return fail("out of device memory (haystack)");
+  LazyUpload up{text, d, n, start > 256 ? (start - 256) & ~255ull : 0};
+  lazy_ = &up;
+  const int rc = shortest_match_device(d, n, start, found, end);
+  lazy_ = nullptr;
+  return rc;
 }
 int Regex::set_matches_host(const uint8_t* text, uint64_t n, uint64_t start, bool* any, uint64_t* masks) {
   std::lock_guard<std::recursive_mutex> lock(mu_);
-  int rc;
-  const uint8_t* d = upload_text(text, n, &rc);
-  if (rc) return rc;
-  return set_matches_device(d, n, start, any, masks);
+  *any = false;
+  if (int rc = init_device()) return rc;
+  uint8_t* d = (uint8_t*)text_.ensure(n + 64);
+  if (!d) return fail("out of device memory (haystack)");
+  LazyUpload up{text, d, n, start > 256 ? (start - 256) & ~255ull : 0};
+  lazy_ = &up;
+  const int rc = set_matches_device(d, n, start, any, masks);
+  lazy_ = nullptr;
+  return rc;
 }
 int Regex::is_match_batch_host(const uint8_t* text, const uint64_t* offsets, uint64_t n_rec, uint8_t* out_bits) {
   std::lock_guard<std::recursive_mutex> lock(mu_);

@@ -152,6 +152,8 @@ class Regex {
   const uint8_t* upload_text(const uint8_t* text, uint64_t n, int* rc);
   int find_all_host_pipelined(const uint8_t* text, uint64_t n, uint8_t* d, uint64_t* d_out, uint64_t* out, uint64_t cap, uint64_t* total);
 
+  struct LazyUpload { const uint8_t* src; uint8_t* dst; uint64_t n, done; };  // host haystack uploaded wave by wave
+  LazyUpload* lazy_ = nullptr;
   std::vector<std::string> patterns_;
   bool is_set_ = false;
   bool sparse_set_ = false;  // a narrowed RegexSet: none of its patterns matched in the first waves

@@ -190,3 +190,35 @@ def test_sharded_forward_searches_on_the_gpu(world):
     _, masks, _ = run(lambda: R.BytesRegexSet(pats), None)
     exp = [i for i, p in enumerate(pats) if pyre.search(p.encode(), text) is not None]
     assert [i for i in range(len(pats)) if (masks[0] >> i) & 1] == exp
+
+
+def test_scalar_find_searches_in_growing_windows():
+    """rure_find on a host haystack uploads and searches windows from `start` (64 KiB, x8 each) and
+    stops at the first span: the C idiom `while (rure_find(re, h, n, pos, &m)) pos = m.end;` must
+    cost about one pass, not one pass per call; results equal the oracle's find_at everywhere,
+    including look-around patterns whose windows start in the middle of the text."""
+    import time
+    text = tiled_corpus(48 << 20) + b" NEEDLE at the end\n"
+    r = R.BytesRegex(r"Holmes|Watson")
+    exp = O.OracleRegex(r"Holmes|Watson").find_iter(text[:4 << 20])
+    t0 = time.perf_counter()
+    pos, got = 0, []
+    while len(got) < 1500:
+        m = r.find_at(text, pos)
+        got.append(m)
+        pos = m[1]
+    dt = time.perf_counter() - t0
+    assert got == exp[:1500]
+    assert dt < 30, dt  # the whole-haystack version of this loop moves 1500 x 48 MiB over PCIe
+    # a match hundreds of windows away, and none at all
+    r = R.BytesRegex(r"NEEDLE")
+    assert r.find_at(text, 12345) == (text.find(b"NEEDLE"), text.find(b"NEEDLE") + 6)
+    assert r.find_at(text, text.find(b"NEEDLE") + 1) is None
+    assert r.is_match_at(text, 5) and not R.BytesRegex(r"NEEDLES").is_match(text)
+    assert R.BytesRegex(r"Sherlock").shortest_match_at(text, 1000) == text.find(b"Sherlock", 1000) + 8
+    small = text[:3 << 20]
+    for pat in (r"(?m)^\w+$", r"(?-u:\b)the(?-u:\b)", r"\w*", r"(?m)^[ab]{2,}\w*?|(?m:$)", r"[^\n]{60,}", r"(?s)Holmes.{70000}"):
+        r, o = R.BytesRegex(pat), O.OracleRegex(pat)
+        for start in (0, 1, 255, 256, 257, 65535, 65536, 65537, 131072, 600000, 2000001, len(small) - 3, len(small)):
+            assert r.find_at(small, start) == o.find_at(small, start), (pat, start)
+            assert r.shortest_match_at(small, start) == o.shortest_match_at(small, start), (pat, start)
