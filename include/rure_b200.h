@@ -61,6 +61,27 @@ bool rure_b200_count_all(rure *re, const uint8_t *haystack, size_t length, size_
 bool rure_b200_set_matches_mask(rure_set *set, const uint8_t *haystack, size_t length,
                                 size_t start, uint64_t *mask_words);
 
+/* ---- replace / split over all matches (bulk forms of src/re_bytes.rs:476-535 replacen and
+ * :316-360, :699-749 split / splitn; the span list and the haystack stay on the device) -------
+ * rure_b200_replace: every non-overlapping match (the first `limit` when limit > 0) is replaced by
+ * `rep`.  expand != 0 expands `$0`, `${0}` and `$$` as src/expand.rs:50-90 does (a reference to
+ * a group the pattern does not have expands to nothing; a reference to any other existing group
+ * fails: captures beyond group 0 are not computed by this backend); expand == 0 is NoExpand.
+ * *out_len receives the length of the result; at most out_cap bytes are written (out may be
+ * NULL to ask for the length).  replace_all = limit 0, replace = limit 1.
+ * rure_b200_split: the pieces between the matches as (start, end) pairs; has_limit / limit as
+ * splitn (limit pieces at most, the last one being the rest of the haystack). */
+bool rure_b200_replace(rure *re, const uint8_t *haystack, size_t length, const uint8_t *rep,
+                       size_t rep_len, int expand, size_t limit, uint8_t *out, size_t out_cap,
+                       size_t *out_len);
+bool rure_b200_replace_device(rure *re, const uint8_t *d_haystack, size_t length,
+                              const uint8_t *rep /* host */, size_t rep_len, int expand, size_t limit,
+                              uint8_t *d_out, size_t out_cap, size_t *out_len);
+bool rure_b200_split(rure *re, const uint8_t *haystack, size_t length, int has_limit, size_t limit,
+                     rure_match *out, size_t cap, size_t *n_pieces);
+bool rure_b200_split_device(rure *re, const uint8_t *d_haystack, size_t length, int has_limit,
+                            size_t limit, rure_match *d_out, size_t cap, size_t *n_pieces);
+
 /* ---- batched records: record i = haystack[offsets[i], offsets[i+1]) -------- */
 /* out_bits: bit (i % 8) of byte (i / 8); (n_records + 7) / 8 bytes */
 bool rure_b200_is_match_batch(rure *re, const uint8_t *haystack, const uint64_t *offsets,

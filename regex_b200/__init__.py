@@ -90,6 +90,10 @@ def _load():
         "rure_b200_shortest_match": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool), POINTER(sz)]),
         "rure_b200_find": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool), POINTER(_Match)]),
         "rure_b200_set_is_match": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool)]),
+        "rure_b200_replace": (c_bool, [vp, u8p, sz, c_char_p, sz, c_int, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_replace_device": (c_bool, [vp, vp, sz, c_char_p, sz, c_int, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_split": (c_bool, [vp, u8p, sz, c_int, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_split_device": (c_bool, [vp, vp, sz, c_int, sz, vp, sz, POINTER(sz)]),
         "rure_b200_find_all": (c_bool, [vp, u8p, sz, vp, sz, POINTER(sz)]),
         "rure_b200_count_all": (c_bool, [vp, u8p, sz, POINTER(sz)]),
         "rure_b200_set_matches_mask": (c_bool, [vp, u8p, sz, sz, POINTER(c_uint64)]),
@@ -275,6 +279,55 @@ class _Compiled:
             if total.value <= cap:
                 return out[: total.value]
             cap = total.value
+
+    # ---- replace / split (re_bytes.rs:316-360, 440-535) -----------------------------
+    def replacen(self, text, limit, rep, expand=True):
+        """`Regex::replacen`: at most `limit` matches replaced (0 = all).  rep: bytes/str; with
+        expand (the default for a plain replacement string, as in the reference) `$0`, `${0}`,
+        `$$` are expanded; expand=False is `NoExpand(rep)`."""
+        p, n, keep = _buf(text)
+        r = rep.encode("utf-8") if isinstance(rep, str) else bytes(rep)
+        ol = c_size_t()
+        if not _lib.rure_b200_replace(self._h, p, n, r, len(r), int(expand), limit, None, 0, byref(ol)):
+            raise Error(_last_error())
+        out = np.empty(max(ol.value, 1), dtype=np.uint8)
+        if not _lib.rure_b200_replace(self._h, p, n, r, len(r), int(expand), limit, out.ctypes.data, ol.value, byref(ol)):
+            raise Error(_last_error())
+        return out[:ol.value].tobytes()
+
+    def replace(self, text, rep, expand=True):
+        return self.replacen(text, 1, rep, expand)
+
+    def replace_all(self, text, rep, expand=True):
+        return self.replacen(text, 0, rep, expand)
+
+    def replace_all_device(self, d_text, rep, d_out=None, expand=True, limit=0):
+        """Device-resident replace_all: returns the output length; writes into d_out (uint8 CUDA tensor) when given."""
+        r = rep.encode("utf-8") if isinstance(rep, str) else bytes(rep)
+        ol = c_size_t()
+        ptr, cap = (0, 0) if d_out is None else (d_out.data_ptr(), d_out.numel())
+        if not _lib.rure_b200_replace_device(self._h, d_text.data_ptr(), d_text.numel(), r, len(r), int(expand), limit, ptr, cap, byref(ol)):
+            raise Error(_last_error())
+        return ol.value
+
+    def _split(self, text, has_limit, limit):
+        p, n, keep = _buf(text)
+        k = c_size_t()
+        if not _lib.rure_b200_split(self._h, p, n, has_limit, limit, None, 0, byref(k)):
+            raise Error(_last_error())
+        out = np.empty((max(k.value, 1), 2), dtype=np.uint64)
+        if not _lib.rure_b200_split(self._h, p, n, has_limit, limit, out.ctypes.data, k.value, byref(k)):
+            raise Error(_last_error())
+        data = bytes(keep) if not isinstance(keep, bytes) else keep
+        return [data[int(a):int(b)] for a, b in out[:k.value]]
+
+    def split(self, text):
+        """`Regex::split`: the pieces of text between the matches."""
+        return self._split(text, 0, 0)
+
+    def splitn(self, text, limit):
+        """`Regex::splitn`: at most `limit` pieces, the last one being the rest of the text."""
+        return self._split(text, 1, limit)
 
     def count_all(self, text):
         p, n, keep = _buf(text)

@@ -355,6 +355,36 @@ bool rure_b200_set_matches_shard_device(rure_set* set, const uint8_t* d_buffer, 
   return forward_shard(set->re, d_buffer, n_buffer, io, true);
 }
 
+// ---- replace_all / replacen / split / splitn (src/re_bytes.rs:316-360, 476-535) ----
+bool rure_b200_replace(rure* re, const uint8_t* haystack, size_t length, const uint8_t* rep, size_t rep_len, int expand, size_t limit,
+                       uint8_t* out, size_t out_cap, size_t* out_len) {
+  uint64_t ol = 0;
+  const bool r = ok(re->re, re->re->replace_host(haystack, length, rep, rep_len, expand != 0, limit, out, out ? out_cap : 0, &ol));
+  if (out_len) *out_len = ol;
+  return r;
+}
+bool rure_b200_replace_device(rure* re, const uint8_t* d_haystack, size_t length, const uint8_t* rep, size_t rep_len, int expand,
+                              size_t limit, uint8_t* d_out, size_t out_cap, size_t* out_len) {
+  uint64_t ol = 0;
+  const bool r = ok(re->re, re->re->replace_device(d_haystack, length, rep, rep_len, expand != 0, limit, d_out, d_out ? out_cap : 0, &ol));
+  if (out_len) *out_len = ol;
+  return r;
+}
+bool rure_b200_split(rure* re, const uint8_t* haystack, size_t length, int has_limit, size_t limit, rure_match* out, size_t cap,
+                     size_t* n_pieces) {
+  uint64_t np = 0;
+  const bool r = ok(re->re, re->re->split_host(haystack, length, has_limit != 0, limit, (uint64_t*)out, out ? cap : 0, &np));
+  if (n_pieces) *n_pieces = np;
+  return r;
+}
+bool rure_b200_split_device(rure* re, const uint8_t* d_haystack, size_t length, int has_limit, size_t limit, rure_match* d_out, size_t cap,
+                            size_t* n_pieces) {
+  uint64_t np = 0;
+  const bool r = ok(re->re, re->re->split_device(d_haystack, length, has_limit != 0, limit, (uint64_t*)d_out, d_out ? cap : 0, &np));
+  if (n_pieces) *n_pieces = np;
+  return r;
+}
+
 const char* rure_b200_last_error(void) { return g_last_error.c_str(); }
 uint64_t rure_b200_kernel_launches(void) { return rbgpu::kernel_launches(); }
 void rure_b200_last_stats(rure* re, double* out8) {

@@ -95,6 +95,18 @@ Regex* Regex::compile(const std::vector<std::string>& patterns, const CompileOpt
     re->min_len = std::min(re->min_len, mn);
     re->max_len = std::max(re->max_len, mx);
   }
+  if (patterns.size() == 1) {  // capture groups of the pattern (only their existence matters: replacement templates)
+    std::vector<const rb::Expr*> stack{&re->exprs_[0]};
+    while (!stack.empty()) {
+      const rb::Expr* x = stack.back();
+      stack.pop_back();
+      if (x->kind == rb::EK::Group && x->cap > 0) {
+        re->n_groups_ = std::max(re->n_groups_, x->cap + 1);
+        if (!x->name.empty()) re->group_names_.push_back(x->name);
+      }
+      for (const rb::Expr& c : x->es) stack.push_back(&c);
+    }
+  }
   if (patterns.empty()) { re->min_len = 0; return re.release(); }
   re->can_match_empty = re->min_len == 0;
   // Validate eagerly what the reference validates at build time (program size)
@@ -1225,6 +1237,212 @@ int Regex::set_matches_batch_device(const uint8_t* d_text, const uint64_t* d_off
   set_matches_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
   RB_LAUNCH_CHECK("set_matches_batch");
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  return 0;
+}
+
+// ------------------------------------------------------- replace_all / split ----
+// All spans of the haystack in spans_all_ (device); *m = their number.
+int Regex::all_spans_device(const uint8_t* d_text, uint64_t n, uint64_t** d_spans, uint64_t* m) {
+  uint64_t total = 0;
+  if (int rc = find_all_device(d_text, n, 0, nullptr, 0, &total)) return rc;
+  uint64_t* sp = (uint64_t*)spans_all_.ensure(std::max<uint64_t>(total, 1) * 16);
+  if (!sp) return fail("out of device memory (spans)");
+  if (total) {
+    uint64_t again = 0;
+    if (int rc = find_all_device(d_text, n, 0, sp, total, &again)) return rc;
+  }
+  *d_spans = sp;
+  *m = total;
+  return 0;
+}
+
+int Regex::replace_device(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit,
+                          uint8_t* d_out, uint64_t out_cap, uint64_t* out_len) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (int rc = replace_prepare(d_text, n, rep, rep_len, expand, limit, out_len)) return rc;
+  if (!d_out) return 0;
+  return replace_emit(d_out, out_cap);
+}
+
+// Template, spans and prefix sums of one replace call; leaves everything replace_emit needs in
+// rep_args_ / rep_lits_ and the device scratch.
+int Regex::replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit,
+                           uint64_t* out_len) {
+  if (is_set_) return fail("replace requires exactly one pattern");
+  // ---- the replacement template (src/expand.rs:50-90) ----
+  rep_args_.assign(sizeof(ReplaceArgs), 0);
+  ReplaceArgs& a = *reinterpret_cast<ReplaceArgs*>(rep_args_.data());
+  a = ReplaceArgs{};
+  std::vector<uint8_t>& lits = rep_lits_;
+  lits.clear();
+  auto literal = [&](const uint8_t* p, uint64_t len) -> bool {
+    if (len == 0) return true;
+    if (a.n_parts && a.part_len[a.n_parts - 1] != 0xFFFFFFFFu && a.part_off[a.n_parts - 1] + a.part_len[a.n_parts - 1] == lits.size()) {
+      a.part_len[a.n_parts - 1] += (uint32_t)len;  // extend the previous literal part
+    } else {
+      if (a.n_parts == kMaxRepParts) return false;
+      a.part_off[a.n_parts] = (uint32_t)lits.size();
+      a.part_len[a.n_parts++] = (uint32_t)len;
+    }
+    lits.insert(lits.end(), p, p + len);
+    a.lit_total += len;
+    return true;
+  };
+  bool fits = true;
+  if (!expand) {
+    fits = literal(rep, rep_len);
+  } else {
+    uint64_t i = 0;
+    auto cap_letter = [](uint8_t b) { return (b >= '0' && b <= '9') || (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || b == '_'; };
+    while (i < rep_len && fits) {
+      uint64_t j = i;
+      while (j < rep_len && rep[j] != '$') j++;
+      fits = literal(rep + i, j - i);
+      i = j;
+      if (i >= rep_len) break;
+      if (i + 1 < rep_len && rep[i + 1] == '$') { fits = fits && literal(rep + i, 1); i += 2; continue; }
+      // find_cap_ref (expand.rs:128-167)
+      uint64_t k = i + 1;
+      bool brace = false;
+      if (k < rep_len && rep[k] == '{') { brace = true; k++; }
+      uint64_t ce = k;
+      while (ce < rep_len && cap_letter(rep[ce])) ce++;
+      bool ok = rep_len - i > 1 && ce > k;
+      std::string name;
+      if (ok) {
+        name.assign((const char*)rep + k, ce - k);
+        if (brace) { if (ce < rep_len && rep[ce] == '}') ce++; else ok = false; }
+      }
+      if (!ok) { fits = fits && literal(rep + i, 1); i += 1; continue; }  // a lone '$'
+      i = ce;
+      bool numeric = name.find_first_not_of("0123456789") == std::string::npos && name.size() <= 9;
+      if (numeric) {
+        const long g = std::atol(name.c_str());
+        if (g == 0) {
+          if (a.n_parts == kMaxRepParts) { fits = false; break; }
+          a.part_len[a.n_parts] = 0xFFFFFFFFu;
+          a.part_off[a.n_parts++] = 0;
+          a.whole_refs++;
+        } else if (g < n_groups_) {
+          return fail("the replacement refers to capture group " + name + "; capture groups other than 0 are not supported by the B200 backend");
+        }  // a group that does not exist expands to nothing
+      } else if (std::find(group_names_.begin(), group_names_.end(), name) != group_names_.end()) {
+        return fail("the replacement refers to capture group '" + name + "'; capture groups other than 0 are not supported by the B200 backend");
+      }
+    }
+  }
+  if (!fits) return fail("replacement template has too many parts");
+  uint64_t* spans;
+  uint64_t m;
+  if (int rc = all_spans_device(d_text, n, &spans, &m)) return rc;
+  if (limit && m > limit) m = limit;
+  cudaStream_t st = (cudaStream_t)stream_;
+  uint64_t* lens = (uint64_t*)lens_.ensure(std::max<uint64_t>(m, 1) * 8);
+  uint64_t* before = (uint64_t*)offset_.ensure(std::max<uint64_t>(m, 1) * 8);
+  const uint64_t n_blocks = (m + 1023) / 1024;
+  uint64_t* block_sums = (uint64_t*)block_sums_.ensure(std::max<uint64_t>(n_blocks, 1) * 8);
+  uint32_t* counters = (uint32_t*)counters_.ensure(128);
+  uint8_t* d_lits = (uint8_t*)lits_.ensure(std::max<size_t>(lits.size(), 16));
+  if (!lens || !before || !block_sums || !counters || !d_lits) return fail("out of device memory (replace scratch)");
+  uint64_t matched = 0;
+  if (m) {
+    span_lengths<<<grid_for(m, 256, 8), 256, 0, st>>>(spans, m, lens);
+    RB_LAUNCH_CHECK("span_lengths");
+    unsigned long long* grand = (unsigned long long*)(counters + 4);
+    scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(lens, before, block_sums, m);
+    RB_LAUNCH_CHECK("scan_counts_local");
+    scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, grand);
+    RB_LAUNCH_CHECK("scan_block_sums");
+    scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(before, block_sums, m);
+    RB_LAUNCH_CHECK("scan_add_block_offsets");
+    RB_CUDA(d2h(&matched, grand, 8));
+  }
+  *out_len = n - matched + m * a.lit_total + (uint64_t)a.whole_refs * matched;
+  a.text = d_text;
+  a.n = n;
+  a.spans = spans;
+  a.n_matches = m;
+  a.lens_before = before;
+  a.lits = d_lits;
+  return 0;
+}
+
+int Regex::replace_emit(uint8_t* d_out, uint64_t out_cap) {
+  ReplaceArgs a = *reinterpret_cast<ReplaceArgs*>(rep_args_.data());
+  const std::vector<uint8_t>& lits = rep_lits_;
+  cudaStream_t st = (cudaStream_t)stream_;
+  uint8_t* d_lits = (uint8_t*)lits_.ptr;
+  const uint64_t n = a.n, m = a.n_matches;
+  if (!lits.empty()) RB_CUDA(cudaMemcpyAsync(d_lits, lits.data(), lits.size(), cudaMemcpyHostToDevice, st));
+  a.out = d_out;
+  a.out_cap = out_cap;
+  if (n) {
+    replace_gaps<<<grid_for(((n + 2047) / 2048) * 32, 256, 8), 256, 0, st>>>(a);
+    RB_LAUNCH_CHECK("replace_gaps");
+  }
+  if (m && a.n_parts) {
+    replace_matches<<<grid_for(m * 32, 256, 8), 256, 0, st>>>(a);
+    RB_LAUNCH_CHECK("replace_matches");
+  }
+  RB_CUDA(cudaStreamSynchronize(st));  // `lits` and the caller's buffers may go away now
+  return 0;
+}
+
+int Regex::replace_host(const uint8_t* text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit, uint8_t* out,
+                        uint64_t out_cap, uint64_t* out_len) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  if ((rc = replace_prepare(d, n, rep, rep_len, expand, limit, out_len))) return rc;
+  if (!out) return 0;
+  uint8_t* d_out = (uint8_t*)rep_out_.ensure(std::max<uint64_t>(*out_len, 16));
+  if (!d_out) return fail("out of device memory (replace output)");
+  if ((rc = replace_emit(d_out, *out_len))) return rc;
+  const uint64_t k = std::min(out_cap, *out_len);
+  if (k) RB_CUDA(d2h(out, d_out, k));
+  return 0;
+}
+
+int Regex::split_device(const uint8_t* d_text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* d_pieces, uint64_t cap, uint64_t* n_pieces) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  *n_pieces = 0;
+  if (is_set_) return fail("split requires exactly one pattern");
+  if (has_limit && limit == 0) return 0;  // re_bytes.rs:738-740
+  uint64_t* spans;
+  uint64_t m;
+  if (int rc = all_spans_device(d_text, n, &spans, &m)) return rc;
+  uint64_t last_end = 0;
+  if (m) RB_CUDA(d2h(&last_end, spans + 2 * m - 1, 8));
+  // Split yields one piece per match and the rest of the text when it is not empty (re_bytes.rs:702-720)
+  const uint64_t p_split = m + (last_end < n ? 1 : 0);
+  uint64_t pieces = p_split;
+  int last_is_rest = 0;
+  if (has_limit && p_split >= limit - 1) {  // SplitN: the limit-th piece is whatever remains, empty or not (re_bytes.rs:737-748)
+    pieces = limit;
+    last_is_rest = 1;
+  }
+  *n_pieces = pieces;
+  if (d_pieces && pieces && cap) {
+    split_pieces<<<grid_for(pieces, 256, 8), 256, 0, (cudaStream_t)stream_>>>(spans, m, n, pieces, last_is_rest, d_pieces, cap);
+    RB_LAUNCH_CHECK("split_pieces");
+    RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  }
+  return 0;
+}
+
+int Regex::split_host(const uint8_t* text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* pieces, uint64_t cap, uint64_t* n_pieces) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  if ((rc = split_device(d, n, has_limit, limit, nullptr, 0, n_pieces))) return rc;
+  if (!pieces || !cap || !*n_pieces) return 0;
+  const uint64_t k = std::min(cap, *n_pieces);
+  uint64_t* d_p = (uint64_t*)pieces_.ensure(k * 16);
+  if (!d_p) return fail("out of device memory (pieces)");
+  if ((rc = split_device(d, n, has_limit, limit, d_p, k, n_pieces))) return rc;
+  RB_CUDA(d2h(pieces, d_p, k * 16));
   return 0;
 }
 

@@ -106,6 +106,17 @@ class Regex {
   int forward_shard_device(const uint8_t* d_text, uint64_t n, uint64_t own_lo, uint64_t own_hi, bool is_first, bool is_last, uint32_t entry,
                            bool want_masks, bool* found, uint64_t* first_end, uint64_t* masks, uint32_t* entry_used, uint32_t* exit_state);
 
+  // ---- bulk operations over the span list (re_bytes.rs:316-360 split/splitn, :476-535 replacen) ----
+  // rep: replacement; expand = `$0`, `${0}`, `$$` as src/expand.rs (a reference to another group fails: captures
+  // beyond group 0 are out of scope; NoExpand = expand false); limit 0 = all matches.  d_out may be null to size.
+  int replace_device(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit,
+                     uint8_t* d_out, uint64_t out_cap, uint64_t* out_len);
+  int replace_host(const uint8_t* text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit,
+                   uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+  // pieces as (start, end) pairs; has_limit/limit as splitn
+  int split_device(const uint8_t* d_text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* d_pieces, uint64_t cap, uint64_t* n_pieces);
+  int split_host(const uint8_t* text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* pieces, uint64_t cap, uint64_t* n_pieces);
+
   // ---- batched records, device-resident text + offsets[n_rec+1] --------------
   int is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits);
   int find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_spans, uint32_t* d_bits);
@@ -143,6 +154,9 @@ class Regex {
   int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
+  int all_spans_device(const uint8_t* d_text, uint64_t n, uint64_t** d_spans, uint64_t* m);
+  int replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit, uint64_t* out_len);
+  int replace_emit(uint8_t* d_out, uint64_t out_cap);
   bool plan_prefilter();  // fills pf_words_ (launch.h PfArgs) when every match has one of <= 4 bytes at a fixed offset
   int forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, bool want_masks, uint64_t* result_host, uint64_t end = ~0ull,
                      uint32_t entry = 0xFFFFFFFFu, uint32_t* exit_out = nullptr);
@@ -172,6 +186,10 @@ class Regex {
   bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
+  DeviceBuf spans_all_, lens_, lits_, rep_out_, pieces_;
+  std::vector<uint8_t> rep_args_, rep_lits_;  // launch.h ReplaceArgs image + literal bytes of the pending replace call
+  int n_groups_ = 1;                      // capture groups incl. group 0
+  std::vector<std::string> group_names_;  // names of the named groups
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};

@@ -403,10 +403,11 @@ __device__ __forceinline__ uint64_t next_bit(const uint64_t* bm, const uint8_t* 
 // halo_err: non-null when the buffer is a shard whose text continues past n (running
 // into n then means the halo was too short, not end-of-text).
 __device__ __forceinline__ uint64_t anchored_end(const DfaView& d, const Table& T, const uint8_t* text, uint64_t n, uint64_t s,
-                                                 uint32_t* halo_err = nullptr) {
+                                                 uint32_t* halo_err = nullptr, uint64_t cap = kNone) {
   uint32_t st = pick_start_fwd(d, text, n, s);
   uint64_t last = kNone;
   for (uint64_t q = s;; q++) {
+    if (q - s > cap) return kTooLong;
     if (q >= n && halo_err) { *halo_err = 1; return last; }
     st = q < n ? T.step(st, __ldg(text + q)) : T.step_eof(st);
     if (st >= d.match_lo) last = q;
@@ -449,8 +450,8 @@ __device__ __forceinline__ uint64_t next_utf8(const uint8_t* text, uint64_t n, u
 // Generic anchored runner: class-indexed table (shared memory when it fits), any start flags.
 struct GenericRunner {
   Table T;
-  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
-    return anchored_end(a.fwd, T, a.text, a.n, s, a.text_continues ? a.err_flag : nullptr);
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s, uint64_t cap = kNone) const {
+    return anchored_end(a.fwd, T, a.text, a.n, s, a.text_continues ? a.err_flag : nullptr, cap);
   }
 };
 // Fast anchored runner: byte-indexed XOR-swizzled table in shared memory (one LDS per
@@ -461,10 +462,11 @@ struct GenericRunner {
 // (scalar arguments only: a reference to the kernel's parameter block would make every
 // thread copy it to its stack.)  FastRunner patterns have a uniform start state.
 __device__ __noinline__ uint64_t slow_anchored_end(const uint16_t* trans, const uint8_t* classes, uint32_t stride, uint32_t match_lo,
-                                                   uint32_t start, const uint8_t* text, uint64_t n, uint64_t s, uint32_t* halo_err) {
+                                                   uint32_t start, const uint8_t* text, uint64_t n, uint64_t s, uint32_t* halo_err, uint64_t cap) {
   uint32_t st = start;
   uint64_t last = kNone;
   for (uint64_t q = s;; q++) {
+    if (q - s > cap) return kTooLong;
     if (q >= n && halo_err) { *halo_err = 1; return last; }
     st = q < n ? trans[st * stride + classes[__ldg(text + q)]] : trans[st * stride + stride - 1];
     if (st >= match_lo) last = q;
@@ -476,15 +478,16 @@ struct FastRunner {
   uint32_t tb, thr, start_e;  // table address, first match row, start row
   const uint16_t* eof;  // by hot id, value in full numbering
   uint32_t match_lo;    // full numbering (for the EOF successor)
-  static __device__ __forceinline__ uint64_t slow(const WalkArgs& a, uint64_t s) {
+  static __device__ __forceinline__ uint64_t slow(const WalkArgs& a, uint64_t s, uint64_t cap) {
     return slow_anchored_end(a.fwd.trans, a.fwd.classes, a.fwd.stride, a.fwd.match_lo, a.fwd.start[32], a.text, a.n, s,
-                             a.text_continues ? a.err_flag : nullptr);
+                             a.text_continues ? a.err_flag : nullptr, cap);
   }
-  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s) const {
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs& a, uint64_t s, uint64_t cap = kNone) const {
     uint32_t e = start_e;
     uint64_t last = kNone;
     const uint32_t live = 2;  // rows 0 (dead) and 1 (trap) end the run
     for (uint64_t q = s;; q += 16) {
+      if (q - s > cap) return kTooLong;
       const uint64_t al = q & ~7ull;
       const uint64_t* wp = reinterpret_cast<const uint64_t*>(a.text + al);
       const uint32_t sh = (uint32_t)(q & 7) * 8;
@@ -510,7 +513,7 @@ struct FastRunner {
           e = hot_next<3>(tb, v[g], e); if (e >= thr) lj = 4 * g + 3;
           if (e < live) { died = true; break; }
         }
-        if (e == 1) return slow(a, s);  // trap: left the hot set
+        if (e == 1) return slow(a, s, cap);  // trap: left the hot set
         if (lj != ~0u) last = q + lj;
         if (died) return last;
         continue;
@@ -529,7 +532,7 @@ struct FastRunner {
         const uint32_t byte = (uint32_t)((j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8))) & 0xFF);
         e = hot_next_b(tb, byte, e);
         if (e >= thr) last = q + j;
-        if (e < live) return e == 1 ? slow(a, s) : last;
+        if (e < live) return e == 1 ? slow(a, s, cap) : last;
       }
     }
   }
@@ -540,7 +543,7 @@ struct FastRunner {
 // the same length, so the leftmost-first end is s + L without touching the haystack.
 struct FixedLenRunner {
   uint64_t len;
-  __device__ __forceinline__ uint64_t end_from(const WalkArgs&, uint64_t s) const { return s + len; }
+  __device__ __forceinline__ uint64_t end_from(const WalkArgs&, uint64_t s, uint64_t = kNone) const { return s + len; }
 };
 
 // Chain state of the find_iter iterator (re_trait.rs:174-179).
@@ -569,6 +572,7 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
   const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
   uint64_t fc = kNone;
+  const uint64_t run_cap = c.chain ? kNone : kSpecRunCap;  // only an exact entry state justifies an arbitrarily long run
   uint64_t cached_w = kNone, word = 0;
   uint64_t pf_w = kNone, pf_word = 0;  // next candidate word, load issued ahead of use
   const uint64_t w0 = cb >> 6, w_end = (ce + 63) >> 6;
@@ -609,7 +613,8 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
       s = (bit & ~63ull) + (uint64_t)__ffsll((long long)m);
     }
     if (fc == kNone) fc = s;
-    const uint64_t e = T.end_from(a, s);
+    const uint64_t e = T.end_from(a, s, run_cap);
+    if (e == kTooLong) { *first_cand = kTooLong; return 0; }  // deferred: see kSpecRunCap
     if (e == kNone) { c.p = s + 1; c.chain = false; continue; }  // unreachable for consistent tables
     uint64_t ms = s;
     if (a.emulate_slice && c.chain && e != c.p) {
@@ -649,6 +654,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
   uint32_t total = 0;
   uint64_t fc = kNone;
+  const uint64_t run_cap = c.chain ? kNone : kSpecRunCap;
   // Spans leave two at a time as whole 32-byte sectors when the destination allows it
   // (staging areas do): the even span of a pair waits in registers for the odd one.
   const bool pair_stores = ((uintptr_t)o & 31) == 0;
@@ -675,7 +681,8 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   if (c.p == kNone) { *first_cand = fc; return 0; }
   if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
     fc = 0;
-    const uint64_t e = T.end_from(a, 0);
+    const uint64_t e = T.end_from(a, 0, run_cap);
+    if (e == kTooLong) { *first_cand = kTooLong; return 0; }
     if (e == kNone) { c.p = 1; c.chain = false; }
     else { emit(0, e); c.p = c.lm = e; c.chain = true; }
   }
@@ -697,7 +704,8 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
     const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
     const uint64_t s = cb + sr + 1;
     if (fc == kNone) fc = s;
-    const uint64_t e = T.end_from(a, s);
+    const uint64_t e = T.end_from(a, s, run_cap);
+    if (e == kTooLong) { *first_cand = kTooLong; return 0; }
     if (e == kNone) {  // unreachable for consistent tables
       cur &= cur - 1;
       c.p = s + 1;
@@ -766,9 +774,15 @@ struct RunnerSetup<1> {
 __device__ __forceinline__ void finish_chunk(const WalkArgs& a, uint64_t k, const Chain& c, uint64_t total, uint64_t fc, bool spec) {
   a.out_p[k] = c.p;
   a.out_lm[k] = c.lm;
+  a.skip[k] = 0;
+  if (fc == kTooLong) {  // the walk gave up on a long match (kSpecRunCap): nothing staged, the stitch decides
+    a.count[k] = 0;
+    a.first_cand[k] = kNone;
+    a.meta[k] = kChunkDeferred << 30;
+    return;
+  }
   a.count[k] = total;
   a.first_cand[k] = fc;
-  a.skip[k] = 0;
   a.meta[k] = (uint32_t)min(total, (uint64_t)kMetaCount) | ((spec && fc == kNone ? kChunkIdent : kChunkOk) << 30);
 }
 
@@ -1599,6 +1613,7 @@ __global__ void stitch_fast(WalkArgs a, uint32_t* counters) {
     const uint32_t meta = a.meta[k];
     const uint64_t cb = a.base + k * (uint64_t)a.chunk;
     const uint64_t ce_next = min(cb + 2 * (uint64_t)a.chunk, a.limit);
+    if ((meta >> 30) == kChunkDeferred) counters[2] = 1;
     if ((meta >> 30) == kChunkOk && k + 1 < a.n_chunks && a.out_p[k] > ce_next) counters[2] = 1;  // a match longer than a chunk
     if (k == 0 || (meta >> 30) != kChunkOk) continue;
     if ((a.meta[k - 1] >> 30) != kChunkOk) continue;  // the neighbour holds no candidate: the entry cannot lie inside this chunk
@@ -1690,7 +1705,15 @@ __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey*
     const ChainKey t = key_join(block_tot[k >> 10], excl[k]);  // entries_local runs with 1024 threads per block
     const bool spec = a.in_p[k] == kSpec;
     if (t.key == 0) {  // nothing to the left contributes (a shard entered speculatively): the chunk's own speculation stands
-      if (!spec || state != kChunkOk || a.skip[k] != 0 || (meta & kMetaPatched)) { a.dirty_list[atomicAdd(&counters[0], 1u)] = (uint32_t)k; a.in_p[k] = kSpec; a.in_lm[k] = kNone; atomicMin(&counters[3], (uint32_t)k); }
+      const uint64_t own_first = a.base + k * (uint64_t)a.chunk + 1;
+      const bool as_is = spec ? (state == kChunkOk && a.skip[k] == 0 && !(meta & kMetaPatched))
+                              : (state == kChunkOk && a.in_p[k] == own_first && a.in_lm[k] == kNone);  // a deferred chunk walked again without the cap
+      if (!as_is) {
+        a.dirty_list[atomicAdd(&counters[0], 1u)] = (uint32_t)k;
+        a.in_p[k] = state == kChunkDeferred ? own_first : kSpec;
+        a.in_lm[k] = kNone;
+        atomicMin(&counters[3], (uint32_t)k);
+      }
       continue;
     }
     const uint64_t tp = key_pos(t.key), tl = t.lm;
@@ -1702,6 +1725,8 @@ __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey*
     if (tp == kNone || tp > ce) {
       new_state = kChunkCovered;
       new_count = 0;
+    } else if (spec && state == kChunkDeferred) {
+      rewalk = true;
     } else if (spec) {
       if (strict) {
         bool ok = tp < c_first || (tp == c_first && !a.emulate_slice && !(a.can_match_empty && tl == c_first));
@@ -1815,6 +1840,79 @@ __global__ void scan_block_sums(uint64_t* block_sums, uint64_t n_blocks, unsigne
 __global__ void scan_add_block_offsets(uint64_t* out, const uint64_t* block_sums, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] += block_sums[blockIdx.x];
+}
+
+// ------------------------------------------------- replace_all / split ----------
+// Bulk forms of the reference's thin loops over find_iter (src/re_bytes.rs:476-535 replacen,
+// :316-360 / :699-749 split): the spans are on the device already, so the haystack never
+// leaves it.  With P_i = total length of the matches before match i, L = literal bytes of
+// the replacement and k = number of `$0` parts, input byte x in the gap in front of match i
+// lands at x + i*L + (k-1)*P_i, and the replacement of match i starts at start_i + that.
+__global__ void span_lengths(const uint64_t* spans, uint64_t n_matches, uint64_t* lens) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_matches; i += (uint64_t)gridDim.x * blockDim.x)
+    lens[i] = spans[2 * i + 1] - spans[2 * i];
+}
+__device__ __forceinline__ int64_t replace_shift(const ReplaceArgs& a, uint64_t i, uint64_t lens_before) {
+  return (int64_t)(i * a.lit_total) + ((int64_t)a.whole_refs - 1) * (int64_t)lens_before;
+}
+// The unmatched text.  One warp per 2 KiB tile of the INPUT (balanced whatever the gap sizes):
+// binary search for the first match that ends after the tile's first byte, then gap by gap.
+__global__ void replace_gaps(ReplaceArgs a) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t tiles = (a.n + 2047) / 2048;
+  for (uint64_t t = warp; t < tiles; t += n_warps) {
+    const uint64_t lo = t * 2048, hi = min(lo + 2048, a.n);
+    uint64_t i0 = 0, i1 = a.n_matches;  // first match with end > lo
+    while (i0 < i1) {
+      const uint64_t mid = (i0 + i1) >> 1;
+      if (a.spans[2 * mid + 1] <= lo) i0 = mid + 1; else i1 = mid;
+    }
+    uint64_t x = lo;
+    for (uint64_t i = i0; x < hi; i++) {
+      const bool tail = i >= a.n_matches;
+      const uint64_t ms = tail ? a.n : a.spans[2 * i], me = tail ? a.n : a.spans[2 * i + 1];
+      const uint64_t before = tail ? (a.n_matches ? a.lens_before[a.n_matches - 1] + (a.spans[2 * a.n_matches - 1] - a.spans[2 * a.n_matches - 2]) : 0)
+                                   : a.lens_before[i];
+      const int64_t shift = replace_shift(a, min(i, a.n_matches), before);
+      const uint64_t ge = min(ms, hi);  // gap [x, ge)
+      for (uint64_t q = x + lane; q < ge; q += 32) {
+        const uint64_t o = (uint64_t)((int64_t)q + shift);
+        if (o < a.out_cap) a.out[o] = a.text[q];
+      }
+      if (tail) break;
+      x = max(x, me);
+    }
+  }
+}
+// The replacements.  One warp per match.
+__global__ void replace_matches(ReplaceArgs a) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = warp; i < a.n_matches; i += n_warps) {
+    const uint64_t ms = a.spans[2 * i], me = a.spans[2 * i + 1];
+    uint64_t o = (uint64_t)((int64_t)ms + replace_shift(a, i, a.lens_before[i]));
+    for (uint32_t p = 0; p < a.n_parts; p++) {
+      const bool whole = a.part_len[p] == 0xFFFFFFFFu;
+      const uint64_t len = whole ? me - ms : a.part_len[p];
+      const uint8_t* src = whole ? a.text + ms : a.lits + a.part_off[p];
+      for (uint64_t q = lane; q < len; q += 32)
+        if (o + q < a.out_cap) a.out[o + q] = src[q];
+      o += len;
+    }
+  }
+}
+// Split (re_bytes.rs:699-721): piece i is the text between match i-1 and match i; the text after
+// the last match is a piece only when it is not empty; SplitN (:734-749): the n-th piece is the rest.
+__global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t n, uint64_t n_pieces, int last_is_rest, uint64_t* pieces, uint64_t cap) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pieces && i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t from = i == 0 ? 0 : (i - 1 < n_matches ? spans[2 * (i - 1) + 1] : n);
+    const uint64_t to = (i < n_matches && !(last_is_rest && i + 1 == n_pieces)) ? spans[2 * i] : n;
+    pieces[2 * i] = from;
+    pieces[2 * i + 1] = to;
+  }
 }
 
 // ---------------------------------------------------------------- batch mode --

@@ -25,6 +25,12 @@ namespace rbgpu {
 
 constexpr uint64_t kNone = ~0ull;        // "no position"
 constexpr uint64_t kSpec = ~0ull - 1;    // chunk entry state is speculative
+constexpr uint64_t kTooLong = ~0ull - 2; // an anchored run of a speculative chunk walk was cut off (see kSpecRunCap)
+// A speculatively entered chunk gives up on a match longer than this: with `(?s)foo.*bar` every
+// chunk that holds a `foo` would otherwise run its automaton to the last `bar` of the haystack,
+// only to learn from the stitch that the one real match covers it.  The chunk is DEFERRED instead:
+// the stitch walks it again with its exact entry state (no cap) unless it is covered.
+constexpr uint64_t kSpecRunCap = 1ull << 18;
 
 struct DfaView {
   const uint16_t* trans;    // [n_states][stride], class-indexed; column stride-1 is EOF

@@ -90,6 +90,31 @@ template <int FAST, int NB>  // NB = PfArgs::n_bytes
 __global__ void literal_scan(const __grid_constant__ WalkArgs a, const __grid_constant__ PfArgs pf, int mode);
 __global__ void compact_staged(WalkArgs a);
 
+// ---- bulk operations over the span list (src/re_bytes.rs:316-360 split, :476-535 replacen) ----
+// The replacement of one match is a sequence of parts: literal bytes, or the text of the whole
+// match (`$0`, src/expand.rs:50-90).
+constexpr uint32_t kMaxRepParts = 16;
+struct ReplaceArgs {
+  const uint8_t* text;
+  uint64_t n;
+  const uint64_t* spans;   // n_matches (start, end) pairs, ordered, non-overlapping
+  uint64_t n_matches;      // matches to replace (after `limit`)
+  const uint64_t* lens_before;  // exclusive prefix sum of the match lengths
+  const uint8_t* lits;     // literal bytes of all parts, concatenated
+  uint32_t n_parts;
+  uint32_t part_len[kMaxRepParts];  // literal length, or 0xFFFFFFFF = the match text
+  uint32_t part_off[kMaxRepParts];  // offset into lits
+  uint64_t lit_total;      // literal bytes per match
+  uint32_t whole_refs;     // `$0` parts per match
+  uint8_t* out;
+  uint64_t out_cap;
+};
+__global__ void span_lengths(const uint64_t* spans, uint64_t n_matches, uint64_t* lens);
+__global__ void replace_gaps(ReplaceArgs a);
+__global__ void replace_matches(ReplaceArgs a);
+// pieces[i] = text between match i-1 and match i; limit as splitn (0 = none)
+__global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t n, uint64_t n_pieces, int last_is_rest, uint64_t* pieces, uint64_t cap);
+
 struct BatchArgs {
   DfaView fwd;
   DfaView rev;
@@ -142,7 +167,7 @@ template <int FAST>
 __global__ void walk_sequential(WalkArgs a);
 __global__ void init_walk_entries(uint64_t* in_p, uint64_t* in_lm, uint32_t* skip, uint64_t n_chunks, uint64_t p0, uint64_t lm0);
 // Chunk states kept in WalkArgs::meta (bits 30-31).
-constexpr uint32_t kChunkOk = 0, kChunkIdent = 1, kChunkCovered = 2;
+constexpr uint32_t kChunkOk = 0, kChunkIdent = 1, kChunkCovered = 2, kChunkDeferred = 3;
 constexpr uint32_t kMetaCount = 0x1FFFFFFFu;
 constexpr uint32_t kMetaPatched = 0x20000000u;  // the first staged span's start was re-derived by the slice rule
 // One entry of the "exit of the last contributing chunk to the left" scan: key = p + 1 (0 = no

@@ -25,11 +25,12 @@ def _device_repeat(base, reps):
 
 
 def test_sticky_automaton_is_solved_by_state_map_composition():
-    """`(?s)foo.*bar` over 1 GiB: the reverse scan's state is "a bar lies somewhere to the right" for
-    the whole haystack, which no warm-up can guess; the single match covers ~260 000 chunks."""
+    """`(?s)foo.*bar` over 256 MiB: the reverse scan's state is "a bar lies somewhere to the right" for
+    the whole haystack, which no warm-up can guess; the single match covers ~65 000 chunks (the
+    anchored run that measures it is one thread's work: DESIGN.md, known limits)."""
     import torch
     base = tiled_corpus(16 << 20)
-    reps = 64
+    reps = 16
     d = _device_repeat(base, reps)
     n = d.numel()
     first_foo = base.find(b"foo")
@@ -217,7 +218,7 @@ def test_scalar_find_searches_in_growing_windows():
     assert r.is_match_at(text, 5) and not R.BytesRegex(r"NEEDLES").is_match(text)
     assert R.BytesRegex(r"Sherlock").shortest_match_at(text, 1000) == text.find(b"Sherlock", 1000) + 8
     small = text[:3 << 20]
-    for pat in (r"(?m)^\w+$", r"(?-u:\b)the(?-u:\b)", r"\w*", r"(?m)^[ab]{2,}\w*?|(?m:$)", r"[^\n]{60,}", r"(?s)Holmes.{70000}"):
+    for pat in (r"(?m)^\w+$", r"(?-u:\b)the(?-u:\b)", r"\w*", r"(?m)^[ab]{2,}\w*?|(?m:$)", r"[^\n]{60,}", r"(?s)Gutenberg.*Gutenberg"):
         r, o = R.BytesRegex(pat), O.OracleRegex(pat)
         for start in (0, 1, 255, 256, 257, 65535, 65536, 65537, 131072, 600000, 2000001, len(small) - 3, len(small)):
             assert r.find_at(small, start) == o.find_at(small, start), (pat, start)
