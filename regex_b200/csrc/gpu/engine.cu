@@ -54,6 +54,9 @@ void* DeviceBuf::ensure(size_t bytes) {
 // staged in shared memory by the fast kernels.
 static constexpr uint32_t kFastStates = 200;
 static size_t hot_bytes(uint32_t rows) { return ((size_t)rows * RB_HOT_ROW + 255) / 256 * 256; }  // kernels.cu hot_table_bytes
+// scan_rev_fast's reverse table with signed row ids (kernels.cu hot_signed_bytes): match rows and the others are rounded apart
+static size_t hot_bytes_signed(const HotView& h) { return hot_bytes(h.n - h.match_lo) + hot_bytes(h.match_lo); }
+static bool hot_signed_ok(const HotView& h) { return h.n != 0 && h.match_lo <= 128 && h.n - h.match_lo <= 128; }
 
 struct Regex::DeviceDfa {
   DfaView view;
@@ -513,7 +516,7 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
   if (fast) {
     block = 1024;
     const bool fw_fixed = fw && fw->fixed_len != 0;
-    smem = fast_scan_smem(hot_bytes(rev->hot.n) + (fw && !fw_fixed ? hot_bytes(fw->fwd_hot.n) : 0));
+    smem = fast_scan_smem(hot_bytes_signed(rev->hot) + (fw && !fw_fixed ? hot_bytes(fw->fwd_hot.n) : 0));
     if (fw_fixed) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -635,7 +638,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   cudaEvent_t ev[3] = {(cudaEvent_t)timing_events_[0], (cudaEvent_t)timing_events_[1], (cudaEvent_t)timing_events_[2]};
   RB_CUDA(cudaEventRecord(ev[0], st));
   const ScanPlan plan = plan_scan(d_text, io->own_lo, io->own_hi,
-                                   revall->hot.n != 0 && fast_scan_smem(hot_bytes(revall->hot.n)) <= 227 * 1024);
+                                   hot_signed_ok(revall->hot) && fast_scan_smem(hot_bytes_signed(revall->hot)) <= 227 * 1024);
   // runner: 2 = fixed-length (no haystack access), 1 = byte-indexed shared-memory table
   // (uniform start state, 8-byte aligned text), 0 = generic
   const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;
@@ -649,7 +652,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   const bool pf_fast = use_pf && fwd->hot.n != 0 && fwd->view.uniform_start;
   // fused: every lane of the fast scan kernel also walks its own segment (chunk == segment)
   const bool fused = !use_pf && plan.fast && wkind != 0 && tuning.fuse && !io->reuse_scan &&
-                     fast_scan_smem(hot_bytes(revall->hot.n) + (wkind == 1 ? hot_bytes(fwd->hot.n) : 0)) <= 227 * 1024;
+                     fast_scan_smem(hot_bytes_signed(revall->hot) + (wkind == 1 ? hot_bytes(fwd->hot.n) : 0)) <= 227 * 1024;
 
   WalkArgs w{};
   w.fwd = fwd->view;
@@ -723,7 +726,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     const uint32_t g = mode == 2 ? 1 : grid_for(chunks * 32, 256, 3);  // one warp per chunk
 #define RB_PF(F, N)                                                                \
     {                                                                              \
-      cudaError_t e__ = allow_smem(literal_scan<F, N>, wsmem);                     \
+      /* the kernel also has ~9 KB of static shared memory: opt in whenever the sum could pass 48 KB */ \
+      cudaError_t e__ = cudaFuncSetAttribute(literal_scan<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(wsmem, 48 * 1024)); \
       if (e__ != cudaSuccess) return e__;                                          \
       literal_scan<F, N><<<g, 256, wsmem, st>>>(args, pf, mode);                   \
       return cudaSuccess;                                                          \

@@ -150,6 +150,52 @@ __device__ __forceinline__ void rev_block16(uint32_t tb, const uint4& v, uint32_
   rev_word<BIT0 + 0>(tb, v.x, e, bits, thr);
 }
 
+// ---- signed row ids (scan_rev_fast's own table) ----
+// The reverse scan records one bit per byte: "did this step enter a match state".  With row
+// ids 0..n-1 that is a compare plus a predicated add per byte (ISETP + @P VIADD).  Here match
+// rows get NEGATIVE ids -1, -2, ... and live BELOW the table's base address (the row address
+// is still base + id * 288, two's complement), entries are loaded sign-extended (LDS.S8), and
+// the bit is the sign: bits = funnel_shift_left(id, bits, 1) -- ONE instruction.  A byte then
+// costs PRMT + IMAD + LDS.S8 + SHF instead of five instructions.  Non-match rows keep ids
+// 0 (dead), 1 (trap), 2...; at most 128 of either kind.
+__device__ __forceinline__ uint32_t hot_signed_below(const HotView& h) { return ((h.n - h.match_lo) * kHotRow + 255u) & ~255u; }  // bytes of match rows
+__device__ __forceinline__ uint32_t hot_signed_bytes(const HotView& h) { return hot_signed_below(h) + ((h.match_lo * kHotRow + 255u) & ~255u); }
+__device__ __forceinline__ uint32_t hot_sid(uint32_t idx, uint32_t match_lo) { return idx < match_lo ? idx : ~(idx - match_lo); }   // row index -> signed id
+__device__ __forceinline__ uint32_t hot_idx(uint32_t sid, uint32_t match_lo) { return (int32_t)sid >= 0 ? sid : match_lo + ~sid; } // and back
+__device__ __forceinline__ void hot_stage_signed(const HotView& h, uint32_t mid) {  // mid = address of row 0 (256-byte aligned)
+  const uint32_t n4 = h.n * 64u;
+  const uint2* src = reinterpret_cast<const uint2*>(h.next256);  // 4 x u16 row indices
+  const uint32_t ml = h.match_lo;
+  for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) {
+    const uint2 v = src[i];
+    const uint32_t a = hot_sid(v.x & 0xFFFFu, ml) & 0xFFu, b = hot_sid(v.x >> 16, ml) & 0xFFu;
+    const uint32_t c = hot_sid(v.y & 0xFFFFu, ml) & 0xFFu, d = hot_sid(v.y >> 16, ml) & 0xFFu;
+    const uint32_t row = (uint32_t)((int32_t)mid + (int32_t)hot_sid(i >> 6, ml) * (int32_t)kHotRow);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (i & 63u) * 4u), "r"(a | (b << 8) | (c << 16) | (d << 24)));
+  }
+}
+template <int K>
+__device__ __forceinline__ uint32_t hot_next_s(uint32_t mid, uint32_t w, uint32_t e) {
+  const uint32_t x = __byte_perm(w, mid, 0x7650 + K);  // mid | byte K of w
+  uint32_t addr, v;
+  asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(e), "r"(x), "n"(RB_HOT_ROW));
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// Consume the 4 bytes of w from the highest address down; after 32 such steps bit i of `bits` is byte i.
+__device__ __forceinline__ void rev_word_s(uint32_t mid, uint32_t w, uint32_t& e, uint32_t& bits) {
+  e = hot_next_s<3>(mid, w, e); bits = __funnelshift_l(e, bits, 1);
+  e = hot_next_s<2>(mid, w, e); bits = __funnelshift_l(e, bits, 1);
+  e = hot_next_s<1>(mid, w, e); bits = __funnelshift_l(e, bits, 1);
+  e = hot_next_s<0>(mid, w, e); bits = __funnelshift_l(e, bits, 1);
+}
+__device__ __forceinline__ void rev_block16_s(uint32_t mid, const uint4& v, uint32_t& e, uint32_t& bits) {
+  rev_word_s(mid, v.w, e, bits);
+  rev_word_s(mid, v.z, e, bits);
+  rev_word_s(mid, v.y, e, bits);
+  rev_word_s(mid, v.x, e, bits);
+}
+
 // ---- TMA ring: per-lane 64-byte groups land in shared memory through cp.async.bulk ----
 // Uncoalesced per-lane LDG.128 costs one L1TEX wavefront per lane (ncu: L1/TEX at 98 %
 // with half of it global loads).  Bulk copies bypass the LSU path; each lane then
@@ -1196,14 +1242,17 @@ template <int FUSED>
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
   // shared layout: [reverse hot table][forward hot table (FUSED == 1)], 256-byte aligned,
   // then, 512-byte aligned, per warp 2 stages x 32 lanes x 64 B, then the mbarriers
-  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
-  const uint32_t fbase = tbase + hot_table_bytes(a.hot.n);
+  // (the reverse table uses signed row ids: match rows below tbase, see hot_stage_signed)
+  const uint32_t tstart = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+  const uint32_t tbase = tstart + hot_signed_below(a.hot);
+  const uint32_t fbase = tstart + hot_signed_bytes(a.hot);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t rings = (fbase + (FUSED == 1 ? hot_table_bytes(wa.fwd_hot.n) : 0u) + 511u) & ~511u;
   const uint32_t ring = rings + wid * kRingWarpBytes;
   const uint32_t bar0 = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
+  const uint32_t rml = a.hot.match_lo;
   {
-    hot_stage(a.hot, tbase);
+    hot_stage_signed(a.hot, tbase);
     if (FUSED == 1) hot_stage(wa.fwd_hot, fbase);
     if (lane == 0) {
       mbar_init(bar0, 32);
@@ -1213,7 +1262,6 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     }
     __syncthreads();
   }
-  const uint32_t thr = a.hot.match_lo;
   const uint32_t my_slot = ring + lane * kRingLaneStride;  // + stage * kRingStageBytes
   const uint64_t total = a.redo_list ? (uint64_t)*a.n_redo : a.n_seg;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -1227,27 +1275,27 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
     uint64_t t = 0, lo = 0, hi = 0, i = 0;
     uint32_t e = 0;
     uint32_t cold = 0;  // != 0: the lane is outside the hot set, in this state of the full table (e sits in the trap row)
-    auto enter = [&](uint32_t full) {
+    auto enter = [&](uint32_t full) {  // e is a signed row id (hot_sid)
       const uint32_t h = a.hot.full2hot[full];
-      if (h != 0xFFFFu) { e = h; cold = 0; }
+      if (h != 0xFFFFu) { e = hot_sid(h, rml); cold = 0; }
       else { e = 1; cold = full; }
     };
-    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[e]; };
+    auto full_state = [&]() -> uint32_t { return cold ? cold : a.hot.hot2full[hot_idx(e, rml)]; };
     auto full_step = [&](uint32_t s, uint32_t byte) -> uint32_t { return a.dfa.trans[s * a.dfa.stride + a.dfa.classes[byte]]; };
     // one 64-byte group: table steps in shared memory; a lane that ends in the trap row
     // (it met a byte outside the hot set, or was cold already) redoes the group on the full table
     auto do_group = [&](const uint4& c0, const uint4& c1, const uint4& c2, const uint4& c3, bool rec, uint32_t& bhi, uint32_t& blo) {
       const uint32_t e0 = e;
-      const uint32_t th = rec ? thr : 0xFFFFFFFFu;
       bhi = blo = 0;
-      rev_block16<16>(tbase, c3, e, bhi, th);
-      rev_block16<0>(tbase, c2, e, bhi, th);
-      rev_block16<16>(tbase, c1, e, blo, th);
-      rev_block16<0>(tbase, c0, e, blo, th);
+      rev_block16_s(tbase, c3, e, bhi);
+      rev_block16_s(tbase, c2, e, bhi);
+      rev_block16_s(tbase, c1, e, blo);
+      rev_block16_s(tbase, c0, e, blo);
+      if (!rec) bhi = blo = 0;  // warm-up bytes: states only
       if (e == 1u) {
         uint64_t bits;
         const uint32_t s1 = slow_group(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo,
-                                       cold ? cold : a.hot.hot2full[e0], c0, c1, c2, c3, &bits);
+                                       cold ? cold : a.hot.hot2full[hot_idx(e0, rml)], c0, c1, c2, c3, &bits);
         bhi = rec ? (uint32_t)(bits >> 32) : 0u;
         blo = rec ? (uint32_t)bits : 0u;
         enter(s1);
