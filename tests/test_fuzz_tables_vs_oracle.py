@@ -39,7 +39,7 @@ def _pattern(rng):
 def test_tables_equal_the_reference_pipeline_on_random_patterns():
     rng = np.random.Generator(np.random.PCG64(20261018))
     cases = rejected = 0
-    for _ in range(700):
+    for _ in range(420):
         p = _pattern(rng)
         for cls, utf8 in ((R.BytesRegex, False), (R.Regex, True)):
             try:
@@ -60,7 +60,7 @@ def test_tables_equal_the_reference_pipeline_on_random_patterns():
                 assert sim.forward_scan(t)[0] == o.shortest_match_at(t), (p, utf8, t)
                 assert sim.batch_find(t) == o.find_at(t), (p, utf8, t)
                 cases += 1
-    assert cases > 5000, (cases, rejected)
+    assert cases > 3000, (cases, rejected)
 
 
 @pytest.mark.parametrize("pat,ok", [(r"(?-u:\b)(?m:^)", False), (r"(?m:$)(?-u:\b)x?", False), (r"(?-u:\B) ??(?m:^)", False),

@@ -199,7 +199,7 @@ def test_sharded_protocol_random_patterns(looks):
     rng = np.random.Generator(np.random.PCG64(0x5AAD + looks))
     cases = 0
     for _ in range(1500):
-        if cases >= 160:
+        if cases >= 90:
             break
         pat = _pattern(rng)
         try:
@@ -217,7 +217,7 @@ def test_sharded_protocol_random_patterns(looks):
             raise
         assert got == O.OracleRegex(pat).find_iter(text), pat
         cases += 1
-    assert cases >= 150, cases
+    assert cases >= 90, cases
 
 
 def test_sharded_protocol_slice_rule_at_a_speculative_boundary():
@@ -227,7 +227,7 @@ def test_sharded_protocol_slice_rule_at_a_speculative_boundary():
     from helpers import xorshift_bytes
     import numpy as np
     rng = np.random.Generator(np.random.PCG64(7))
-    for seed in range(40):
+    for seed in range(12):
         text = xorshift_bytes(seed, 948, b"abc \n")
         assert _run_threads(pat, text, 3) == O.OracleRegex(pat).find_iter(text), seed
 
@@ -274,7 +274,7 @@ def test_sharded_shortest_match_and_set_matches():
     fixed = [(r"(?s)wat.*son", base), (r"Holmes", base), (r"zzzz", base), (r"(?m)^The$", base), (r"\d{4}", base),
              (r"(?-u:\b)s\w+e(?-u:\b)", base), (r"a$", b"x" * 700 + b"a"), (r"^x", b"x" * 600), (r"", b"q" * 600)]
     cases = saw_redo = 0
-    for it in range(140):
+    for it in range(70):
         if it < len(fixed):
             pat, text = fixed[it]
         else:
@@ -289,7 +289,7 @@ def test_sharded_shortest_match_and_set_matches():
         assert first == O.OracleRegex(pat).shortest_match_at(text), (pat, world)
         saw_redo += rounds > 0
         cases += 1
-    for it in range(40):
+    for it in range(20):
         pats = [_pattern(rng) for _ in range(int(rng.integers(2, 6)))] + ["Holmes", "(?s)a.*b"]
         try:
             R.BytesRegexSet(pats)
@@ -301,4 +301,4 @@ def test_sharded_shortest_match_and_set_matches():
         assert got == list(O.OracleRegex(pats).set_matches(text)), pats
         saw_redo += rounds > 0
         cases += 1
-    assert cases > 120 and saw_redo > 5, (cases, saw_redo)
+    assert cases > 60 and saw_redo > 3, (cases, saw_redo)
