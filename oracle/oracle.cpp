@@ -175,6 +175,88 @@ struct PikeVm {
   }
 };
 
+// ------------------------------------------------------- Pike VM with captures --
+// src/pikevm.rs:130-352 with the per-thread capture slots: what the reference runs to fill
+// `Captures` once the DFA has found the match (src/exec.rs:861-875, captures_nfa_with_match:
+// the NFA over text[..e'] from the match start, e' two characters past the match end).
+struct CapVm {
+  const Program& prog;
+  size_t n_slots;
+  struct Threads {
+    std::vector<uint32_t> dense, sparse;
+    std::vector<size_t> caps;  // [ip][slot]
+    size_t n_slots = 0;
+    void init(size_t n, size_t slots) { dense.clear(); sparse.assign(n, 0); caps.assign(n * slots, NONE); n_slots = slots; }
+    bool contains(uint32_t ip) const { uint32_t i = sparse[ip]; return i < dense.size() && dense[i] == ip; }
+    void insert(uint32_t ip) { sparse[ip] = (uint32_t)dense.size(); dense.push_back(ip); }
+  };
+  struct Frame { bool is_cap; uint32_t ip_or_slot; size_t pos; };
+  std::vector<Frame> stack;
+  explicit CapVm(const Program& p) : prog(p), n_slots(2 * (size_t)p.n_captures) {}
+
+  void add(Threads& l, std::vector<size_t>& tc, uint32_t ip0, const uint8_t* t, size_t n, size_t at) {  // pikevm.rs:274-352
+    stack.push_back({false, ip0, 0});
+    while (!stack.empty()) {
+      Frame f = stack.back();
+      stack.pop_back();
+      if (f.is_cap) { tc[f.ip_or_slot] = f.pos; continue; }
+      uint32_t ip = f.ip_or_slot;
+      for (;;) {
+        if (l.contains(ip)) break;
+        l.insert(ip);
+        const Inst& in = prog.insts[ip];
+        if (in.op == Op::EmptyLook) {
+          if (!PikeVm::look_ok(in.look, t, n, at)) break;
+          ip = in.a;
+        } else if (in.op == Op::Save) {
+          if (in.b < n_slots) {
+            stack.push_back({true, in.b, tc[in.b]});
+            tc[in.b] = at;
+          }
+          ip = in.a;
+        } else if (in.op == Op::Split) {
+          stack.push_back({false, in.b, 0});
+          ip = in.a;
+        } else {
+          for (size_t k = 0; k < n_slots; k++) l.caps[ip * n_slots + k] = tc[k];
+          break;
+        }
+      }
+    }
+  }
+  bool exec(const uint8_t* t, size_t n, size_t start, std::vector<size_t>& slots) {  // pikevm.rs:130-228, one regex
+    Threads clist, nlist;
+    clist.init(prog.insts.size(), n_slots);
+    nlist.init(prog.insts.size(), n_slots);
+    slots.assign(n_slots, NONE);
+    std::vector<size_t> tc(n_slots, NONE);
+    bool matched = false;
+    for (size_t at = start;; at++) {
+      if (clist.dense.empty()) {
+        if (matched || at != start) break;  // the capture program is anchored at `start`
+        add(clist, tc, prog.start_anchored, t, n, at);
+      }
+      for (size_t i = 0; i < clist.dense.size(); i++) {
+        const uint32_t ip = clist.dense[i];
+        const Inst& in = prog.insts[ip];
+        if (in.op == Op::Match) {
+          for (size_t k = 0; k < n_slots; k++) slots[k] = clist.caps[ip * n_slots + k];
+          matched = true;
+          break;  // leftmost-first
+        }
+        if (in.op == Op::Bytes && at < n && in.lo <= t[at] && t[at] <= in.hi) {
+          std::vector<size_t> caps_of(clist.caps.begin() + ip * n_slots, clist.caps.begin() + (ip + 1) * n_slots);
+          add(nlist, caps_of, in.a, t, n, at + 1);
+        }
+      }
+      if (at >= n) break;
+      std::swap(clist, nlist);
+      nlist.dense.clear();
+    }
+    return matched;
+  }
+};
+
 // ----------------------------------------------------------------- lazy DFA --
 // src/dfa.rs.  States are created on demand and cached for the lifetime of the
 // object (the reference's cache flush / give-up heuristics, dfa.rs:1282-1320,
@@ -414,6 +496,7 @@ struct LazyDfa {
 struct Regex {
   std::vector<std::string> pats;
   Program nfa, dfa, dfa_rev;
+  Program caps;  // anchored forward program WITH Save instructions for every group (captures)
   std::unique_ptr<LazyDfa> fwd, rev;
   bool only_utf8 = false;
   std::string error;
@@ -490,6 +573,20 @@ struct Regex {
     }
     return fwd->forward_many(t, n, start, m);
   }
+  // exec.rs:527-590 read_captures_at with MatchType::Dfa: the DFA pipeline finds the match, the
+  // NFA fills the groups over the narrowed window (exec.rs:861-875).
+  bool captures_at(const uint8_t* t, size_t n, size_t start, std::vector<size_t>& slots) {
+    size_t s, e;
+    if (!find_at(0, t, n, start, &s, &e)) return false;
+    auto next_utf8 = [&](size_t i) {  // src/utf8.rs:24-40
+      if (i >= n) return i + 1;
+      const uint8_t b = t[i];
+      return i + (b <= 0x7F ? 1 : b <= 0xDF ? 2 : b <= 0xEF ? 3 : 4);
+    };
+    const size_t e2 = std::min(next_utf8(next_utf8(e)), n);
+    CapVm vm(caps);
+    return vm.exec(t, e2, s, slots);
+  }
   size_t next_after_empty(const uint8_t* t, size_t n, size_t i) const {
     if (!only_utf8) return i + 1;  // exec.rs:375-377
     if (i >= n) return i + 1;      // utf8.rs:24-40
@@ -516,6 +613,11 @@ static Regex* build(const std::vector<std::string>& pats, uint32_t flags, bool o
   o.size_limit = size_limit;
   o.unanchored_prefix = false; o.saves = false;
   if (!rb::compile(exprs, o, &re->nfa, &err)) { re->error = err.msg; return re.release(); }
+  if (exprs.size() == 1) {
+    o.saves = true;
+    if (!rb::compile(exprs, o, &re->caps, &err)) { re->error = err.msg; return re.release(); }
+    o.saves = false;
+  }
   o.unanchored_prefix = true;
   if (!rb::compile(exprs, o, &re->dfa, &err)) { re->error = err.msg; return re.release(); }
   o.reverse = true; o.unanchored_prefix = false;
@@ -623,6 +725,15 @@ int oracle_set_matches(void* h, int engine, const uint8_t* t, size_t n, size_t s
   bool any = re->pats.empty() ? false : re->many_at(engine, t, n, start, m);
   for (size_t i = 0; i < m.size(); i++) out[i] = m[i];
   return any;
+}
+// Captures::get(i) for every group: slots[2i], slots[2i+1] (SIZE_MAX = the group did not take part).
+// Returns the number of groups (incl. group 0) on a match, 0 otherwise.
+size_t oracle_captures_at(void* h, const uint8_t* t, size_t n, size_t start, size_t* slots, size_t max_slots) {
+  auto* re = (oracle::Regex*)h;
+  std::vector<size_t> v;
+  if (re->pats.size() != 1 || !re->captures_at(t, n, start, v)) return 0;
+  for (size_t k = 0; k < v.size() && k < max_slots; k++) slots[k] = v[k];
+  return v.size() / 2;
 }
 size_t oracle_num_patterns(void* h) { return ((oracle::Regex*)h)->pats.size(); }
 

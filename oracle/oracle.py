@@ -38,6 +38,8 @@ def lib():
         L.oracle_find_iter.restype = c_size_t
         L.oracle_find_iter.argtypes = [c_void_p, c_int, c_char_p, c_size_t, POINTER(c_size_t), c_size_t]
         L.oracle_set_matches.argtypes = [c_void_p, c_int, c_char_p, c_size_t, c_size_t, POINTER(c_uint8)]
+        L.oracle_captures_at.restype = c_size_t
+        L.oracle_captures_at.argtypes = [c_void_p, c_char_p, c_size_t, c_size_t, POINTER(c_size_t), c_size_t]
         L.oracle_num_patterns.restype = c_size_t
         L.oracle_num_patterns.argtypes = [c_void_p]
         L.oracle_count_parallel.restype = c_size_t
@@ -90,6 +92,15 @@ class OracleRegex:
 
     def is_match_at(self, text, start=0, engine=ENGINE_DFA):
         return bool(lib().oracle_is_match_at(self._h, engine, text, len(text), start))
+
+    def captures_at(self, text, start=0):
+        """`Regex::captures` (group spans, None for groups that did not take part), or None."""
+        buf = (c_size_t * 512)()
+        g = lib().oracle_captures_at(self._h, text, len(text), start, buf, 512)
+        if g == 0:
+            return None
+        none = (1 << 64) - 1
+        return [None if buf[2 * i] == none else (buf[2 * i], buf[2 * i + 1]) for i in range(g)]
 
     def find_iter(self, text, engine=ENGINE_DFA, cap=None):
         n = lib().oracle_find_iter(self._h, engine, text, len(text), None, 0) if cap is None else cap

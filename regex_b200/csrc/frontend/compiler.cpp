@@ -416,7 +416,18 @@ struct Compiler {
         p.has_unicode_word_boundary = true; set_word_boundary(); return c_look(Look::NotWordBoundary);
       case EK::WordBoundaryAscii: set_word_boundary(); return c_look(Look::WordBoundaryAscii);
       case EK::NotWordBoundaryAscii: set_word_boundary(); return c_look(Look::NotWordBoundaryAscii);
-      case EK::Group: return c(e.es[0]);  // captures are out of scope (DFA programs drop Save)
+      case EK::Group: {  // compile.rs:345-362: Save pairs only in the capture program (DFA programs drop them)
+        if (!opt.saves || e.cap <= 0 || rev) return c(e.es[0]);
+        p.n_captures = std::max(p.n_captures, e.cap + 1);
+        Inst s0; s0.op = Op::Save; s0.a = kUnset; s0.b = 2 * (uint32_t)e.cap;
+        const uint32_t a = emit(s0);
+        Patch q = c(e.es[0]);
+        p.insts[a].a = q.entry;
+        Inst s1; s1.op = Op::Save; s1.a = kUnset; s1.b = 2 * (uint32_t)e.cap + 1;
+        const uint32_t b = emit(s1);
+        fill(q.holes, b);
+        return {{{b, 0}}, a};
+      }
       case EK::Concat: {
         std::vector<const Expr*> es;
         if (rev) for (size_t k = e.es.size(); k-- > 0;) es.push_back(&e.es[k]);

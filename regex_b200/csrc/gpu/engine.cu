@@ -143,6 +143,8 @@ Regex::~Regex() {
   for (auto*& d : dev_) { delete d; d = nullptr; }
   if (pinned_) cudaFreeHost(pinned_);
   for (void* e : timing_events_) if (e) cudaEventDestroy((cudaEvent_t)e);
+  if (fork_event_) cudaEventDestroy((cudaEvent_t)fork_event_);
+  if (join_event_) cudaEventDestroy((cudaEvent_t)join_event_);
   if (copy_stream_) cudaStreamDestroy((cudaStream_t)copy_stream_);
   if (back_stream_) cudaStreamDestroy((cudaStream_t)back_stream_);
   if (own_stream_) cudaStreamDestroy((cudaStream_t)own_stream_);
@@ -926,6 +928,14 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
   RB_CUDA(allow_smem(scan_fwd_reduce, smem));
   // whole warps of full segments go to the fast kernel; segment 0, the ragged end and the EOF step stay generic
   const uint64_t n_full = (std::min(limit, n) - start) / seg;
+  bool fast_launched = false;
+  if (!fork_event_) {
+    cudaEvent_t e1, e2;
+    RB_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    RB_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    fork_event_ = e1;
+    join_event_ = e2;
+  }
   if (fast_ok && seg % 64 == 0 && a.warm <= seg && n_full >= 34) {
     const uint64_t skip_lo = 1, skip_hi = 1 + (n_full - 1) / 32 * 32;
     CUtensorMap tmap;
@@ -943,12 +953,33 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
       a.skip_hi = skip_hi;
       const size_t fsm = fast_scan_smem(hot_bytes(fwd->hot.n));
       RB_CUDA(cudaFuncSetAttribute(scan_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      RB_CUDA(cudaEventRecord((cudaEvent_t)fork_event_, st));  // the side stream starts once everything before this point is done
       scan_fwd_fast<<<grid_for(skip_hi - skip_lo, 1024, 1), 1024, fsm, st>>>(a, tmap);
       RB_LAUNCH_CHECK("scan_fwd_fast");
+      fast_launched = true;
     }
   }
-  scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
-  RB_LAUNCH_CHECK("scan_fwd_reduce");
+  // The generic kernel takes what the fast one leaves (segment 0, the ragged end, the end-of-text
+  // step): a handful of 4 KiB segments walked by single threads, ~0.25 ms of pure latency (ncu
+  // profiles/r02: 10 % issue, 3 % of the warps).  It runs beside the fast kernel on a second stream.
+  if (fast_launched) {
+    if (!copy_stream_) {
+      cudaStream_t s1, s2;
+      RB_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+      RB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      copy_stream_ = s1;
+      back_stream_ = s2;
+    }
+    cudaStream_t side = (cudaStream_t)back_stream_;
+    RB_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)fork_event_, 0));
+    scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, side>>>(a);
+    RB_LAUNCH_CHECK("scan_fwd_reduce");
+    RB_CUDA(cudaEventRecord((cudaEvent_t)join_event_, side));
+    RB_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)join_event_, 0));
+  } else {
+    scan_fwd_reduce<<<grid_for(n_seg, tuning.block, tuning.blocks_per_sm), tuning.block, smem, st>>>(a);
+    RB_LAUNCH_CHECK("scan_fwd_reduce");
+  }
   for (uint32_t round = 0;; round++) {
     RB_CUDA(cudaMemsetAsync(counters, 0, 4, st));
     verify_segments<<<grid_for(n_seg, 256, 8), 256, 0, st>>>(a.guess, a.fin, n_seg, 0, redo, counters);
@@ -985,7 +1016,7 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
 }
 
 // is_match / shortest_match / RegexSet::matches over one haystack, in waves of growing size
-// (32 MiB, x8 each) so that the search stops early the way the reference does:
+// (64 MiB, x16 each) so that the search stops early the way the reference does:
 //   - a single pattern stops at the first wave that holds a match (dfa.rs:658-667, quit_after_match);
 //   - a set stops once every pattern has matched (dfa.rs:675-682);
 //   - a set ALSO narrows: patterns that matched in the first waves need no further tracking,
@@ -993,7 +1024,7 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
 //     open (usually a handful of rare ones: small, shared-memory resident, fast kernel) instead
 //     of the product automaton of all of them.  That automaton knows nothing about the bytes
 //     already passed, so it scans from `start` again; narrowing happens after the first two
-//     waves only, which bounds the repeated work to 1/8 of the haystack.
+//     waves only, which bounds the repeated work to 1/16 of the haystack.
 // end: positions [start, end) are searched (n + 1 = to the end of the text, the default); entry:
 // exact automaton state at `start` (a shard, kNoEntry = a fresh search); *exit_state: the exact
 // state after the last position (what the right-hand shard must be entered with).
@@ -1056,7 +1087,7 @@ int Regex::forward_reduce(const uint8_t* d_text, uint64_t n, uint64_t start, boo
     }
     lo = limit;
     entry = exit_state;
-    wave *= 8;
+    wave *= 16;
   }
   return 0;
 }

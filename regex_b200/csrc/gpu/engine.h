@@ -34,7 +34,7 @@ struct Tuning {
   uint32_t warm = 0;       // 0 = automatic (bounded patterns: max match length; else 128)
   uint32_t block = 256;
   uint32_t blocks_per_sm = 8;
-  uint64_t wave0 = 32ull << 20;  // first wave of a forward search in bytes (x8 per wave); 0 = one wave
+  uint64_t wave0 = 64ull << 20;  // first wave of a forward search in bytes (x16 per wave); 0 = one wave
   bool narrow_sets = true;
   int prefilter = 1;             // literal_scan instead of the DFA scan: 0 never, 1 when the scanned byte is estimated rare enough
                                  // to win (one byte, <= ~0.12 % of the haystack), 2 whenever the pattern qualifies structurally       // RegexSet::matches: continue with the automaton of the still-unmatched patterns
@@ -193,6 +193,7 @@ class Regex {
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};
+  void *fork_event_ = nullptr, *join_event_ = nullptr;  // forward scans: the generic edge kernel runs beside the fast one
   int pf_state_ = 0;               // 0 = not decided yet, 1 = prefilter applies, -1 = it does not
   uint32_t pf_freq_ = 0;           // estimated frequency of the scanned bytes, parts per 65536
   std::vector<uint32_t> pf_words_; // PfArgs image (engine.cu)

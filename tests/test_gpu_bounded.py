@@ -106,6 +106,7 @@ def test_forward_search_waves_and_early_exit():
     d = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
     for pat, exp in [(r"NEEDLE", len(a) + 3 + 6), (r"quick", text.find(b"quick") + 5), (r"zebra", None), (r"dog \d+\nxx", len(a) + 2)]:
         r = R.BytesRegex(pat)
+        r.set_option("wave0", 32 << 20)
         assert r.shortest_match_device(d) == exp, pat
         waves = r.last_stats()["waves"]
         assert waves == (1 if pat == "quick" else 2), (pat, waves)
