@@ -82,6 +82,18 @@ bool rure_b200_split(rure *re, const uint8_t *haystack, size_t length, int has_l
 bool rure_b200_split_device(rure *re, const uint8_t *d_haystack, size_t length, int has_limit,
                             size_t limit, rure_match *d_out, size_t cap, size_t *n_pieces);
 
+/* ---- capture groups (src/exec.rs:527-590 read_captures_at; rure_find_captures & co in rure.h use
+ * the same path).  The DFA path finds each match; one GPU thread per match then runs the
+ * reference's NFA simulation with slots (src/pikevm.rs:130-352) over the narrowed window
+ * (src/exec.rs:861-875).  slots: 2 * rure_b200_captures_len(re) entries per match -- start, end of
+ * every group, SIZE_MAX where a group did not take part. */
+size_t rure_b200_captures_len(rure *re);
+bool rure_b200_captures(rure *re, const uint8_t *haystack, size_t length, size_t start, bool *found,
+                        size_t *slots);
+/* every match of find_iter with its groups: slots[min(cap, *n_matches)][2 * n_groups] */
+bool rure_b200_captures_all(rure *re, const uint8_t *haystack, size_t length, size_t *slots, size_t cap,
+                            size_t *n_matches, size_t *n_groups);
+
 /* ---- batched records: record i = haystack[offsets[i], offsets[i+1]) -------- */
 /* out_bits: bit (i % 8) of byte (i / 8); (n_records + 7) / 8 bytes */
 bool rure_b200_is_match_batch(rure *re, const uint8_t *haystack, const uint64_t *offsets,

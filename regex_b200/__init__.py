@@ -94,6 +94,10 @@ def _load():
         "rure_b200_replace_device": (c_bool, [vp, vp, sz, c_char_p, sz, c_int, sz, vp, sz, POINTER(sz)]),
         "rure_b200_split": (c_bool, [vp, u8p, sz, c_int, sz, vp, sz, POINTER(sz)]),
         "rure_b200_split_device": (c_bool, [vp, vp, sz, c_int, sz, vp, sz, POINTER(sz)]),
+        "rure_b200_captures_len": (sz, [vp]),
+        "rure_b200_captures": (c_bool, [vp, u8p, sz, sz, POINTER(c_bool), vp]),
+        "rure_b200_captures_all": (c_bool, [vp, u8p, sz, vp, sz, POINTER(sz), POINTER(sz)]),
+        "rure_capture_name_index": (ctypes.c_int32, [vp, c_char_p]),
         "rure_b200_find_all": (c_bool, [vp, u8p, sz, vp, sz, POINTER(sz)]),
         "rure_b200_count_all": (c_bool, [vp, u8p, sz, POINTER(sz)]),
         "rure_b200_set_matches_mask": (c_bool, [vp, u8p, sz, sz, POINTER(c_uint64)]),
@@ -279,6 +283,46 @@ class _Compiled:
             if total.value <= cap:
                 return out[: total.value]
             cap = total.value
+
+    # ---- capture groups (re_bytes.rs:226-262 captures / captures_iter) ----------------
+    def captures_len(self):
+        """Number of capture groups, group 0 included (`Regex::captures_len`)."""
+        return int(_lib.rure_b200_captures_len(self._h))
+
+    def capture_name_index(self, name):
+        i = int(_lib.rure_capture_name_index(self._h, name.encode("utf-8")))
+        return None if i < 0 else i
+
+    def captures_at(self, text, start=0):
+        """`Regex::captures`: [(start, end) or None for every group], or None without a match."""
+        p, n, keep = _buf(text)
+        g = self.captures_len()
+        slots = np.empty(2 * g, dtype=np.uint64)
+        found = c_bool()
+        if not _lib.rure_b200_captures(self._h, p, n, start, byref(found), slots.ctypes.data):
+            raise Error(_last_error())
+        if not found.value:
+            return None
+        none = np.uint64(0xFFFFFFFFFFFFFFFF)
+        return [None if slots[2 * i] == none else (int(slots[2 * i]), int(slots[2 * i + 1])) for i in range(g)]
+
+    def captures(self, text):
+        return self.captures_at(text, 0)
+
+    def captures_all(self, text):
+        """`Regex::captures_iter` in one pass: uint64 [n_matches, n_groups, 2], 2**64-1 where a group did not take part."""
+        p, n, keep = _buf(text)
+        m, g = c_size_t(), c_size_t()
+        if not _lib.rure_b200_captures_all(self._h, p, n, None, 0, byref(m), byref(g)):
+            raise Error(_last_error())
+        out = np.empty((max(m.value, 1), g.value, 2), dtype=np.uint64)
+        if m.value and not _lib.rure_b200_captures_all(self._h, p, n, out.ctypes.data, m.value, byref(m), byref(g)):
+            raise Error(_last_error())
+        return out[:m.value]
+
+    def captures_iter(self, text):
+        none = 0xFFFFFFFFFFFFFFFF
+        return [[None if int(a) == none else (int(a), int(b)) for a, b in row] for row in self.captures_all(text)]
 
     # ---- replace / split (re_bytes.rs:316-360, 440-535) -----------------------------
     def replacen(self, text, limit, rep, expand=True):

@@ -25,8 +25,9 @@ struct rure_set {
   Regex* re = nullptr;
 };
 struct rure_captures {
+  size_t n_groups = 1;
   bool has = false;
-  rure_match m{0, 0};
+  std::vector<uint64_t> slots;  // 2 per group, ~0 = the group did not take part
 };
 struct rure_iter {
   rure* re;
@@ -39,9 +40,13 @@ struct rure_iter {
   bool cached = false;
   std::vector<rure_match> spans;
   size_t next = 0;
+  std::vector<uint64_t> slots;  // capture slots of every cached span (filled by the first rure_iter_next_captures)
+  bool have_slots = false;
 };
 struct rure_iter_capture_names {
-  int unused;
+  std::vector<std::string> names;  // one per group, "" = unnamed
+  size_t next = 0;
+  std::vector<char*> handed_out;
 };
 
 static thread_local std::string g_last_error;
@@ -126,15 +131,39 @@ bool rure_find(rure* re, const uint8_t* haystack, size_t length, size_t start, r
   return found;
 }
 bool rure_find_captures(rure* re, const uint8_t* haystack, size_t length, size_t start, rure_captures* captures) {
-  rure_match m;
-  bool found = rure_find(re, haystack, length, start, &m);
-  if (captures) { captures->has = found; if (found) captures->m = m; }
+  bool found = false;
+  std::vector<uint64_t> slots(2 * (size_t)re->re->n_groups(), ~0ull);
+  if (!ok(re->re, re->re->captures_at_host(haystack, length, start, &found, slots.data()))) die("rure_find_captures");
+  if (captures) {
+    captures->has = found;
+    captures->slots = found ? slots : std::vector<uint64_t>(slots.size(), ~0ull);
+  }
   return found;
 }
-int32_t rure_capture_name_index(rure*, const char*) { return -1; }
-rure_iter_capture_names* rure_iter_capture_names_new(rure*) { return new rure_iter_capture_names(); }
-void rure_iter_capture_names_free(rure_iter_capture_names* it) { delete it; }
-bool rure_iter_capture_names_next(rure_iter_capture_names*, char**) { return false; }
+int32_t rure_capture_name_index(rure* re, const char* name) {
+  if (!name) return -1;
+  for (const auto& g : re->re->group_names())
+    if (g.first == name) return g.second;
+  return -1;
+}
+rure_iter_capture_names* rure_iter_capture_names_new(rure* re) {
+  auto* it = new rure_iter_capture_names();
+  it->names.assign((size_t)re->re->n_groups(), "");
+  for (const auto& g : re->re->group_names()) it->names[(size_t)g.second] = g.first;
+  return it;
+}
+void rure_iter_capture_names_free(rure_iter_capture_names* it) {
+  if (!it) return;
+  for (char* p : it->handed_out) std::free(p);
+  delete it;
+}
+bool rure_iter_capture_names_next(rure_iter_capture_names* it, char** name) {
+  if (!name || it->next >= it->names.size()) return false;
+  char* p = strdup(it->names[it->next++].c_str());  // owned by the iterator, like the reference's CString::into_raw list
+  it->handed_out.push_back(p);
+  *name = p;
+  return true;
+}
 
 rure_iter* rure_iter_new(rure* re) {
   rure_iter* it = new rure_iter();
@@ -181,19 +210,57 @@ bool rure_iter_next(rure_iter* it, const uint8_t* haystack, size_t length, rure_
 }
 bool rure_iter_next_captures(rure_iter* it, const uint8_t* haystack, size_t length, rure_captures* captures) {
   rure_match m;
-  bool found = rure_iter_next(it, haystack, length, &m);
-  if (captures) { captures->has = found; if (found) captures->m = m; }
-  return found;
-}
-
-rure_captures* rure_captures_new(rure*) { return new rure_captures(); }
-void rure_captures_free(rure_captures* c) { delete c; }
-bool rure_captures_at(rure_captures* c, size_t i, rure_match* match) {
-  if (i != 0 || !c->has) return false;
-  if (match) *match = c->m;
+  const size_t before = it->next;
+  const bool found = rure_iter_next(it, haystack, length, &m);
+  if (!captures) return found;
+  const size_t ns = 2 * (size_t)it->re->re->n_groups();
+  captures->has = found;
+  captures->slots.assign(ns, ~0ull);
+  if (!found) return false;
+  if (!it->have_slots) {  // the groups of every cached span in one pass
+    uint64_t total = 0;
+    it->slots.assign(std::max<size_t>(it->spans.size(), 1) * ns, ~0ull);
+    if (!ok(it->re->re, it->re->re->captures_all_host(haystack, length, it->slots.data(), it->spans.size(), &total))) die("rure_iter_next_captures");
+    it->have_slots = true;
+  }
+  // the cached spans are find_iter from the iterator's position at caching time; the capture pass saw the same list
+  size_t idx = it->next - 1;
+  (void)before;
+  if (it->slots.size() >= (idx + 1) * ns && it->slots[idx * ns] == m.start && it->slots[idx * ns + 1] == m.end) {
+    std::copy(it->slots.begin() + idx * ns, it->slots.begin() + (idx + 1) * ns, captures->slots.begin());
+  } else {  // an iterator that started mid-haystack: ask for this match alone
+    bool f2 = false;
+    if (!ok(it->re->re, it->re->re->captures_at_host(haystack, length, m.start, &f2, captures->slots.data()))) die("rure_iter_next_captures");
+  }
   return true;
 }
-size_t rure_captures_len(rure_captures*) { return 1; }
+
+rure_captures* rure_captures_new(rure* re) {
+  auto* c = new rure_captures();
+  c->n_groups = (size_t)re->re->n_groups();
+  c->slots.assign(2 * c->n_groups, ~0ull);
+  return c;
+}
+void rure_captures_free(rure_captures* c) { delete c; }
+bool rure_captures_at(rure_captures* c, size_t i, rure_match* match) {
+  if (!c->has || i >= c->n_groups || c->slots[2 * i] == ~0ull || c->slots[2 * i + 1] == ~0ull) return false;
+  if (match) { match->start = c->slots[2 * i]; match->end = c->slots[2 * i + 1]; }
+  return true;
+}
+size_t rure_captures_len(rure_captures* c) { return c->n_groups; }
+
+// every match with all its groups: slots[i][2 * n_groups], SIZE_MAX where a group did not take part
+bool rure_b200_captures_all(rure* re, const uint8_t* haystack, size_t length, size_t* slots, size_t cap, size_t* n_matches, size_t* n_groups) {
+  uint64_t m = 0;
+  if (n_groups) *n_groups = (size_t)re->re->n_groups();
+  const bool r = ok(re->re, re->re->captures_all_host(haystack, length, (uint64_t*)slots, slots ? cap : 0, &m));
+  if (n_matches) *n_matches = m;
+  return r;
+}
+bool rure_b200_captures(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, size_t* slots) {
+  return ok(re->re, re->re->captures_at_host(haystack, length, start, found, (uint64_t*)slots));
+}
+size_t rure_b200_captures_len(rure* re) { return (size_t)re->re->n_groups(); }
 
 rure_options* rure_options_new(void) { return new rure_options(); }
 void rure_options_free(rure_options* o) { delete o; }

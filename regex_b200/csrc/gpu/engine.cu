@@ -105,7 +105,7 @@ Regex* Regex::compile(const std::vector<std::string>& patterns, const CompileOpt
       stack.pop_back();
       if (x->kind == rb::EK::Group && x->cap > 0) {
         re->n_groups_ = std::max(re->n_groups_, x->cap + 1);
-        if (!x->name.empty()) re->group_names_.push_back(x->name);
+        if (!x->name.empty()) { re->group_names_.push_back(x->name); re->group_name_index_.emplace_back(x->name, x->cap); }
       }
       for (const rb::Expr& c : x->es) stack.push_back(&c);
     }
@@ -1478,6 +1478,102 @@ int Regex::split_host(const uint8_t* text, uint64_t n, bool has_limit, uint64_t 
   if (!d_p) return fail("out of device memory (pieces)");
   if ((rc = split_device(d, n, has_limit, limit, d_p, k, n_pieces))) return rc;
   RB_CUDA(d2h(pieces, d_p, k * 16));
+  return 0;
+}
+
+// ------------------------------------------------------------ capture groups ----
+int Regex::ensure_capture_program() {
+  if (cap_n_insts_) return 0;
+  if (is_set_ || patterns_.size() != 1) return fail("captures require exactly one pattern (exec.rs:587-589)");
+  if (int rc = init_device()) return rc;
+  rb::CompileOptions co;
+  co.only_utf8 = opt_.only_utf8;
+  co.size_limit = opt_.size_limit;
+  co.unanchored_prefix = false;
+  co.saves = true;
+  rb::Program prog;
+  rb::Error err;
+  if (!rb::compile(exprs_, co, &prog, &err)) return fail(err.msg);
+  std::vector<NfaInst> insts(prog.insts.size());
+  for (size_t i = 0; i < insts.size(); i++) {
+    const rb::Inst& in = prog.insts[i];
+    insts[i].op_look_lo_hi = (uint32_t)in.op | ((uint32_t)in.look << 8) | ((uint32_t)in.lo << 16) | ((uint32_t)in.hi << 24);
+    insts[i].a = in.a;
+    insts[i].b = in.b;
+  }
+  NfaInst* d = (NfaInst*)cap_insts_.ensure(insts.size() * sizeof(NfaInst));
+  if (!d) return fail("out of device memory (capture program)");
+  RB_CUDA(cudaMemcpyAsync(d, insts.data(), insts.size() * sizeof(NfaInst), cudaMemcpyHostToDevice, (cudaStream_t)stream_));
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  cap_n_insts_ = (uint32_t)insts.size();
+  cap_start_ = prog.start_anchored;
+  return 0;
+}
+
+int Regex::captures_device(const uint8_t* d_text, uint64_t n, const uint64_t* d_spans, uint64_t m, uint64_t* d_slots) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  if (int rc = ensure_capture_program()) return rc;
+  if (m == 0) return 0;
+  CapArgs a{};
+  a.insts = (const NfaInst*)cap_insts_.ptr;
+  a.n_insts = cap_n_insts_;
+  a.start_ip = cap_start_;
+  a.n_slots = 2 * (uint32_t)n_groups_;
+  a.text = d_text;
+  a.n = n;
+  a.spans = d_spans;
+  a.n_matches = m;
+  a.slots = d_slots;
+  // kernels.cu pike_captures: two slot tables, thread caps, stack positions, four index arrays, stack tags
+  const uint64_t ni = a.n_insts, ns = a.n_slots;
+  a.per_thread = (2 * ni * ns * 8 + ns * 8 + (2 * ni + 4) * 8 + 4 * ni * 4 + (2 * ni + 4) * 4 + 15) / 16 * 16;
+  if (a.per_thread > (8u << 20)) return fail("the pattern is too large for capture extraction on the device (program x groups)");
+  uint64_t threads = std::min<uint64_t>((m + 63) / 64 * 64, 16384);
+  while (threads > 64 && threads * a.per_thread > (1ull << 30)) threads /= 2;
+  a.scratch = (uint8_t*)cap_scratch_.ensure(threads * a.per_thread);
+  if (!a.scratch) return fail("out of device memory (capture scratch)");
+  pike_captures<<<(uint32_t)(threads / 64), 64, 0, (cudaStream_t)stream_>>>(a);
+  RB_LAUNCH_CHECK("pike_captures");
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  return 0;
+}
+
+int Regex::captures_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* slots) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  uint64_t s = 0, e = 0;
+  if (int rc = find_at_host(text, n, start, found, &s, &e)) return rc;  // the DFA path finds the match (exec.rs:547-556)
+  if (!*found) return 0;
+  // the window the capture pass reads: one byte of look-behind, two characters of look-ahead
+  uint8_t* d = (uint8_t*)text_.ensure(n + 64);
+  const uint64_t lo = s ? s - 1 : 0, hi = std::min<uint64_t>(n, e + 8);
+  cudaStream_t st = (cudaStream_t)stream_;
+  RB_CUDA(cudaMemcpyAsync(d + lo, text + lo, hi - lo, cudaMemcpyHostToDevice, st));
+  uint64_t* d_span = (uint64_t*)cap_span_.ensure(16);
+  const uint32_t ns = 2 * (uint32_t)n_groups_;
+  uint64_t* d_slots = (uint64_t*)cap_slots_.ensure(ns * 8);
+  if (!d_span || !d_slots) return fail("out of device memory (captures)");
+  const uint64_t span[2] = {s, e};
+  RB_CUDA(cudaMemcpyAsync(d_span, span, 16, cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  if (int rc = captures_device(d, hi, d_span, 1, d_slots)) return rc;  // hi < n only shortens a haystack the window never reaches...
+  RB_CUDA(d2h(slots, d_slots, ns * 8));
+  return 0;
+}
+
+int Regex::captures_all_host(const uint8_t* text, uint64_t n, uint64_t* slots, uint64_t cap, uint64_t* m) {
+  std::lock_guard<std::recursive_mutex> lock(mu_);
+  int rc;
+  const uint8_t* d = upload_text(text, n, &rc);
+  if (rc) return rc;
+  uint64_t* spans;
+  if ((rc = all_spans_device(d, n, &spans, m))) return rc;
+  const uint64_t k = std::min(cap, *m);
+  if (!slots || !k) return 0;
+  const uint32_t ns = 2 * (uint32_t)n_groups_;
+  uint64_t* d_slots = (uint64_t*)cap_slots_.ensure(k * ns * 8);
+  if (!d_slots) return fail("out of device memory (captures)");
+  if ((rc = captures_device(d, n, spans, k, d_slots))) return rc;
+  RB_CUDA(d2h(slots, d_slots, k * ns * 8));
   return 0;
 }
 

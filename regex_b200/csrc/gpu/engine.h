@@ -117,6 +117,16 @@ class Regex {
   int split_device(const uint8_t* d_text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* d_pieces, uint64_t cap, uint64_t* n_pieces);
   int split_host(const uint8_t* text, uint64_t n, bool has_limit, uint64_t limit, uint64_t* pieces, uint64_t cap, uint64_t* n_pieces);
 
+  // ---- capture groups (exec.rs:527-590 read_captures_at, :861-875 captures_nfa_with_match) ----
+  int n_groups() const { return n_groups_; }
+  const std::vector<std::pair<std::string, int>>& group_names() const { return group_name_index_; }
+  // slots of every match in d_spans: d_slots[m][2 * n_groups], kNone where a group did not take part
+  int captures_device(const uint8_t* d_text, uint64_t n, const uint64_t* d_spans, uint64_t m, uint64_t* d_slots);
+  // Regex::captures at `start` on a host haystack: slots[2 * n_groups]
+  int captures_at_host(const uint8_t* text, uint64_t n, uint64_t start, bool* found, uint64_t* slots);
+  // every match with its groups: slots[min(cap, *m)][2 * n_groups]
+  int captures_all_host(const uint8_t* text, uint64_t n, uint64_t* slots, uint64_t cap, uint64_t* m);
+
   // ---- batched records, device-resident text + offsets[n_rec+1] --------------
   int is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint32_t* d_bits);
   int find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, uint64_t n_rec, uint64_t* d_spans, uint32_t* d_bits);
@@ -155,6 +165,7 @@ class Regex {
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
   int all_spans_device(const uint8_t* d_text, uint64_t n, uint64_t** d_spans, uint64_t* m);
+  int ensure_capture_program();
   int replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit, uint64_t* out_len);
   int replace_emit(uint8_t* d_out, uint64_t out_cap);
   bool plan_prefilter();  // fills pf_words_ (launch.h PfArgs) when every match has one of <= 4 bytes at a fixed offset
@@ -190,6 +201,9 @@ class Regex {
   std::vector<uint8_t> rep_args_, rep_lits_;  // launch.h ReplaceArgs image + literal bytes of the pending replace call
   int n_groups_ = 1;                      // capture groups incl. group 0
   std::vector<std::string> group_names_;  // names of the named groups
+  std::vector<std::pair<std::string, int>> group_name_index_;  // (name, group index)
+  DeviceBuf cap_insts_, cap_scratch_, cap_slots_, cap_span_;
+  uint32_t cap_n_insts_ = 0, cap_start_ = 0;  // capture program on the device (0 = not uploaded yet)
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};

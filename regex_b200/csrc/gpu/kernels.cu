@@ -1963,6 +1963,126 @@ __global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t
   }
 }
 
+// ----------------------------------------------------------- capture groups ----
+// The reference fills `Captures` by running its NFA simulation over the window the DFA
+// narrowed down: from the match start to two characters past the match end
+// (src/exec.rs:861-875 captures_nfa_with_match).  Same here: one thread per match runs the Pike
+// VM of src/pikevm.rs:130-352 (thread lists in priority order, per-thread slot arrays, the
+// explicit stack that restores slots behind a Save) over the capture program -- the anchored
+// forward program compiled WITH Save instructions.  Scratch lives in global memory, one slab per
+// resident thread; this is a per-match O(window x program) pass, not a streaming kernel.
+__device__ __forceinline__ bool look_holds(uint32_t look, const uint8_t* t, uint64_t n, uint64_t at) {  // src/input.rs:268-318
+  const bool w1 = at > 0 && is_word_byte(t[at - 1]);
+  const bool w2 = at < n && is_word_byte(t[at]);
+  switch (look) {
+    case 0: return at == 0 || t[at - 1] == '\n';  // StartLine
+    case 1: return at == n || t[at] == '\n';      // EndLine
+    case 2: return at == 0;                        // StartText
+    case 3: return at == n;                        // EndText
+    case 4: case 6: return w1 != w2;               // word boundary (ASCII; the Unicode one is rejected at compile time)
+    default: return w1 == w2;
+  }
+}
+struct PikeList {
+  uint32_t* sparse;
+  uint32_t* dense;
+  uint64_t* caps;  // [ip][slot]
+  uint32_t count;
+  __device__ __forceinline__ bool contains(uint32_t ip) const { const uint32_t i = sparse[ip]; return i < count && dense[i] == ip; }
+  __device__ __forceinline__ void insert(uint32_t ip) { sparse[ip] = count; dense[count++] = ip; }
+};
+// pikevm.rs:274-352: follow the epsilon transitions from ip0 in priority order
+__device__ void pike_add(const CapArgs& a, PikeList& l, uint64_t* tc, uint32_t ip0, uint64_t n, uint64_t at, uint32_t* stk_tag, uint64_t* stk_pos) {
+  uint32_t sp = 0;
+  stk_tag[sp] = ip0; stk_pos[sp++] = 0;  // tag < 0x80000000: an instruction to visit; else: restore slot (tag & 0x7FFFFFFF) to pos
+  while (sp) {
+    --sp;
+    const uint32_t tag = stk_tag[sp];
+    if (tag & 0x80000000u) { tc[tag & 0x7FFFFFFFu] = stk_pos[sp]; continue; }
+    uint32_t ip = tag;
+    for (;;) {
+      if (l.contains(ip)) break;
+      l.insert(ip);
+      const NfaInst in = a.insts[ip];
+      const uint32_t op = in.op_look_lo_hi & 0xFF;
+      if (op == 3) {         // EmptyLook
+        if (!look_holds((in.op_look_lo_hi >> 8) & 0xFF, a.text, n, at)) break;
+        ip = in.a;
+      } else if (op == 1) {  // Save
+        if (in.b < a.n_slots) {
+          stk_tag[sp] = 0x80000000u | in.b; stk_pos[sp++] = tc[in.b];
+          tc[in.b] = at;
+        }
+        ip = in.a;
+      } else if (op == 2) {  // Split: goto1 first, goto2 later
+        stk_tag[sp] = in.b; stk_pos[sp++] = 0;
+        ip = in.a;
+      } else {               // Match or Bytes: the thread waits here with its slots
+        for (uint32_t k = 0; k < a.n_slots; k++) l.caps[(uint64_t)ip * a.n_slots + k] = tc[k];
+        break;
+      }
+    }
+  }
+}
+__global__ void pike_captures(CapArgs a) {
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+  uint8_t* mine = a.scratch + tid * a.per_thread;
+  const uint64_t ni = a.n_insts, ns = a.n_slots;
+  PikeList L[2];
+  uint64_t off = 0;
+  for (int j = 0; j < 2; j++) { L[j].caps = reinterpret_cast<uint64_t*>(mine + off); off += ni * ns * 8; }
+  uint64_t* tc = reinterpret_cast<uint64_t*>(mine + off); off += ns * 8;
+  uint64_t* stk_pos = reinterpret_cast<uint64_t*>(mine + off); off += (2 * ni + 4) * 8;
+  for (int j = 0; j < 2; j++) { L[j].sparse = reinterpret_cast<uint32_t*>(mine + off); off += ni * 4; L[j].dense = reinterpret_cast<uint32_t*>(mine + off); off += ni * 4; }
+  uint32_t* stk_tag = reinterpret_cast<uint32_t*>(mine + off);
+  for (uint64_t m = tid; m < a.n_matches; m += n_threads) {
+    const uint64_t s = a.spans[2 * m], e = a.spans[2 * m + 1];
+    uint64_t* out = a.slots + m * ns;
+    // the window ends two characters past the match (look-ahead needs them; utf8.rs:24-40 next_utf8)
+    uint64_t n = e;
+    for (int r = 0; r < 2; r++) {
+      if (n >= a.n) { n = a.n; break; }
+      const uint32_t b = a.text[n];
+      n += b <= 0x7F ? 1 : b <= 0xDF ? 2 : b <= 0xEF ? 3 : 4;
+    }
+    n = min(n, a.n);
+    for (uint32_t k = 0; k < ns; k++) { out[k] = kNone; tc[k] = kNone; }
+    int cur = 0;
+    L[0].count = L[1].count = 0;
+    for (uint64_t i = 0; i < ni; i++) L[0].sparse[i] = L[1].sparse[i] = 0;
+    bool matched = false;
+    for (uint64_t at = s;; at++) {
+      PikeList& cl = L[cur];
+      PikeList& nl = L[cur ^ 1];
+      if (cl.count == 0) {
+        if (matched || at != s) break;  // the capture program is anchored at the match start
+        pike_add(a, cl, tc, a.start_ip, n, at, stk_tag, stk_pos);
+      }
+      for (uint32_t i = 0; i < cl.count; i++) {
+        const uint32_t ip = cl.dense[i];
+        const NfaInst in = a.insts[ip];
+        const uint32_t op = in.op_look_lo_hi & 0xFF;
+        if (op == 0) {  // Match: leftmost-first -- lower-priority threads of this step are dropped
+          for (uint32_t k = 0; k < ns; k++) out[k] = cl.caps[(uint64_t)ip * ns + k];
+          matched = true;
+          break;
+        }
+        if (op == 4 && at < n) {  // Bytes
+          const uint32_t b = a.text[at];
+          if (((in.op_look_lo_hi >> 16) & 0xFF) <= b && b <= (in.op_look_lo_hi >> 24)) {
+            for (uint32_t k = 0; k < ns; k++) tc[k] = cl.caps[(uint64_t)ip * ns + k];
+            pike_add(a, nl, tc, in.a, n, at + 1, stk_tag, stk_pos);
+          }
+        }
+      }
+      if (at >= n) break;
+      cl.count = 0;
+      cur ^= 1;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- batch mode --
 // One thread per record; each record is its own haystack (record-local ^, $, \b).
 __global__ void is_match_batch(BatchArgs a) {

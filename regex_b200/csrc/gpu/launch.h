@@ -115,6 +115,21 @@ __global__ void replace_matches(ReplaceArgs a);
 // pieces[i] = text between match i-1 and match i; limit as splitn (0 = none)
 __global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t n, uint64_t n_pieces, int last_is_rest, uint64_t* pieces, uint64_t cap);
 
+// ---- capture groups on the narrowed window (src/exec.rs:861-875, src/pikevm.rs:130-352) ----
+struct NfaInst { uint32_t op_look_lo_hi; uint32_t a, b; };  // op | look << 8 | lo << 16 | hi << 24; a, b as rb::Inst
+struct CapArgs {
+  const NfaInst* insts;
+  uint32_t n_insts, start_ip, n_slots;
+  const uint8_t* text;
+  uint64_t n;
+  const uint64_t* spans;   // (start, end) of every match, from the DFA path
+  uint64_t n_matches;
+  uint64_t* slots;         // [n_matches][n_slots], kNone = the group did not take part
+  uint8_t* scratch;        // per resident thread: two thread lists with their slot arrays, a stack (see kernels.cu)
+  uint64_t per_thread;
+};
+__global__ void pike_captures(CapArgs a);
+
 struct BatchArgs {
   DfaView fwd;
   DfaView rev;

@@ -410,8 +410,7 @@ def test_sharded_search_matches_whole_haystack(world):
 def test_reference_ctest_binary():
     """regex-capi/ctest/test.c, compiled unchanged against include/rure.h and linked to
     librure_b200.so by __graft_entry__.build() (needs the reference tree, so the binary is
-    prebuilt).  Everything but the three tests that read capture group >= 1 must pass
-    (captures are out of scope)."""
+    prebuilt).  All twelve tests must pass, the three that read capture groups included."""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ctest")
     if not os.path.exists(exe):
@@ -420,10 +419,10 @@ def test_reference_ctest_binary():
     lines = [l for l in r.stderr.splitlines() if l.startswith(("PASSED", "FAILED"))]
     failed = {l.split(": ")[1] for l in lines if l.startswith("FAILED")}
     passed = {l.split(": ")[1] for l in lines if l.startswith("PASSED")}
-    assert failed <= {"test_captures", "test_iter", "test_iter_capture_names"}, (failed, r.stderr[-2000:])
-    assert passed >= {"test_is_match", "test_shortest_match", "test_find", "test_flags", "test_compile_error",
-                      "test_compile_error_size_limit", "test_regex_set_match", "test_regex_set_options",
-                      "test_regex_set_match_start"}, (passed, r.stderr[-2000:])
+    assert not failed, (failed, r.stderr[-2000:])
+    assert passed >= {"test_is_match", "test_shortest_match", "test_find", "test_captures", "test_iter", "test_iter_capture_names",
+                      "test_flags", "test_compile_error", "test_compile_error_size_limit", "test_regex_set_match",
+                      "test_regex_set_options", "test_regex_set_match_start"}, (passed, r.stderr[-2000:])
     # the iterator example (group 0 path) must run to completion over sherlock.txt
     it = subprocess.run([os.path.join(os.path.dirname(exe), "iter_example")], capture_output=True, text=True, timeout=120, cwd=GOLDEN)
     assert it.returncode == 0, it.stderr[-500:]

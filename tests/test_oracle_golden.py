@@ -129,3 +129,33 @@ def test_python_re_crosscheck():
         exp = [(m.start(), m.end()) for m in pyre.finditer(pat.encode(), text)]
         # Python's bytes patterns are byte-oriented: compare with the (?-u) flavour.
         assert O.OracleRegex("(?-u)" + pat, only_utf8=False).find_iter(text) == exp, pat
+
+
+def test_oracle_captures_equal_the_reference_vectors():
+    """Every capture group the reference's mat! vectors list (tests/macros.rs:22-52 compares as many
+    groups as the test names): the oracle's Pike VM with slots (src/pikevm.rs:130-352) after the
+    DFA pipeline (src/exec.rs:527-590, 861-875)."""
+    from helpers import vectors
+    n = multi = 0
+    for x in vectors():
+        if x["kind"] != "mat":
+            continue
+        text = bytes.fromhex(x["text_hex"])
+        for mode in x["modes"]:
+            try:
+                o = O.OracleRegex(x["re"], only_utf8=mode == "str")
+            except O.OracleError:
+                continue
+            if o.needs_unicode_word_boundary:
+                continue
+            got = o.captures_at(text)
+            exp = x["groups"]
+            if exp[0] is None:
+                assert got is None, (x["name"], got)
+                continue
+            assert got is not None, x["name"]
+            got = [list(g) if g is not None else None for g in got][:len(exp)]
+            assert got == exp, (x["name"], x["re"], got, exp)
+            n += 1
+            multi += len(exp) > 1
+    assert n > 700 and multi > 300, (n, multi)

@@ -10,8 +10,9 @@ Sources (all plain text in the reference tree; nothing is compiled or run):
   examples/regexdna-{input,output}.txt + examples/shootout-regex-dna.rs:26-34
   tests/noparse.rs              patterns that must fail to compile
 
-Only group 0 of mat! cases is kept (captures are out of scope).  Haystacks are
-stored as hex so raw-byte cases (tests/bytes.rs R(b"...")) survive JSON.
+mat! cases keep group 0 in "expected" and every listed group in "groups" (the macro compares
+as many groups as the test lists, tests/macros.rs:22-52).  Haystacks are stored as hex so
+raw-byte cases (tests/bytes.rs R(b"...")) survive JSON.
 
 Usage: python tools/scrape_golden.py [/root/reference]
 """
@@ -170,6 +171,8 @@ for fname, modes in FILES.items():
                 else:
                     a, b = re.match(r"Some\(\((\d+),\s*(\d+)\)\)", ",".join(args[3:5])).groups()
                     v["expected"] = [int(a), int(b)]
+                v["groups"] = [[int(g.group(1)), int(g.group(2))] if g.group(1) is not None else None
+                               for g in re.finditer(r"Some\(\((\d+),\s*(\d+)\)\)|None", rest)]
             elif kind == "matiter":
                 v["expected"] = [[int(a), int(b)] for a, b in re.findall(r"\((\d+),\s*(\d+)\)", rest)]
             elif kind == "ismatch":
