@@ -233,8 +233,13 @@ struct CapVm {
     bool matched = false;
     for (size_t at = start;; at++) {
       if (clist.dense.empty()) {
-        if (matched || at != start) break;  // the capture program is anchored at `start`
-        add(clist, tc, prog.start_anchored, t, n, at);
+        if (matched || (at != 0 && prog.is_anchored_start)) break;  // pikevm.rs:143-158 (at.is_start() is position 0)
+      }
+      // a new thread at every position until something has matched (pikevm.rs:172-175): the lazy
+      // prefix of the program; its slots start out empty (the caller's slots are all None then)
+      if (clist.dense.empty() || (!prog.is_anchored_start && !matched)) {
+        std::fill(tc.begin(), tc.end(), NONE);
+        add(clist, tc, prog.start, t, n, at);
       }
       for (size_t i = 0; i < clist.dense.size(); i++) {
         const uint32_t ip = clist.dense[i];
@@ -496,7 +501,7 @@ struct LazyDfa {
 struct Regex {
   std::vector<std::string> pats;
   Program nfa, dfa, dfa_rev;
-  Program caps;  // anchored forward program WITH Save instructions for every group (captures)
+  Program caps;  // the forward program (lazy prefix included) WITH Save instructions for every group (captures)
   std::unique_ptr<LazyDfa> fwd, rev;
   bool only_utf8 = false;
   std::string error;
@@ -615,6 +620,7 @@ static Regex* build(const std::vector<std::string>& pats, uint32_t flags, bool o
   if (!rb::compile(exprs, o, &re->nfa, &err)) { re->error = err.msg; return re.release(); }
   if (exprs.size() == 1) {
     o.saves = true;
+    o.unanchored_prefix = true;
     if (!rb::compile(exprs, o, &re->caps, &err)) { re->error = err.msg; return re.release(); }
     o.saves = false;
   }

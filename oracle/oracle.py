@@ -102,6 +102,28 @@ class OracleRegex:
         none = (1 << 64) - 1
         return [None if buf[2 * i] == none else (buf[2 * i], buf[2 * i + 1]) for i in range(g)]
 
+    def captures_iter(self, text, only_utf8=False):
+        """`Regex::captures_iter` (re_trait.rs:236-263): the find_iter rule over read_captures_at."""
+        out, last_end, last_match, n = [], 0, None, len(text)
+        while last_end <= n:
+            c = self.captures_at(text, last_end)
+            if c is None:
+                break
+            s, e = c[0]
+            if s == e:
+                if only_utf8 and e < n:
+                    b = text[e]
+                    last_end = e + (1 if b <= 0x7F else 2 if b <= 0xDF else 3 if b <= 0xEF else 4)
+                else:
+                    last_end = e + 1
+                if e == last_match:
+                    continue
+            else:
+                last_end = e
+            last_match = e
+            out.append(c)
+        return out
+
     def find_iter(self, text, engine=ENGINE_DFA, cap=None):
         n = lib().oracle_find_iter(self._h, engine, text, len(text), None, 0) if cap is None else cap
         buf = (c_size_t * (2 * max(1, n)))()

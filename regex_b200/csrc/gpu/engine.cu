@@ -1312,7 +1312,7 @@ int Regex::replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep
   lits.clear();
   auto literal = [&](const uint8_t* p, uint64_t len) -> bool {
     if (len == 0) return true;
-    if (a.n_parts && a.part_len[a.n_parts - 1] != 0xFFFFFFFFu && a.part_off[a.n_parts - 1] + a.part_len[a.n_parts - 1] == lits.size()) {
+    if (a.n_parts && !(a.part_len[a.n_parts - 1] & kRepGroup) && a.part_off[a.n_parts - 1] + a.part_len[a.n_parts - 1] == lits.size()) {
       a.part_len[a.n_parts - 1] += (uint32_t)len;  // extend the previous literal part
     } else {
       if (a.n_parts == kMaxRepParts) return false;
@@ -1323,7 +1323,7 @@ int Regex::replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep
     a.lit_total += len;
     return true;
   };
-  bool fits = true;
+  bool fits = true, needs_groups = false;
   if (!expand) {
     fits = literal(rep, rep_len);
   } else {
@@ -1350,19 +1350,19 @@ int Regex::replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep
       }
       if (!ok) { fits = fits && literal(rep + i, 1); i += 1; continue; }  // a lone '$'
       i = ce;
-      bool numeric = name.find_first_not_of("0123456789") == std::string::npos && name.size() <= 9;
-      if (numeric) {
-        const long g = std::atol(name.c_str());
-        if (g == 0) {
-          if (a.n_parts == kMaxRepParts) { fits = false; break; }
-          a.part_len[a.n_parts] = 0xFFFFFFFFu;
-          a.part_off[a.n_parts++] = 0;
-          a.whole_refs++;
-        } else if (g < n_groups_) {
-          return fail("the replacement refers to capture group " + name + "; capture groups other than 0 are not supported by the B200 backend");
-        }  // a group that does not exist expands to nothing
-      } else if (std::find(group_names_.begin(), group_names_.end(), name) != group_names_.end()) {
-        return fail("the replacement refers to capture group '" + name + "'; capture groups other than 0 are not supported by the B200 backend");
+      // expand.rs:78-87: a number is a group index, anything else a group name; a group the pattern
+      // does not have expands to nothing
+      long g = -1;
+      if (name.find_first_not_of("0123456789") == std::string::npos) {
+        g = name.size() <= 9 ? std::atol(name.c_str()) : -1;
+      } else {
+        for (const auto& gn : group_name_index_) if (gn.first == name) g = gn.second;
+      }
+      if (g >= 0 && g < n_groups_) {
+        if (a.n_parts == kMaxRepParts) { fits = false; break; }
+        a.part_len[a.n_parts] = kRepGroup | (uint32_t)g;
+        a.part_off[a.n_parts++] = 0;
+        if (g > 0) needs_groups = true;
       }
     }
   }
@@ -1379,26 +1379,45 @@ int Regex::replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep
   uint32_t* counters = (uint32_t*)counters_.ensure(128);
   uint8_t* d_lits = (uint8_t*)lits_.ensure(std::max<size_t>(lits.size(), 16));
   if (!lens || !before || !block_sums || !counters || !d_lits) return fail("out of device memory (replace scratch)");
-  uint64_t matched = 0;
-  if (m) {
-    span_lengths<<<grid_for(m, 256, 8), 256, 0, st>>>(spans, m, lens);
-    RB_LAUNCH_CHECK("span_lengths");
-    unsigned long long* grand = (unsigned long long*)(counters + 4);
-    scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(lens, before, block_sums, m);
-    RB_LAUNCH_CHECK("scan_counts_local");
-    scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, grand);
-    RB_LAUNCH_CHECK("scan_block_sums");
-    scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(before, block_sums, m);
-    RB_LAUNCH_CHECK("scan_add_block_offsets");
-    RB_CUDA(d2h(&matched, grand, 8));
-  }
-  *out_len = n - matched + m * a.lit_total + (uint64_t)a.whole_refs * matched;
+  uint64_t* reps_before = (uint64_t*)reps_before_.ensure(std::max<uint64_t>(m, 1) * 8);
+  if (!reps_before) return fail("out of device memory (replace scratch)");
   a.text = d_text;
   a.n = n;
   a.spans = spans;
   a.n_matches = m;
   a.lens_before = before;
+  a.reps_before = reps_before;
   a.lits = d_lits;
+  if (needs_groups && m) {  // `$1`, `$name`: the groups of every match (capture pass on the narrowed windows)
+    a.n_slots = 2 * (uint32_t)n_groups_;
+    uint64_t* d_slots = (uint64_t*)cap_slots_.ensure(m * a.n_slots * 8);
+    if (!d_slots) return fail("out of device memory (captures)");
+    if (int rc = captures_device(d_text, n, spans, m, d_slots)) return rc;
+    a.slots = d_slots;
+  }
+  uint64_t matched = 0, replaced = 0;
+  if (m) {
+    unsigned long long* grand = (unsigned long long*)(counters + 4);
+    auto prefix = [&](uint64_t* out, uint64_t* total) -> int {  // exclusive prefix sum of lens[] into out[]
+      scan_counts_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(lens, out, block_sums, m);
+      RB_LAUNCH_CHECK("scan_counts_local");
+      scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, grand);
+      RB_LAUNCH_CHECK("scan_block_sums");
+      scan_add_block_offsets<<<(uint32_t)n_blocks, 1024, 0, st>>>(out, block_sums, m);
+      RB_LAUNCH_CHECK("scan_add_block_offsets");
+      RB_CUDA(d2h(total, grand, 8));
+      return 0;
+    };
+    span_lengths<<<grid_for(m, 256, 8), 256, 0, st>>>(spans, m, lens);
+    RB_LAUNCH_CHECK("span_lengths");
+    if (int rc = prefix(before, &matched)) return rc;
+    replace_lengths<<<grid_for(m, 256, 8), 256, 0, st>>>(a, lens);
+    RB_LAUNCH_CHECK("replace_lengths");
+    if (int rc = prefix(reps_before, &replaced)) return rc;
+  }
+  rep_totals_[0] = matched;
+  rep_totals_[1] = replaced;
+  *out_len = n - matched + replaced;
   return 0;
 }
 
@@ -1412,7 +1431,7 @@ int Regex::replace_emit(uint8_t* d_out, uint64_t out_cap) {
   a.out = d_out;
   a.out_cap = out_cap;
   if (n) {
-    replace_gaps<<<grid_for(((n + 2047) / 2048) * 32, 256, 8), 256, 0, st>>>(a);
+    replace_gaps<<<grid_for(((n + 2047) / 2048) * 32, 256, 8), 256, 0, st>>>(a, rep_totals_[0], rep_totals_[1]);
     RB_LAUNCH_CHECK("replace_gaps");
   }
   if (m && a.n_parts) {
@@ -1489,7 +1508,7 @@ int Regex::ensure_capture_program() {
   rb::CompileOptions co;
   co.only_utf8 = opt_.only_utf8;
   co.size_limit = opt_.size_limit;
-  co.unanchored_prefix = false;
+  co.unanchored_prefix = true;
   co.saves = true;
   rb::Program prog;
   rb::Error err;
@@ -1506,7 +1525,8 @@ int Regex::ensure_capture_program() {
   RB_CUDA(cudaMemcpyAsync(d, insts.data(), insts.size() * sizeof(NfaInst), cudaMemcpyHostToDevice, (cudaStream_t)stream_));
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   cap_n_insts_ = (uint32_t)insts.size();
-  cap_start_ = prog.start_anchored;
+  cap_start_ = prog.start;
+  cap_anchored_ = prog.is_anchored_start;
   return 0;
 }
 
@@ -1518,6 +1538,7 @@ int Regex::captures_device(const uint8_t* d_text, uint64_t n, const uint64_t* d_
   a.insts = (const NfaInst*)cap_insts_.ptr;
   a.n_insts = cap_n_insts_;
   a.start_ip = cap_start_;
+  a.anchored_start = cap_anchored_ ? 1 : 0;
   a.n_slots = 2 * (uint32_t)n_groups_;
   a.text = d_text;
   a.n = n;
@@ -1555,8 +1576,9 @@ int Regex::captures_at_host(const uint8_t* text, uint64_t n, uint64_t start, boo
   const uint64_t span[2] = {s, e};
   RB_CUDA(cudaMemcpyAsync(d_span, span, 16, cudaMemcpyHostToDevice, st));
   RB_CUDA(cudaStreamSynchronize(st));
-  if (int rc = captures_device(d, hi, d_span, 1, d_slots)) return rc;  // hi < n only shortens a haystack the window never reaches...
+  if (int rc = captures_device(d, hi, d_span, 1, d_slots)) return rc;  // (hi bounds a window the pass never leaves)
   RB_CUDA(d2h(slots, d_slots, ns * 8));
+  *found = slots[0] != kNone;  // exec.rs:896-906: the result is what the NFA found in the window
   return 0;
 }
 
@@ -1574,6 +1596,44 @@ int Regex::captures_all_host(const uint8_t* text, uint64_t n, uint64_t* slots, u
   if (!d_slots) return fail("out of device memory (captures)");
   if ((rc = captures_device(d, n, spans, k, d_slots))) return rc;
   RB_CUDA(d2h(slots, d_slots, k * ns * 8));
+  // CaptureMatches (re_trait.rs:236-263) iterates on what read_captures_at returns, i.e. on the NFA's
+  // group 0.  That is the find_iter span except where the reverse-on-slice quirk gave
+  // the DFA a start no match begins at; from the first such match on, iterate like the reference.
+  std::vector<uint64_t> h_spans(2 * k);
+  RB_CUDA(d2h(h_spans.data(), spans, k * 16));
+  uint64_t j = 0;
+  while (j < k && slots[j * ns] == h_spans[2 * j] && slots[j * ns + 1] == h_spans[2 * j + 1]) j++;
+  if (j == k && *m <= cap) return 0;
+  if (j == k) return 0;  // the caller's buffer ends before any divergence
+  auto next_after_empty = [&](uint64_t i) -> uint64_t {  // exec.rs:335-337, 375-377
+    if (!only_utf8 || i >= n) return i + 1;
+    const uint8_t b = text[i];
+    return i + (b <= 0x7F ? 1 : b <= 0xDF ? 2 : b <= 0xEF ? 3 : 4);
+  };
+  uint64_t last_end = 0, last_match = kNone;
+  if (j) {
+    const uint64_t ps = h_spans[2 * (j - 1)], pe = h_spans[2 * (j - 1) + 1];
+    last_end = ps == pe ? next_after_empty(pe) : pe;
+    last_match = pe;
+  }
+  std::vector<uint64_t> one(ns);
+  uint64_t count = j;
+  while (last_end <= n) {
+    bool found = false;
+    if ((rc = captures_at_host(text, n, last_end, &found, one.data()))) return rc;
+    if (!found) break;
+    const uint64_t s = one[0], e = one[1];
+    if (s == e) {
+      last_end = next_after_empty(e);
+      if (e == last_match) continue;
+    } else {
+      last_end = e;
+    }
+    last_match = e;
+    if (count < cap) std::copy(one.begin(), one.end(), slots + count * ns);
+    count++;
+  }
+  *m = count;
   return 0;
 }
 

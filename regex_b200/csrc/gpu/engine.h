@@ -197,13 +197,15 @@ class Regex {
   bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
-  DeviceBuf spans_all_, lens_, lits_, rep_out_, pieces_;
+  DeviceBuf spans_all_, lens_, lits_, rep_out_, pieces_, reps_before_;
+  uint64_t rep_totals_[2] = {0, 0};  // matched bytes, replacement bytes of the pending replace call
   std::vector<uint8_t> rep_args_, rep_lits_;  // launch.h ReplaceArgs image + literal bytes of the pending replace call
   int n_groups_ = 1;                      // capture groups incl. group 0
   std::vector<std::string> group_names_;  // names of the named groups
   std::vector<std::pair<std::string, int>> group_name_index_;  // (name, group index)
   DeviceBuf cap_insts_, cap_scratch_, cap_slots_, cap_span_;
   uint32_t cap_n_insts_ = 0, cap_start_ = 0;  // capture program on the device (0 = not uploaded yet)
+  bool cap_anchored_ = false;
   DeviceBuf in_p_, in_lm_, out_p_, out_lm_, count_, offset_, dirty_, first_cand_, skip_, meta_, excl_, btot_, present_, kidx_, kstates_, maps_, comp_, bentry_, exact_, stage_, block_sums_, out_, bits_, masks_;
   void* pinned_ = nullptr;  // small pinned staging area for counters / scalars
   void* timing_events_[3] = {nullptr, nullptr, nullptr};

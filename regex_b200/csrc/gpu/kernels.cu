@@ -1893,19 +1893,35 @@ __global__ void scan_add_block_offsets(uint64_t* out, const uint64_t* block_sums
 // ------------------------------------------------- replace_all / split ----------
 // Bulk forms of the reference's thin loops over find_iter (src/re_bytes.rs:476-535 replacen,
 // :316-360 / :699-749 split): the spans are on the device already, so the haystack never
-// leaves it.  With P_i = total length of the matches before match i, L = literal bytes of
-// the replacement and k = number of `$0` parts, input byte x in the gap in front of match i
-// lands at x + i*L + (k-1)*P_i, and the replacement of match i starts at start_i + that.
+// leaves it.
 __global__ void span_lengths(const uint64_t* spans, uint64_t n_matches, uint64_t* lens) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_matches; i += (uint64_t)gridDim.x * blockDim.x)
     lens[i] = spans[2 * i + 1] - spans[2 * i];
 }
-__device__ __forceinline__ int64_t replace_shift(const ReplaceArgs& a, uint64_t i, uint64_t lens_before) {
-  return (int64_t)(i * a.lit_total) + ((int64_t)a.whole_refs - 1) * (int64_t)lens_before;
+// span of group g of match i (kNone start = the group did not take part: expands to nothing)
+__device__ __forceinline__ void rep_group(const ReplaceArgs& a, uint64_t i, uint32_t g, uint64_t* s, uint64_t* e) {
+  if (g == 0 || !a.slots) { *s = a.spans[2 * i]; *e = a.spans[2 * i + 1]; return; }
+  *s = a.slots[i * a.n_slots + 2 * g];
+  *e = a.slots[i * a.n_slots + 2 * g + 1];
+  if (*s == kNone || *e == kNone) *s = *e = 0;
+}
+__global__ void replace_lengths(ReplaceArgs a, uint64_t* rep_lens) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < a.n_matches; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t len = a.lit_total;
+    for (uint32_t p = 0; p < a.n_parts; p++)
+      if (a.part_len[p] & kRepGroup) {
+        uint64_t s, e;
+        rep_group(a, i, a.part_len[p] & ~kRepGroup, &s, &e);
+        len += e - s;
+      }
+    rep_lens[i] = len;
+  }
 }
 // The unmatched text.  One warp per 2 KiB tile of the INPUT (balanced whatever the gap sizes):
 // binary search for the first match that ends after the tile's first byte, then gap by gap.
-__global__ void replace_gaps(ReplaceArgs a) {
+// With P_i / R_i = total length of the matches / replacements before match i, input byte x in the
+// gap in front of match i lands at x - P_i + R_i.
+__global__ void replace_gaps(ReplaceArgs a, uint64_t matched_total, uint64_t replaced_total) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1921,9 +1937,7 @@ __global__ void replace_gaps(ReplaceArgs a) {
     for (uint64_t i = i0; x < hi; i++) {
       const bool tail = i >= a.n_matches;
       const uint64_t ms = tail ? a.n : a.spans[2 * i], me = tail ? a.n : a.spans[2 * i + 1];
-      const uint64_t before = tail ? (a.n_matches ? a.lens_before[a.n_matches - 1] + (a.spans[2 * a.n_matches - 1] - a.spans[2 * a.n_matches - 2]) : 0)
-                                   : a.lens_before[i];
-      const int64_t shift = replace_shift(a, min(i, a.n_matches), before);
+      const int64_t shift = tail ? (int64_t)replaced_total - (int64_t)matched_total : (int64_t)a.reps_before[i] - (int64_t)a.lens_before[i];
       const uint64_t ge = min(ms, hi);  // gap [x, ge)
       for (uint64_t q = x + lane; q < ge; q += 32) {
         const uint64_t o = (uint64_t)((int64_t)q + shift);
@@ -1940,12 +1954,19 @@ __global__ void replace_matches(ReplaceArgs a) {
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t i = warp; i < a.n_matches; i += n_warps) {
-    const uint64_t ms = a.spans[2 * i], me = a.spans[2 * i + 1];
-    uint64_t o = (uint64_t)((int64_t)ms + replace_shift(a, i, a.lens_before[i]));
+    uint64_t o = a.spans[2 * i] - a.lens_before[i] + a.reps_before[i];
     for (uint32_t p = 0; p < a.n_parts; p++) {
-      const bool whole = a.part_len[p] == 0xFFFFFFFFu;
-      const uint64_t len = whole ? me - ms : a.part_len[p];
-      const uint8_t* src = whole ? a.text + ms : a.lits + a.part_off[p];
+      uint64_t len;
+      const uint8_t* src;
+      if (a.part_len[p] & kRepGroup) {
+        uint64_t s, e;
+        rep_group(a, i, a.part_len[p] & ~kRepGroup, &s, &e);
+        len = e - s;
+        src = a.text + s;
+      } else {
+        len = a.part_len[p];
+        src = a.lits + a.part_off[p];
+      }
       for (uint64_t q = lane; q < len; q += 32)
         if (o + q < a.out_cap) a.out[o + q] = src[q];
       o += len;
@@ -1968,8 +1989,11 @@ __global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t
 // narrowed down: from the match start to two characters past the match end
 // (src/exec.rs:861-875 captures_nfa_with_match).  Same here: one thread per match runs the Pike
 // VM of src/pikevm.rs:130-352 (thread lists in priority order, per-thread slot arrays, the
-// explicit stack that restores slots behind a Save) over the capture program -- the anchored
-// forward program compiled WITH Save instructions.  Scratch lives in global memory, one slab per
+// explicit stack that restores slots behind a Save) over the capture program -- the forward
+// program, lazy prefix included, compiled WITH Save instructions.  (The search starts at the
+// match start the DFA found; where the reverse-on-slice quirk of SURVEY H1 made that start one
+// no match begins at, the NFA reports the next match inside the window or none, as it does in
+// the reference.)  Scratch lives in global memory, one slab per
 // resident thread; this is a per-match O(window x program) pass, not a streaming kernel.
 __device__ __forceinline__ bool look_holds(uint32_t look, const uint8_t* t, uint64_t n, uint64_t at) {  // src/input.rs:268-318
   const bool w1 = at > 0 && is_word_byte(t[at - 1]);
@@ -2055,8 +2079,11 @@ __global__ void pike_captures(CapArgs a) {
     for (uint64_t at = s;; at++) {
       PikeList& cl = L[cur];
       PikeList& nl = L[cur ^ 1];
-      if (cl.count == 0) {
-        if (matched || at != s) break;  // the capture program is anchored at the match start
+      if (cl.count == 0 && (matched || (at != 0 && a.anchored_start))) break;  // pikevm.rs:143-158
+      // a new thread at every position until something has matched: the program's lazy prefix
+      // (pikevm.rs:172-175); its slots start out empty
+      if (cl.count == 0 || (!a.anchored_start && !matched)) {
+        for (uint32_t k = 0; k < ns; k++) tc[k] = kNone;
         pike_add(a, cl, tc, a.start_ip, n, at, stk_tag, stk_pos);
       }
       for (uint32_t i = 0; i < cl.count; i++) {

@@ -91,26 +91,30 @@ __global__ void literal_scan(const __grid_constant__ WalkArgs a, const __grid_co
 __global__ void compact_staged(WalkArgs a);
 
 // ---- bulk operations over the span list (src/re_bytes.rs:316-360 split, :476-535 replacen) ----
-// The replacement of one match is a sequence of parts: literal bytes, or the text of the whole
-// match (`$0`, src/expand.rs:50-90).
+// The replacement of one match is a sequence of parts: literal bytes, or the text of a capture
+// group of that match (`$0`, `$2`, `$name`; src/expand.rs:50-90).
 constexpr uint32_t kMaxRepParts = 16;
+constexpr uint32_t kRepGroup = 0x80000000u;  // part_len = kRepGroup | group index
 struct ReplaceArgs {
   const uint8_t* text;
   uint64_t n;
   const uint64_t* spans;   // n_matches (start, end) pairs, ordered, non-overlapping
   uint64_t n_matches;      // matches to replace (after `limit`)
   const uint64_t* lens_before;  // exclusive prefix sum of the match lengths
+  const uint64_t* reps_before;  // exclusive prefix sum of the replacement lengths
+  const uint64_t* slots;   // [n_matches][n_slots] group spans (null when only group 0 is referenced)
+  uint32_t n_slots;
   const uint8_t* lits;     // literal bytes of all parts, concatenated
   uint32_t n_parts;
-  uint32_t part_len[kMaxRepParts];  // literal length, or 0xFFFFFFFF = the match text
+  uint32_t part_len[kMaxRepParts];  // literal length, or kRepGroup | g
   uint32_t part_off[kMaxRepParts];  // offset into lits
   uint64_t lit_total;      // literal bytes per match
-  uint32_t whole_refs;     // `$0` parts per match
   uint8_t* out;
   uint64_t out_cap;
 };
+__global__ void replace_lengths(ReplaceArgs a, uint64_t* rep_lens);
 __global__ void span_lengths(const uint64_t* spans, uint64_t n_matches, uint64_t* lens);
-__global__ void replace_gaps(ReplaceArgs a);
+__global__ void replace_gaps(ReplaceArgs a, uint64_t matched_total, uint64_t replaced_total);
 __global__ void replace_matches(ReplaceArgs a);
 // pieces[i] = text between match i-1 and match i; limit as splitn (0 = none)
 __global__ void split_pieces(const uint64_t* spans, uint64_t n_matches, uint64_t n, uint64_t n_pieces, int last_is_rest, uint64_t* pieces, uint64_t cap);
@@ -120,6 +124,7 @@ struct NfaInst { uint32_t op_look_lo_hi; uint32_t a, b; };  // op | look << 8 | 
 struct CapArgs {
   const NfaInst* insts;
   uint32_t n_insts, start_ip, n_slots;
+  int anchored_start;      // the pattern begins with ^ (no lazy prefix, no later threads)
   const uint8_t* text;
   uint64_t n;
   const uint64_t* spans;   // (start, end) of every match, from the DFA path

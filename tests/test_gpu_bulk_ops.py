@@ -104,10 +104,8 @@ def test_reference_doc_examples_and_expansion():
     assert r.replace_all(b"abbc", b"$0", expand=False) == b"a$0c"
     assert r.replacen(b"b b b b", 2, b"X") == b"X X b b"
     assert r.replace_all(b"nothing here", b"X") == b"nothing here"
-    with pytest.raises(R.Error, match="capture group"):
-        R.BytesRegex(r"(a)(?P<last>b)").replace_all(b"ab", b"$2$1")
-    with pytest.raises(R.Error, match="capture group"):
-        R.BytesRegex(r"(a)(?P<last>b)").replace_all(b"ab", b"$last")
+    assert R.BytesRegex(r"(a)(?P<last>b)").replace_all(b"ab ab", b"$2$1") == b"ba ba"
+    assert R.BytesRegex(r"(a)(?P<last>b)").replace_all(b"ab", b"<$last>") == b"<b>"
     assert R.BytesRegex(r"(a)(?P<last>b)").replace_all(b"ab", b"$2$1", expand=False) == b"$2$1"
 
 
@@ -143,3 +141,29 @@ def test_replace_all_device_resident_large():
     assert n_out == len(one) * reps
     got = out.cpu().numpy()
     assert got[:len(one)].tobytes() == one and got[-len(one):].tobytes() == one
+
+
+def test_replacement_templates_with_capture_groups():
+    """`$1`, `${2}`, `$name` (src/expand.rs:50-90) through the capture pass; the reference's doc
+    examples (re_bytes.rs:383-440) and a model over the oracle's captures."""
+    r = R.BytesRegex(r"(?P<last>[^,\s]+),\s+(?P<first>\S+)")
+    assert r.replace(b"Springsteen, Bruce", b"$first $last") == b"Bruce Springsteen"
+    assert r.replace(b"Springsteen, Bruce", b"$2 $1") == b"Bruce Springsteen"
+    assert r.replace(b"Springsteen, Bruce", b"${first}_$last") == b"Bruce_Springsteen"
+    assert r.replace(b"Springsteen, Bruce", b"$first_$last") == b"Springsteen"  # `$first_` is a group that does not exist
+    assert r.replace(b"Springsteen, Bruce", b"$2 $last", expand=False) == b"$2 $last"
+    pat, rep = r"(\w+)\s+(Holmes|Watson)(,)?", b"[$2|$1$3]"
+    text = sherlock_text()[:300000]
+    o = O.OracleRegex(pat)
+
+    def expand(c):
+        g = [text[x[0]:x[1]] if x is not None else b"" for x in c]
+        return b"[" + g[2] + b"|" + g[1] + g[3] + b"]"
+
+    out, last = [], 0
+    for c in o.captures_iter(text):
+        out.append(text[last:c[0][0]])
+        out.append(expand(c))
+        last = c[0][1]
+    out.append(text[last:])
+    assert R.BytesRegex(pat).replace_all(text, rep) == b"".join(out)

@@ -72,10 +72,6 @@ def test_captures_random_patterns():
             continue
         o = O.OracleRegex(p)
         text = xorshift_bytes(int(rng.integers(0, 1 << 30)), int(rng.integers(50, 600)), b"abc \n" if rng.random() < 0.7 else b"ab1 _\n")
-        spans = o.find_iter(text)
-        got = r.captures_iter(text)
-        assert [g[0] for g in got] == spans, p
-        for i in range(min(len(spans), 40)):
-            assert got[i] == o.captures_at(text, spans[i][0]), (p, text, i)
+        assert r.captures_iter(text) == o.captures_iter(text), (p, text)
         assert r.captures(text) == o.captures_at(text), p
         n += 1
