@@ -1204,6 +1204,7 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
     const size_t fsm = hot_bytes(fwd->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<0>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
+    RB_CUDA(cudaMemsetAsync(d_bits, 0, (n_rec + 31) / 32 * 4, (cudaStream_t)stream_));  // the lanes set bits with atomicOr
     batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
     RB_LAUNCH_CHECK("batch_fast<0>");
   } else {
@@ -1238,6 +1239,7 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
     const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<1>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
+    RB_CUDA(cudaMemsetAsync(d_bits, 0, (n_rec + 31) / 32 * 4, (cudaStream_t)stream_));
     batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
     RB_LAUNCH_CHECK("batch_fast<1>");
   } else {

@@ -2210,6 +2210,16 @@ __device__ __noinline__ bool slow_find_record(const DfaView* f, const DfaView* r
 
 // MODE 0: is_match (forward all-match automaton, stop at the first match state);
 // MODE 1: find (forward leftmost-first end, then the reverse longest automaton for the start).
+//
+// Every lane works through its own records (r = thread id, + grid size, ...) in a flat loop
+// whose body is ONE step of at most 16 bytes of whatever record the lane is on; a lane that
+// finishes a record fetches its next one in the same trip.  The round-1 kernel kept the 32
+// lanes of a warp on the same record index (a ballot wrote their bits): 70 % of the log lines
+// match within 20 bytes, so most lanes idled until the slowest line of the warp was done
+// (ncu r02: 8.5 of 32 threads per instruction).  Results leave by atomicOr (bits, zeroed by the
+// host) and per-record stores.  MODE 1 runs two such loops: all forward scans (the end, with
+// the start marked pending), then all reverse scans, each lane over the records it scanned.
+constexpr uint64_t kPendingStart = ~0ull - 1;
 template <int MODE>
 __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
   const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
@@ -2217,37 +2227,45 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
   hot_stage(a.fwd_hot, fbase);
   if (MODE == 1) hot_stage(a.rev_hot, rbase);
   __syncthreads();
-  const uint32_t fthr = a.fwd_hot.match_lo, flive = 2;
-  const uint32_t rthr = a.rev_hot.match_lo, rlive = 2;
+  const uint32_t fthr = a.fwd_hot.match_lo, rthr = a.rev_hot.match_lo, live = 2;
   const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // multiple of 32: warps stay on one ballot word
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r - lane < a.n_rec; r += stride) {
-    bool hit = false;
-    uint64_t ms = 0, me = 0;
-    if (r < a.n_rec) {
-      const uint64_t lo = a.offsets[r], len = a.offsets[r + 1] - lo;
-      const uint8_t* p = a.text + lo;
-      bool cold = false;
-      // ---- forward ----
-      const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
-      uint32_t e = h0 == 0xFFFFu ? 1u : h0;
-      uint64_t last = kNone;
-      uint32_t mx = 0;
-      uint64_t q = 0;
-      bool done = false;
-      while (!done) {
-        const uint64_t left = len - q;
-        if (left == 0) {  // EOF step
-          if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
-          break;
-        }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  auto set_bit = [&](uint64_t r) { atomicOr(&a.out_bits[r >> 5], 1u << (r & 31)); };
+  // ------------------------------------------------------------ forward ----
+  {
+    uint64_t r = first, len = 0, q = 0, last = kNone;
+    const uint8_t* p = nullptr;
+    uint32_t e = 0, mx = 0;
+    bool have = false;
+    for (;;) {
+      if (!have && r < a.n_rec) {
+        const uint64_t lo = a.offsets[r];
+        len = a.offsets[r + 1] - lo;
+        p = a.text + lo;
+        q = 0;
+        last = kNone;
+        mx = 0;
+        const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
+        e = h0 == 0xFFFFu ? 1u : h0;
+        have = true;
+      }
+      if (!__any_sync(0xffffffffu, have)) break;
+      if (!have) continue;
+      bool fin = false;
+      const uint64_t left = len - q;
+      if (e < live) {
+        fin = true;  // dead or outside the hot set from the start
+      } else if (left == 0) {  // end-of-text step (dfa.rs:748-763)
+        if (a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
+        fin = true;
+      } else {
         const uint8_t* wp = p + q;
         const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+        const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
         if (al + 24 <= buf_hi) {
           uint32_t v[4];
           window16(wp, v);
-          const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
           uint32_t lj = ~0u;
           if (nb == 16) {
 #pragma unroll
@@ -2256,99 +2274,124 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
               e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
               e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
               e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
-              if (e < flive || (MODE == 0 && mx >= fthr)) { done = true; break; }
+              if (e < live || (MODE == 0 && mx >= fthr)) break;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 15; i++) {
-              if ((uint32_t)i < nb) {
+              if ((uint32_t)i < nb && e >= live) {
                 e = hot_next_b(fbase, window_byte(v, i), e);
                 if (MODE == 0) mx = max(mx, e);
                 else if (e >= fthr) lj = i;
               }
             }
-            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
           }
           if (MODE == 1 && lj != ~0u) last = q + lj;
-          q += nb;
         } else {  // the last bytes of the whole buffer: byte loads
-          for (uint64_t i = 0; i < left && !done; i++) {
+          for (uint32_t i = 0; i < nb && e >= live; i++) {
             e = hot_next_b(fbase, p[q + i], e);
             if (MODE == 0) mx = max(mx, e);
             else if (e >= fthr) last = q + i;
-            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
           }
-          q += left;
         }
+        q += nb;
+        if (e < live || (MODE == 0 && mx >= fthr)) fin = true;
       }
-      if (e == 1u && !(MODE == 0 && mx >= fthr)) cold = true;  // trap row
+      if (!fin) continue;
+      const bool cold = e == 1u && !(MODE == 0 && mx >= fthr);  // trap row: the record left the hot set
       if (MODE == 0) {
-        hit = cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr;
+        if (cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr) set_bit(r);
       } else if (cold) {
-        hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
-      } else if (last != kNone) {
-        // ---- reverse from the match end (exec.rs:651-657; the record is its own slice) ----
-        me = last;
-        uint64_t start = kNone;
-        bool rcold = false;
-        if (me == 0) {
-          start = 0;
-        } else {
-          const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, me)];
-          const uint32_t hr = a.rev_hot.full2hot[sf];
-          if (sf == 0) {
-            start = kNone;
-          } else if (hr == 0xFFFFu) {
-            rcold = true;
-          } else {
-            uint32_t er = hr;
-            uint64_t at = me;
-            bool rdone = false;
-            while (at > 0 && !rdone) {
-              const uint8_t* wp = p + at - 16;  // window = bytes [at-16, at); only the last min(16, at) belong to the record
-              const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
-              const uint32_t nb = at >= 16 ? 16u : (uint32_t)at;
-              if (al >= a.text && al + 24 <= buf_hi) {
-                uint32_t v[4];
-                window16(wp, v);
-                uint32_t lj = ~0u;
-#pragma unroll
-                for (int i = 15; i >= 0; i--) {
-                  if ((uint32_t)(15 - i) < nb && !rdone) {
-                    er = hot_next_b(rbase, window_byte(v, i), er);
-                    if (er >= rthr) lj = i;
-                    if (er < rlive) rdone = true;
-                  }
-                }
-                if (lj != ~0u) start = at - 16 + lj + 1;
-                at -= nb;
-              } else {
-                for (uint32_t i = 0; i < nb && !rdone; i++) {
-                  at--;
-                  er = hot_next_b(rbase, p[at], er);
-                  if (er >= rthr) start = at + 1;
-                  if (er < rlive) rdone = true;
-                }
-              }
-            }
-            if (er == 1u) rcold = true;
-            else if (!rdone && a.rev_hot.eof[er] >= a.rev.match_lo) start = 0;
-          }
-        }
-        if (rcold) {
-          hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
-        } else if (start != kNone) {
-          hit = true;
-          ms = start;
-        }
-      }
-      if (MODE == 1) {
+        uint64_t ms = 0, me = 0;
+        const bool hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
         a.out_spans[2 * r] = hit ? ms : 0;
         a.out_spans[2 * r + 1] = hit ? me : 0;
+        if (hit) set_bit(r);
+      } else {
+        a.out_spans[2 * r] = last == kNone ? 0 : kPendingStart;
+        a.out_spans[2 * r + 1] = last == kNone ? 0 : last;
       }
+      have = false;
+      r += stride;
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) a.out_bits[r >> 5] = bits;
+  }
+  if (MODE == 0) return;
+  // ------------------------------------------------------------ reverse ----
+  // from the match end back over the record (exec.rs:651-657; the record is its own slice)
+  {
+    uint64_t r = first, len = 0, at = 0, start = kNone;
+    const uint8_t* p = nullptr;
+    uint32_t er = 0;
+    bool have = false;
+    for (;;) {
+      while (!have && r < a.n_rec) {
+        if (a.out_spans[2 * r] != kPendingStart) { r += stride; continue; }
+        const uint64_t lo = a.offsets[r];
+        len = a.offsets[r + 1] - lo;
+        p = a.text + lo;
+        at = a.out_spans[2 * r + 1];
+        start = kNone;
+        er = 0;
+        if (at == 0) {
+          start = 0;  // an empty match at the record's first position (exec.rs:647)
+        } else {
+          const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, at)];
+          const uint32_t hr = a.rev_hot.full2hot[sf];
+          er = sf == 0 ? 0u : (hr == 0xFFFFu ? 1u : hr);
+        }
+        have = true;
+      }
+      if (!__any_sync(0xffffffffu, have)) break;
+      if (!have) continue;
+      bool fin = false;
+      if (start == 0 || er < live) {
+        fin = true;
+      } else if (at == 0) {  // beginning of the record: the end-of-text step of the reverse scan
+        if (a.rev_hot.eof[er] >= a.rev.match_lo) start = 0;
+        fin = true;
+      } else {
+        const uint8_t* wp = p + at - 16;  // window = bytes [at-16, at); only the last min(16, at) belong to the record
+        const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+        const uint32_t nb = at >= 16 ? 16u : (uint32_t)at;
+        if (al >= a.text && al + 24 <= buf_hi) {
+          uint32_t v[4];
+          window16(wp, v);
+          uint32_t lj = ~0u;
+#pragma unroll
+          for (int i = 15; i >= 0; i--) {
+            if ((uint32_t)(15 - i) < nb && er >= live) {
+              er = hot_next_b(rbase, window_byte(v, i), er);
+              if (er >= rthr) lj = i;
+            }
+          }
+          if (lj != ~0u) start = at - 16 + lj + 1;
+          at -= nb;
+        } else {
+          for (uint32_t i = 0; i < nb && er >= live; i++) {
+            at--;
+            er = hot_next_b(rbase, p[at], er);
+            if (er >= rthr) start = at + 1;
+          }
+        }
+        if (er < live) fin = true;
+      }
+      if (!fin) continue;
+      if (er == 1u && start != 0) {  // trap row (or a start state outside the hot set): the full tables decide
+        uint64_t ms = 0, me = 0;
+        const bool hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+        a.out_spans[2 * r] = hit ? ms : 0;
+        a.out_spans[2 * r + 1] = hit ? me : 0;
+        if (hit) set_bit(r);
+      } else if (start != kNone) {
+        a.out_spans[2 * r] = start;
+        set_bit(r);
+      } else {
+        a.out_spans[2 * r] = 0;
+        a.out_spans[2 * r + 1] = 0;
+      }
+      have = false;
+      r += stride;
+    }
   }
 }
 template __global__ void batch_fast<0>(BatchArgs);
