@@ -212,6 +212,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO writes to stdout by default: the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n = int(args.gib * GIB)          # bytes owned per GPU (multiple of 256)

@@ -200,16 +200,19 @@ int Regex::check(int e, const char* what) {
   } while (0)
 
 // Stream, pinned scalars and timing events of this object.  Every copy and kernel of the
-// library is issued on stream_ (or on the two pipeline streams, ordered by events), never on
-// the legacy default stream: own_stream_ is non-blocking, so a default-stream copy would not
-// be ordered with the kernels that follow it.
+// library is issued on stream_ (or on the two pipeline streams, ordered by events).  The
+// library's own stream is a BLOCKING stream: it is ordered with the legacy default stream,
+// which is where a caller that never heard of streams (or torch's default stream) produced the
+// device buffers it hands to the *_device entry points -- a non-blocking stream raced with
+// `torch.zeros(...)` of the output buffer in the tests.  Callers on another stream pass it
+// with rure_b200_set_stream.
 int Regex::init_device() {
   if (!pinned_) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
       return fail("no CUDA device available: regex_b200 has no CPU matching path");
     cudaStream_t s;
-    RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamDefault));
     own_stream_ = s;
     RB_CUDA(cudaMallocHost(&pinned_, 4096));
     for (void*& e : timing_events_) {

@@ -2234,40 +2234,46 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
   auto set_bit = [&](uint64_t r) { atomicOr(&a.out_bits[r >> 5], 1u << (r & 31)); };
   // ------------------------------------------------------------ forward ----
   {
+    constexpr uint32_t kStartPending = 0xFFFFFFFEu;  // the start state needs the record's first byte (word-boundary flags)
     uint64_t r = first, len = 0, q = 0, last = kNone;
+    uint64_t nlo = 0, nhi = 0;  // offsets of record r, loaded one record ahead so that a lane changing records does not stall its warp
+    if (r < a.n_rec) { nlo = a.offsets[r]; nhi = a.offsets[r + 1]; }
     const uint8_t* p = nullptr;
     uint32_t e = 0, mx = 0;
     bool have = false;
     for (;;) {
       if (!have && r < a.n_rec) {
-        const uint64_t lo = a.offsets[r];
-        len = a.offsets[r + 1] - lo;
-        p = a.text + lo;
+        len = nhi - nlo;
+        p = a.text + nlo;
         q = 0;
         last = kNone;
         mx = 0;
-        const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
-        e = h0 == 0xFFFFu ? 1u : h0;
+        e = a.fwd.uniform_start ? a.fwd_hot.start : kStartPending;
         have = true;
+        const uint64_t rn = r + stride;
+        if (rn < a.n_rec) { nlo = a.offsets[rn]; nhi = a.offsets[rn + 1]; }
       }
       if (!__any_sync(0xffffffffu, have)) break;
       if (!have) continue;
-      bool fin = false;
       const uint64_t left = len - q;
-      if (e < live) {
-        fin = true;  // dead or outside the hot set from the start
-      } else if (left == 0) {  // end-of-text step (dfa.rs:748-763)
-        if (a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
-        fin = true;
-      } else {
+      auto start_state = [&](uint32_t b0, bool empty) {  // flags_forward(p, len, 0) without touching the haystack again
+        int f = 1 | 4;
+        if (empty) f |= 2 | 8;
+        f |= (!empty && is_word_byte(b0)) ? 16 : 32;
+        const uint32_t h0 = a.fwd_hot.full2hot[a.fwd_g->start[f]];
+        e = h0 == 0xFFFFu ? 1u : h0;
+      };
+      if (left != 0) {
         const uint8_t* wp = p + q;
         const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
         const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
         if (al + 24 <= buf_hi) {
           uint32_t v[4];
           window16(wp, v);
+          if (e == kStartPending) start_state(v[0] & 0xFFu, false);
           uint32_t lj = ~0u;
-          if (nb == 16) {
+          if (e < live) {
+          } else if (nb == 16) {
 #pragma unroll
             for (int g = 0; g < 4; g++) {
               e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
@@ -2288,6 +2294,7 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           }
           if (MODE == 1 && lj != ~0u) last = q + lj;
         } else {  // the last bytes of the whole buffer: byte loads
+          if (e == kStartPending) start_state(p[q], false);
           for (uint32_t i = 0; i < nb && e >= live; i++) {
             e = hot_next_b(fbase, p[q + i], e);
             if (MODE == 0) mx = max(mx, e);
@@ -2295,7 +2302,13 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
           }
         }
         q += nb;
-        if (e < live || (MODE == 0 && mx >= fthr)) fin = true;
+      } else if (e == kStartPending) {
+        start_state(0, true);
+      }
+      bool fin = e < live || (MODE == 0 && mx >= fthr);
+      if (!fin && q == len) {  // end-of-text step (dfa.rs:748-763), in the same trip as the record's last bytes
+        if (a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
+        fin = true;
       }
       if (!fin) continue;
       const bool cold = e == 1u && !(MODE == 0 && mx >= fthr);  // trap row: the record left the hot set
