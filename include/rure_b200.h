@@ -183,7 +183,8 @@ uint64_t rure_b200_kernel_launches(void);
 void rure_b200_last_stats(rure *re, double *out8);
 /* The same plus out[8..11] = sequential stitch passes, state-map passes (segments run from
  * every boundary state), waves of the last forward search, path of the last find_all
- * (0 generic scan, 1 fast scan, 2 fused scan+walk, 3 literal prefilter).  n = doubles to write. */
+ * (0 generic scan, 1 fast scan, 2 fused scan+walk, 3 literal prefilter), out[12] = matches longer
+ * than 256 KiB that were measured by the parallel long-run pass.  n = doubles to write. */
 void rure_b200_last_stats_ex(rure *re, double *out, size_t n);
 void rure_b200_set_last_stats_ex(rure_set *set, double *out, size_t n);
 /* Named knobs (tests, tuning): "wave0" bytes of the first wave of is_match / shortest_match /

@@ -23,7 +23,7 @@ DFA_FWD_ANCHORED_LF, DFA_REV_UNANCHORED_ALL, DFA_FWD_UNANCHORED_ALL, DFA_REV_ANC
 
 
 _STAT_KEYS = ["scan_ms", "walk_ms", "total_ms", "scan_redo_rounds", "scan_redo_segments", "stitch_rounds", "stitch_dirty_chunks",
-              "fused", "sequential_passes", "map_passes", "waves", "path"]
+              "fused", "sequential_passes", "map_passes", "waves", "path", "long_runs"]
 
 
 class Error(Exception):
@@ -447,8 +447,8 @@ class _Compiled:
 
     # ---- diagnostics ------------------------------------------------------------
     def last_stats(self):
-        out = (c_double * 12)()
-        _lib.rure_b200_last_stats_ex(self._h, out, 12)
+        out = (c_double * 13)()
+        _lib.rure_b200_last_stats_ex(self._h, out, 13)
         return dict(zip(_STAT_KEYS, list(out)))
 
     def set_option(self, name, value):
@@ -506,8 +506,8 @@ class _SetBase:
     _only_utf8 = False
 
     def last_stats(self):
-        out = (c_double * 12)()
-        _lib.rure_b200_set_last_stats_ex(self._h, out, 12)
+        out = (c_double * 13)()
+        _lib.rure_b200_set_last_stats_ex(self._h, out, 13)
         return dict(zip(_STAT_KEYS, list(out)))
 
     def set_option(self, name, value):

@@ -464,10 +464,11 @@ void rure_b200_last_stats(rure* re, double* out8) {
 }
 static void stats_ex(Regex* r, double* out, size_t n) {
   const rbgpu::Stats& s = r->stats;
-  const double v[12] = {s.scan_ms, s.walk_ms, s.total_ms, (double)s.scan_redo_rounds, (double)s.scan_redo_segments,
+  const double v[13] = {s.scan_ms, s.walk_ms, s.total_ms, (double)s.scan_redo_rounds, (double)s.scan_redo_segments,
                         (double)s.stitch_rounds, (double)s.stitch_dirty_chunks, s.fused ? 1.0 : 0.0,
-                        (double)s.sequential_passes, (double)s.map_passes, (double)s.waves, (double)s.path};
-  for (size_t i = 0; i < n && i < 12; i++) out[i] = v[i];
+                        (double)s.sequential_passes, (double)s.map_passes, (double)s.waves, (double)s.path,
+                        (double)s.long_runs};
+  for (size_t i = 0; i < n && i < 13; i++) out[i] = v[i];
 }
 void rure_b200_last_stats_ex(rure* re, double* out, size_t n) { stats_ex(re->re, out, n); }
 void rure_b200_set_last_stats_ex(rure_set* set, double* out, size_t n) { stats_ex(set->re, out, n); }

@@ -402,6 +402,102 @@ bool Regex::plan_prefilter() {
   return true;
 }
 
+// ------------------------------------------------------------ long matches ----
+// End of the leftmost-first match anchored at s when it is too long for one thread: the
+// anchored automaton over [s, n) in 4 KiB segments, every segment entered in its exact state
+// (state maps from EVERY state of the automaton, composed -- the states of `(?s)foo.*bar`
+// after `foo` never converge, so no warm-up guess would do), then a maximum over the last match
+// positions.  (states + 2) generic passes over the run instead of ~10 s per GiB for one thread.
+int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool text_continues, uint64_t* e_out) {
+  DeviceDfa* fwd;
+  if (int rc = ensure(kFwdAnchoredLF, &fwd)) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const uint32_t k = fwd->view.n_states;
+  const uint32_t seg = 4096;
+  ScanArgs g{};
+  g.dfa = fwd->view;
+  const size_t smem = smem_for(fwd->view);
+  g.use_smem = smem != 0;
+  g.text = d_text;
+  g.n = n;
+  g.base = s;
+  g.seg = seg;
+  uint32_t* counters = (uint32_t*)counters_.ptr;
+  uint16_t* d_states = (uint16_t*)kstates_.ensure(k * 2);
+  uint16_t* d_kidx = (uint16_t*)kidx_.ensure(65536 * 2);
+  uint16_t* d_first = (uint16_t*)present_.ensure(65536);  // (two bytes of it: the entry state of the first segment)
+  if (!d_states || !d_kidx || !d_first) return fail("out of device memory (long run)");
+  std::vector<uint16_t> ident(k);
+  for (uint32_t i = 0; i < k; i++) ident[i] = (uint16_t)i;
+  RB_CUDA(cudaMemcpyAsync(d_states, ident.data(), k * 2, cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(d_kidx, ident.data(), k * 2, cudaMemcpyHostToDevice, st));
+  // the start state at s: the look-behind flags come from the bytes next to s (pick_start_fwd)
+  uint16_t start_state = fwd->view.start[32];
+  if (!fwd->view.uniform_start) {
+    uint8_t around[2] = {0, 0};
+    const uint64_t lo = s ? s - 1 : 0, hi = std::min(n, s + 1);
+    RB_CUDA(d2h(around, d_text + lo, hi - lo));
+    const bool has_prev = s > 0, has_cur = s < n;
+    const uint8_t prev = has_prev ? around[0] : 0, cur = has_cur ? around[has_prev ? 1 : 0] : 0;
+    auto word = [](uint8_t b) { return (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || (b >= '0' && b <= '9') || b == '_'; };
+    int f = 0;
+    if (s == 0) f |= 1;
+    if (n == 0) f |= 2 | 8;
+    if (s == 0 || prev == '\n') f |= 4;
+    const bool last = has_prev && word(prev), cw = has_cur && word(cur);
+    f |= (last == cw) ? 32 : 16;
+    if (last) f |= 64;
+    start_state = fwd->view.start[f];
+  }
+  RB_CUDA(cudaMemcpyAsync(d_first, &start_state, 2, cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));  // `ident` and `start_state` leave scope below
+  RB_CUDA(allow_smem(scan_map, smem));
+  RB_CUDA(allow_smem(scan_last_match, smem));
+  // growing windows from s: a long match is rarely the whole rest of the haystack
+  for (uint64_t window = 8ull << 20;; window *= 8) {
+    const uint64_t end = window >= n - s ? n : s + window;
+    const uint64_t n_seg = std::max<uint64_t>(1, (end - s + seg - 1) / seg);
+    const uint64_t n_blocks = (n_seg + kMapBlock - 1) / kMapBlock;
+    g.limit = end;
+    g.n_seg = n_seg;
+    uint16_t* maps = (uint16_t*)maps_.ensure(n_seg * k * 2);
+    uint16_t* comp = (uint16_t*)comp_.ensure(n_blocks * k * 2);
+    uint16_t* bentry = (uint16_t*)bentry_.ensure(n_blocks * 2);
+    uint16_t* exact = (uint16_t*)exact_.ensure(n_seg * 2);
+    if (!maps || !comp || !bentry || !exact) return fail("out of device memory (long run)");
+    scan_map<<<grid_for(n_seg * k, 256, tuning.blocks_per_sm), 256, smem, st>>>(g, 0, d_states, k, maps);
+    RB_LAUNCH_CHECK("scan_map");
+    compose_blocks<<<(uint32_t)((n_blocks * k + 255) / 256), 256, 0, st>>>(maps, d_kidx, d_states, k, n_seg, 0, comp);
+    RB_LAUNCH_CHECK("compose_blocks");
+    compose_top<<<1, 32, 0, st>>>(comp, d_kidx, k, n_blocks, 0, d_first, bentry);
+    RB_LAUNCH_CHECK("compose_top");
+    compose_fill<<<(uint32_t)((n_blocks + 255) / 256), 256, 0, st>>>(maps, d_kidx, k, n_seg, 0, bentry, exact);
+    RB_LAUNCH_CHECK("compose_fill");
+    unsigned long long* best = (unsigned long long*)(counters + 8);
+    RB_CUDA(cudaMemsetAsync(best, 0, 12, st));  // best, then the alive flag at counters[10]
+    scan_last_match<<<grid_for(n_seg, 256, tuning.blocks_per_sm), 256, smem, st>>>(g, exact, best, counters + 10);
+    RB_LAUNCH_CHECK("scan_last_match");
+    uint32_t h[4] = {0, 0, 0, 0};
+    RB_CUDA(d2h(h, best, 12));
+    stats.map_passes += k;
+    const bool alive = h[2] != 0;
+    if (alive && end < n) continue;
+    const uint64_t found = (uint64_t)h[0] | ((uint64_t)h[1] << 32);
+    if (alive && text_continues) {
+      // the run meets the end of a shard's halo: the same verdict as the walk kernels give (err_flag), read
+      // by the caller once the search is through
+      const uint32_t one = 1;
+      RB_CUDA(cudaMemcpyAsync(counters + 28, &one, 4, cudaMemcpyHostToDevice, st));
+      RB_CUDA(cudaStreamSynchronize(st));
+      *e_out = found ? found - 1 : n;
+      return 0;
+    }
+    if (found == 0) return fail("internal error: a candidate start has no match (long run)");
+    *e_out = found - 1;
+    return 0;
+  }
+}
+
 // ------------------------------------------------- bounded fix-up of entry states --
 // Exact entry state of every segment by state-map composition (kernels.cu, "exact entry states"):
 // K = the states seen at segment boundaries, closed under the per-segment maps; on return
@@ -699,6 +795,16 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   // entry states: chunk 0 starts the real chain at `start`; the rest speculate.
   w.err_flag = counters + 28;
   w.floor_flag = counters + 29;
+  // long anchored runs go to resolve_long_run (automata of up to 128 states); counters[6..7] = the request slot
+  const bool can_resolve = fwd->view.n_states <= 128;
+  uint64_t* long_tab = (uint64_t*)long_tab_.ensure(kMaxLongRuns * 16);
+  if (!long_tab) return fail("out of device memory (long runs)");
+  uint32_t n_long = 0;
+  w.exact_cap = can_resolve ? kExactRunCap : kNone;
+  w.long_tab = long_tab;
+  w.n_long = 0;
+  w.long_req = (unsigned long long*)(counters + 6);
+  RB_CUDA(cudaMemsetAsync(w.long_req, 0xFF, 8, st));
   w.clamp_p = io->chain_clamped ? io->chain_p : kNone;
   RB_CUDA(cudaMemsetAsync(w.err_flag, 0, 8, st));
   init_walk_entries<<<grid_for(nc, 256, 8), 256, 0, st>>>(w.in_p, w.in_lm, w.skip, nc, io->chain_p, io->chain_lm);
@@ -764,7 +870,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     }
   }
   // ---- stitch: bring the speculative chunk walks into agreement with the sequential iterator ----
-  stats.stitch_rounds = stats.stitch_dirty_chunks = stats.sequential_passes = 0;
+  stats.stitch_rounds = stats.stitch_dirty_chunks = stats.sequential_passes = stats.long_runs = 0;
   const bool strict = emulate || can_match_empty;
   bool general = strict;
   uint32_t* hc = (uint32_t*)pinned_ + 64;  // host copy of counters[0..3]
@@ -774,7 +880,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     RB_LAUNCH_CHECK("stitch_fast");
     RB_CUDA(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
-    general = hc[2] != 0;
+    general = hc[2] != 0;  // (a deferred chunk -- long run -- asks for the general loop too)
   }
   ChainKey* grand_key = nullptr;
   if (general) {
@@ -787,7 +893,8 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
     wd.n_dirty = counters;
     uint32_t dirty_rounds = 0;
     for (;;) {
-      entries_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w, excl, btot);
+      RB_CUDA(cudaMemsetAsync(counters + 12, 0xFF, 4, st));  // [12] leftmost deferred chunk
+      entries_local<<<(uint32_t)n_blocks, 1024, 0, st>>>(w, excl, btot, counters + 12);
       RB_LAUNCH_CHECK("entries_local");
       entries_blocks<<<1, 1024, 0, st>>>(btot, n_blocks, grand_key);
       RB_LAUNCH_CHECK("entries_blocks");
@@ -795,10 +902,33 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
       RB_CUDA(cudaMemsetAsync(counters + 3, 0xFF, 4, st));  // [3] smallest chunk index to walk again
       stitch_resolve<<<grid_for(nc, 256, 8), 256, 0, st>>>(wd, excl, btot, counters);
       RB_LAUNCH_CHECK("stitch_resolve");
-      RB_CUDA(cudaMemcpyAsync(hc, counters, 16, cudaMemcpyDeviceToHost, st));
+      RB_CUDA(cudaMemcpyAsync(hc, counters, 32, cudaMemcpyDeviceToHost, st));
       RB_CUDA(cudaStreamSynchronize(st));
       const uint32_t n_dirty = hc[0], n_changed = hc[1];
-      if (n_dirty == 0 && n_changed == 0) break;
+      const uint64_t long_s = *(const uint64_t*)(hc + 6);
+      bool serve = long_s != kNone;
+      if (serve) {
+        // the request of a chunk that this round found covered by an earlier match is dropped
+        uint32_t m = 0;
+        RB_CUDA(d2h(&m, w.meta + (long_s - w.base) / w.chunk, 4));
+        serve = (m >> 30) == kChunkDeferred;
+        if (!serve) RB_CUDA(cudaMemsetAsync(w.long_req, 0xFF, 8, st));
+      }
+      if (serve) {
+        // a chunk walked from its exact entry met a match longer than kExactRunCap: measure it in parallel,
+        // remember it, and let the stitch walk the deferred chunk again
+        if (n_long == kMaxLongRuns) return fail("more than 256 matches longer than 256 KiB in one search");
+        uint64_t e = kNone;
+        if (int rc = resolve_long_run(d_text, n, long_s, !io->is_last, &e)) return rc;
+        const uint64_t pair[2] = {long_s, e};
+        RB_CUDA(cudaMemcpyAsync(long_tab + 2 * n_long, pair, 16, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemsetAsync(w.long_req, 0xFF, 8, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        n_long++;
+        w.n_long = wd.n_long = n_long;
+        stats.long_runs++;
+      }
+      if (n_dirty == 0 && n_changed == 0 && !serve) break;
       stats.stitch_rounds++;
       stats.stitch_dirty_chunks += n_dirty;
       if (n_dirty == 0) continue;
@@ -1207,7 +1337,6 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
     const size_t fsm = hot_bytes(fwd->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<0>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
-    RB_CUDA(cudaMemsetAsync(d_bits, 0, (n_rec + 31) / 32 * 4, (cudaStream_t)stream_));  // the lanes set bits with atomicOr
     batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
     RB_LAUNCH_CHECK("batch_fast<0>");
   } else {
@@ -1242,7 +1371,6 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
     const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
     RB_CUDA(allow_smem(batch_fast<1>, fsm));
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
-    RB_CUDA(cudaMemsetAsync(d_bits, 0, (n_rec + 31) / 32 * 4, (cudaStream_t)stream_));
     batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
     RB_LAUNCH_CHECK("batch_fast<1>");
   } else {

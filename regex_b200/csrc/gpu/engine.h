@@ -44,7 +44,7 @@ struct Tuning {
 
 struct Stats {  // filled by the last single-haystack call (diagnostics, bench roofline)
   uint64_t scan_redo_rounds = 0, scan_redo_segments = 0;
-  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0, sequential_passes = 0, map_passes = 0, waves = 0;
+  uint64_t stitch_rounds = 0, stitch_dirty_chunks = 0, sequential_passes = 0, map_passes = 0, waves = 0, long_runs = 0;
   float scan_ms = 0, walk_ms = 0, total_ms = 0;
   bool fused = false;  // the scan kernel also walked the chains (scan_ms covers both)
   int path = 0;        // last find_all: 0 generic scan, 1 fast scan, 2 fused scan + walk, 3 literal prefilter
@@ -164,6 +164,7 @@ class Regex {
   int scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_t limit, ShardIO* io, const ScanPlan& plan,
                   const void* fused_walk);
   int solve_entries(const void* scan_args, bool reverse);
+  int resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool text_continues, uint64_t* e_out);
   int all_spans_device(const uint8_t* d_text, uint64_t n, uint64_t** d_spans, uint64_t* m);
   int ensure_capture_program();
   int replace_prepare(const uint8_t* d_text, uint64_t n, const uint8_t* rep, uint64_t rep_len, bool expand, uint64_t limit, uint64_t* out_len);
@@ -197,6 +198,8 @@ class Regex {
   bool use_ext_stream_ = false;
   // scratch (grow-only)
   DeviceBuf text_, offsets_, bitmap_, guess_, fin_, redo_, counters_, seg_first_, seg_mask_;
+  DeviceBuf long_tab_;
+  static constexpr uint32_t kMaxLongRuns = 256;
   DeviceBuf spans_all_, lens_, lits_, rep_out_, pieces_, reps_before_;
   uint64_t rep_totals_[2] = {0, 0};  // matched bytes, replacement bytes of the pending replace call
   std::vector<uint8_t> rep_args_, rep_lits_;  // launch.h ReplaceArgs image + literal bytes of the pending replace call

@@ -398,6 +398,29 @@ __global__ void publish_exact(const uint16_t* exact, uint64_t n_seg, int reverse
   }
 }
 
+// One long anchored run, in parallel (engine.cu resolve_long_run): every segment is entered in its
+// exact state (state-map composition), so "the last position at which the leftmost-first
+// automaton was in a match state before it died" is a maximum over segments.
+__global__ void scan_last_match(ScanArgs a, const uint16_t* exact, unsigned long long* best, uint32_t* alive_at_end) {
+  const Table T = stage_table(a.dfa, g_smem, a.use_smem);
+  const uint32_t match_lo = a.dfa.match_lo;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < a.n_seg; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t s = exact[t];
+    if (s == 0) continue;  // the run died further left
+    const uint64_t lo = a.base + t * a.seg, hi = min(lo + a.seg, a.limit);  // a.limit: end of the window (<= n)
+    uint64_t last = kNone;
+    for (uint64_t q = lo; q < hi && s != 0; q++) {
+      s = T.step(s, a.text[q]);
+      if (s >= match_lo) last = q;
+    }
+    if (hi == a.limit && s != 0) {
+      *alive_at_end = 1;  // the run goes on past the window (or meets the end of the text)
+      if (a.limit == a.n && T.step_eof(s) >= match_lo) last = a.n;
+    }
+    if (last != kNone) atomicMax(best, (unsigned long long)last + 1);
+  }
+}
+
 // result[0] = min first-match position, result[1..] = OR of masks.
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result) {
@@ -598,6 +621,20 @@ struct Chain {
   bool chain;      // p is a real restart point of the reference iterator
 };
 
+// End of the match anchored at s for a chunk walk.  Speculative walks give up early (kSpecRunCap);
+// walks from an exact entry state take matches of up to exact_cap bytes themselves, look longer
+// ones up in the table of runs the host has measured with a parallel scan, and otherwise ask for
+// that (long_req) -- in both cases kTooLong defers the chunk.
+template <typename Runner>
+__device__ __forceinline__ uint64_t run_end(const WalkArgs& a, const Runner& T, uint64_t s, bool exact) {
+  if (exact)
+    for (uint32_t i = 0; i < a.n_long; i++)
+      if (a.long_tab[2 * i] == s) return a.long_tab[2 * i + 1];
+  const uint64_t e = T.end_from(a, s, exact ? a.exact_cap : kSpecRunCap);
+  if (e == kTooLong && exact) atomicMin(a.long_req, (unsigned long long)s);
+  return e;
+}
+
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
                                                       uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz);
@@ -618,7 +655,7 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
   const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
   uint64_t fc = kNone;
-  const uint64_t run_cap = c.chain ? kNone : kSpecRunCap;  // only an exact entry state justifies an arbitrarily long run
+  const bool exact = c.chain;  // only an exact entry state justifies a long run
   uint64_t cached_w = kNone, word = 0;
   uint64_t pf_w = kNone, pf_word = 0;  // next candidate word, load issued ahead of use
   const uint64_t w0 = cb >> 6, w_end = (ce + 63) >> 6;
@@ -659,7 +696,7 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
       s = (bit & ~63ull) + (uint64_t)__ffsll((long long)m);
     }
     if (fc == kNone) fc = s;
-    const uint64_t e = T.end_from(a, s, run_cap);
+    const uint64_t e = run_end(a, T, s, exact);
     if (e == kTooLong) { *first_cand = kTooLong; return 0; }  // deferred: see kSpecRunCap
     if (e == kNone) { c.p = s + 1; c.chain = false; continue; }  // unreachable for consistent tables
     uint64_t ms = s;
@@ -700,7 +737,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
   uint32_t total = 0;
   uint64_t fc = kNone;
-  const uint64_t run_cap = c.chain ? kNone : kSpecRunCap;
+  const bool exact = c.chain;
   // Spans leave two at a time as whole 32-byte sectors when the destination allows it
   // (staging areas do): the even span of a pair waits in registers for the odd one.
   const bool pair_stores = ((uintptr_t)o & 31) == 0;
@@ -727,7 +764,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   if (c.p == kNone) { *first_cand = fc; return 0; }
   if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
     fc = 0;
-    const uint64_t e = T.end_from(a, 0, run_cap);
+    const uint64_t e = run_end(a, T, 0, exact);
     if (e == kTooLong) { *first_cand = kTooLong; return 0; }
     if (e == kNone) { c.p = 1; c.chain = false; }
     else { emit(0, e); c.p = c.lm = e; c.chain = true; }
@@ -750,7 +787,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
     const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
     const uint64_t s = cb + sr + 1;
     if (fc == kNone) fc = s;
-    const uint64_t e = T.end_from(a, s, run_cap);
+    const uint64_t e = run_end(a, T, s, exact);
     if (e == kTooLong) { *first_cand = kTooLong; return 0; }
     if (e == kNone) {  // unreachable for consistent tables
       cur &= cur - 1;
@@ -962,7 +999,12 @@ __device__ __forceinline__ uint32_t flags_to_bits(uint32_t t) {  // bits 7,15,23
 // streaming loop stays small (the first version inlined it three times and starved on
 // instruction fetch: ncu "no instruction" 7.9 stalls per issue).
 template <typename Runner>
-__device__ __noinline__ uint64_t pf_verify(const WalkArgs* a, const Runner* R, uint64_t s) { return R->end_from(*a, s); }
+__device__ __noinline__ uint64_t pf_verify(const WalkArgs* a, const Runner* R, uint64_t s, bool exact) {
+  if (exact)
+    for (uint32_t i = 0; i < a->n_long; i++)
+      if (a->long_tab[2 * i] == s) return a->long_tab[2 * i + 1];
+  return R->end_from(*a, s, exact ? a->exact_cap : kSpecRunCap);  // kTooLong: the caller defers the chunk (run_end)
+}
 
 // Is a match possible with its scanned byte at q?  Tests the bytes at the first offsets of the
 // would-be match against the sets the automaton allows there (the set at offset o holds
@@ -1013,6 +1055,9 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
   uint64_t total = 0, fc = kNone;
   uint64_t p = c.p, lm = c.lm;               // warp-uniform iterator state
   uint32_t cnt = 0;                          // queued hits of this lane
+  const bool exact = c.chain;
+  uint64_t long_s = kNone;                   // uniform: a match the iterator needs ran past the cap (chunk deferred)
+  constexpr uint32_t kLenAgain = 0xFFFFFFFFu, kLenTooLong = 0xFFFFFFFEu;
   auto accept = [&](uint64_t s, uint64_t e) {  // uniform arguments
     if (s < p) return;
     if (fc == kNone) fc = s;
@@ -1033,8 +1078,9 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
         const uint64_t s = pf_candidate(a, pf, sets, q);  // includes the byte at q itself (the set at offset o)
         uint32_t len = 0;
         if (s != kNone && s >= p) {
-          const uint64_t e = pf_verify(&a, &R, s);
-          if (e != kNone) len = (uint32_t)min(e - s, (uint64_t)0xFFFFFFFFu);
+          const uint64_t e = pf_verify(&a, &R, s, exact);
+          if (e == kTooLong) len = kLenTooLong;
+          else if (e != kNone) len = e - s >= kLenTooLong ? kLenAgain : (uint32_t)(e - s);
         }
         qlen[r * 32 + lane] = len;
       }
@@ -1050,8 +1096,11 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
       const int owner = __ffs(__ballot_sync(0xffffffffu, key == m)) - 1;
       const uint32_t len = __shfl_sync(0xffffffffu, cur < cnt ? qlen[cur * 32 + lane] : 0u, owner);
       const uint64_t s = cb + m - pf.o;
-      accept(s, len == 0xFFFFFFFFu ? pf_verify(&a, &R, s) : s + len);  // a match of 4 GiB or more: ask again for its end
       if ((int)lane == owner) cur++;
+      if (s < p) continue;  // inside the match accepted before it
+      const uint64_t e = len == kLenTooLong ? kTooLong : len == kLenAgain ? pf_verify(&a, &R, s, exact) : s + len;  // (4 GiB or more: ask again)
+      if (e == kTooLong) { long_s = s; break; }
+      accept(s, e);
     }
     cnt = 0;
     __syncwarp();
@@ -1118,17 +1167,24 @@ __device__ __forceinline__ uint64_t pf_walk_chunk(const WalkArgs& a, const PfArg
             for (uint32_t i = 0; i < pf.n_bytes; i++) is = is || byte == (pf.bcast[i] & 0xFFu);
             if (!is) continue;
             const uint64_t s = pf_candidate(a, pf, sets, q);
-            if (s == kNone || s < p) continue;
-            const uint64_t e = pf_verify(&a, &R, s);
-            if (e != kNone) accept(s, e);
+            if (s == kNone || s < p || long_s != kNone) continue;
+            const uint64_t e = pf_verify(&a, &R, s, exact);
+            if (e == kTooLong) long_s = s;
+            else if (e != kNone) accept(s, e);
           }
         }
       }
     } else if (__any_sync(0xffffffffu, cnt + 2 > kPfSlots)) {
       flush();  // little room left: empty the queues before the next piece
     }
+    if (long_s != kNone) break;
   }
-  flush();
+  if (long_s == kNone) flush();
+  if (long_s != kNone) {  // as chunk_walk: nothing of this walk counts, the stitch walks the chunk again
+    if (exact && lane == 0) atomicMin(a.long_req, (unsigned long long)long_s);
+    *first_cand = kTooLong;
+    return 0;
+  }
   c.p = p;
   c.lm = lm;
   if (total) c.chain = true;
@@ -1161,6 +1217,7 @@ __global__ void __launch_bounds__(256, 3) literal_scan(const __grid_constant__ W
       const uint64_t total = pf_walk_chunk<NB>(a, pf, sets, wq, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
       if (spec && total == 0) { c.p = a.base + k * (uint64_t)a.chunk + 1; }
       if (lane == 0) finish_chunk(a, k, c, total, fc, spec);
+      if (fc == kTooLong) return;  // as walk_sequential
       c.chain = true;
     }
     return;
@@ -1676,11 +1733,12 @@ __global__ void stitch_fast(WalkArgs a, uint32_t* counters) {
 }
 
 // Exclusive scan of the chunk contributions inside blocks of blockDim.x chunks.
-__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot) {
+__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot, uint32_t* first_deferred) {
   __shared__ ChainKey ws[32];
   const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   ChainKey mine = k < a.n_chunks ? chunk_contribution(a, k) : ChainKey{0, kNone};
+  if (k < a.n_chunks && (a.meta[k] >> 30) == kChunkDeferred) atomicMin(first_deferred, (uint32_t)k);
   ChainKey x = mine;
   for (int o = 1; o < 32; o <<= 1) {
     ChainKey y{__shfl_up_sync(0xffffffffu, x.key, o), __shfl_up_sync(0xffffffffu, x.lm, o)};
@@ -1744,9 +1802,13 @@ __global__ void entries_blocks(ChainKey* block_tot, uint64_t n_blocks, ChainKey*
 
 __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey* block_tot, uint32_t* counters) {
   const bool strict = a.emulate_slice || a.can_match_empty;
+  const uint64_t deferred_hi = (uint64_t)counters[12] + kDeferredWindow;  // counters[12]: entries_local's leftmost deferred chunk
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < a.n_chunks;
        k += (uint64_t)gridDim.x * blockDim.x) {
-    if (k == 0) continue;  // chunk 0 holds the real entry state
+    if (k == 0) {  // chunk 0 holds the real entry state; it is walked again only after a long run was handed to the host
+      if ((a.meta[0] >> 30) == kChunkDeferred) { a.dirty_list[atomicAdd(&counters[0], 1u)] = 0; atomicMin(&counters[3], 0u); }
+      continue;
+    }
     const uint32_t meta = a.meta[k];
     const uint32_t state = meta >> 30, cnt = meta & kMetaCount;
     if (state == kChunkIdent) continue;
@@ -1756,6 +1818,7 @@ __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey*
       const uint64_t own_first = a.base + k * (uint64_t)a.chunk + 1;
       const bool as_is = spec ? (state == kChunkOk && a.skip[k] == 0 && !(meta & kMetaPatched))
                               : (state == kChunkOk && a.in_p[k] == own_first && a.in_lm[k] == kNone);  // a deferred chunk walked again without the cap
+      if (state == kChunkDeferred && k >= deferred_hi) continue;  // waits for the deferred chunks further left
       if (!as_is) {
         a.dirty_list[atomicAdd(&counters[0], 1u)] = (uint32_t)k;
         a.in_p[k] = state == kChunkDeferred ? own_first : kSpec;
@@ -1773,6 +1836,8 @@ __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey*
     if (tp == kNone || tp > ce) {
       new_state = kChunkCovered;
       new_count = 0;
+    } else if (state == kChunkDeferred && k >= deferred_hi) {
+      continue;  // waits for the deferred chunks further left (most likely one of their matches covers it)
     } else if (spec && state == kChunkDeferred) {
       rewalk = true;
     } else if (spec) {
@@ -1793,7 +1858,8 @@ __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey*
         else new_count = cnt - new_skip;
       }
     } else {
-      rewalk = a.in_p[k] != tp || (strict && a.in_lm[k] != tl);
+      // (a deferred chunk walked from its exact entry is waiting for the host to measure a long run)
+      rewalk = state == kChunkDeferred || a.in_p[k] != tp || (strict && a.in_lm[k] != tl);
     }
     if (rewalk) {
       a.in_p[k] = tp;
@@ -1830,6 +1896,7 @@ __global__ void __launch_bounds__(256) walk_sequential(WalkArgs a) {
     uint64_t fc = kNone, total = 0;
     if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
     finish_chunk(a, k, c, total, fc, spec);
+    if (fc == kTooLong) return;  // a long run went to the host: the stitch loop resumes from this chunk once it is measured
     c.chain = true;  // an IDENT first chunk hands on its assumed first position: nothing lies before it in this shard
   }
 }
@@ -2210,16 +2277,6 @@ __device__ __noinline__ bool slow_find_record(const DfaView* f, const DfaView* r
 
 // MODE 0: is_match (forward all-match automaton, stop at the first match state);
 // MODE 1: find (forward leftmost-first end, then the reverse longest automaton for the start).
-//
-// Every lane works through its own records (r = thread id, + grid size, ...) in a flat loop
-// whose body is ONE step of at most 16 bytes of whatever record the lane is on; a lane that
-// finishes a record fetches its next one in the same trip.  The round-1 kernel kept the 32
-// lanes of a warp on the same record index (a ballot wrote their bits): 70 % of the log lines
-// match within 20 bytes, so most lanes idled until the slowest line of the warp was done
-// (ncu r02: 8.5 of 32 threads per instruction).  Results leave by atomicOr (bits, zeroed by the
-// host) and per-record stores.  MODE 1 runs two such loops: all forward scans (the end, with
-// the start marked pending), then all reverse scans, each lane over the records it scanned.
-constexpr uint64_t kPendingStart = ~0ull - 1;
 template <int MODE>
 __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
   const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
@@ -2227,184 +2284,138 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
   hot_stage(a.fwd_hot, fbase);
   if (MODE == 1) hot_stage(a.rev_hot, rbase);
   __syncthreads();
-  const uint32_t fthr = a.fwd_hot.match_lo, rthr = a.rev_hot.match_lo, live = 2;
+  const uint32_t fthr = a.fwd_hot.match_lo, flive = 2;
+  const uint32_t rthr = a.rev_hot.match_lo, rlive = 2;
   const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  auto set_bit = [&](uint64_t r) { atomicOr(&a.out_bits[r >> 5], 1u << (r & 31)); };
-  // ------------------------------------------------------------ forward ----
-  {
-    constexpr uint32_t kStartPending = 0xFFFFFFFEu;  // the start state needs the record's first byte (word-boundary flags)
-    uint64_t r = first, len = 0, q = 0, last = kNone;
-    uint64_t nlo = 0, nhi = 0;  // offsets of record r, loaded one record ahead so that a lane changing records does not stall its warp
-    if (r < a.n_rec) { nlo = a.offsets[r]; nhi = a.offsets[r + 1]; }
-    const uint8_t* p = nullptr;
-    uint32_t e = 0, mx = 0;
-    bool have = false;
-    for (;;) {
-      if (!have && r < a.n_rec) {
-        len = nhi - nlo;
-        p = a.text + nlo;
-        q = 0;
-        last = kNone;
-        mx = 0;
-        e = a.fwd.uniform_start ? a.fwd_hot.start : kStartPending;
-        have = true;
-        const uint64_t rn = r + stride;
-        if (rn < a.n_rec) { nlo = a.offsets[rn]; nhi = a.offsets[rn + 1]; }
-      }
-      if (!__any_sync(0xffffffffu, have)) break;
-      if (!have) continue;
-      const uint64_t left = len - q;
-      auto start_state = [&](uint32_t b0, bool empty) {  // flags_forward(p, len, 0) without touching the haystack again
-        int f = 1 | 4;
-        if (empty) f |= 2 | 8;
-        f |= (!empty && is_word_byte(b0)) ? 16 : 32;
-        const uint32_t h0 = a.fwd_hot.full2hot[a.fwd_g->start[f]];
-        e = h0 == 0xFFFFu ? 1u : h0;
-      };
-      if (left != 0) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // multiple of 32: warps stay on one ballot word
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r - lane < a.n_rec; r += stride) {
+    bool hit = false;
+    uint64_t ms = 0, me = 0;
+    if (r < a.n_rec) {
+      const uint64_t lo = a.offsets[r], len = a.offsets[r + 1] - lo;
+      const uint8_t* p = a.text + lo;
+      bool cold = false;
+      // ---- forward ----
+      const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
+      uint32_t e = h0 == 0xFFFFu ? 1u : h0;
+      uint64_t last = kNone;
+      uint32_t mx = 0;
+      uint64_t q = 0;
+      bool done = false;
+      while (!done) {
+        const uint64_t left = len - q;
+        if (left == 0) {  // EOF step
+          if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
+          break;
+        }
         const uint8_t* wp = p + q;
         const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
-        const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
         if (al + 24 <= buf_hi) {
           uint32_t v[4];
           window16(wp, v);
-          if (e == kStartPending) start_state(v[0] & 0xFFu, false);
+          const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
           uint32_t lj = ~0u;
-          if (e < live) {
-          } else if (nb == 16) {
+          if (nb == 16) {
 #pragma unroll
             for (int g = 0; g < 4; g++) {
               e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
               e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
               e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
               e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
-              if (e < live || (MODE == 0 && mx >= fthr)) break;
+              if (e < flive || (MODE == 0 && mx >= fthr)) { done = true; break; }
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 15; i++) {
-              if ((uint32_t)i < nb && e >= live) {
+              if ((uint32_t)i < nb) {
                 e = hot_next_b(fbase, window_byte(v, i), e);
                 if (MODE == 0) mx = max(mx, e);
                 else if (e >= fthr) lj = i;
               }
             }
+            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
           }
           if (MODE == 1 && lj != ~0u) last = q + lj;
+          q += nb;
         } else {  // the last bytes of the whole buffer: byte loads
-          if (e == kStartPending) start_state(p[q], false);
-          for (uint32_t i = 0; i < nb && e >= live; i++) {
+          for (uint64_t i = 0; i < left && !done; i++) {
             e = hot_next_b(fbase, p[q + i], e);
             if (MODE == 0) mx = max(mx, e);
             else if (e >= fthr) last = q + i;
+            if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
           }
+          q += left;
         }
-        q += nb;
-      } else if (e == kStartPending) {
-        start_state(0, true);
       }
-      bool fin = e < live || (MODE == 0 && mx >= fthr);
-      if (!fin && q == len) {  // end-of-text step (dfa.rs:748-763), in the same trip as the record's last bytes
-        if (a.fwd_hot.eof[e] >= a.fwd.match_lo) { last = len; mx = 0xFFFFFFFFu; }
-        fin = true;
-      }
-      if (!fin) continue;
-      const bool cold = e == 1u && !(MODE == 0 && mx >= fthr);  // trap row: the record left the hot set
+      if (e == 1u && !(MODE == 0 && mx >= fthr)) cold = true;  // trap row
       if (MODE == 0) {
-        if (cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr) set_bit(r);
+        hit = cold ? slow_is_match_record(a.fwd_g, p, len) : mx >= fthr;
       } else if (cold) {
-        uint64_t ms = 0, me = 0;
-        const bool hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
-        a.out_spans[2 * r] = hit ? ms : 0;
-        a.out_spans[2 * r + 1] = hit ? me : 0;
-        if (hit) set_bit(r);
-      } else {
-        a.out_spans[2 * r] = last == kNone ? 0 : kPendingStart;
-        a.out_spans[2 * r + 1] = last == kNone ? 0 : last;
-      }
-      have = false;
-      r += stride;
-    }
-  }
-  if (MODE == 0) return;
-  // ------------------------------------------------------------ reverse ----
-  // from the match end back over the record (exec.rs:651-657; the record is its own slice)
-  {
-    uint64_t r = first, len = 0, at = 0, start = kNone;
-    const uint8_t* p = nullptr;
-    uint32_t er = 0;
-    bool have = false;
-    for (;;) {
-      while (!have && r < a.n_rec) {
-        if (a.out_spans[2 * r] != kPendingStart) { r += stride; continue; }
-        const uint64_t lo = a.offsets[r];
-        len = a.offsets[r + 1] - lo;
-        p = a.text + lo;
-        at = a.out_spans[2 * r + 1];
-        start = kNone;
-        er = 0;
-        if (at == 0) {
-          start = 0;  // an empty match at the record's first position (exec.rs:647)
+        hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+      } else if (last != kNone) {
+        // ---- reverse from the match end (exec.rs:651-657; the record is its own slice) ----
+        me = last;
+        uint64_t start = kNone;
+        bool rcold = false;
+        if (me == 0) {
+          start = 0;
         } else {
-          const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, at)];
+          const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, me)];
           const uint32_t hr = a.rev_hot.full2hot[sf];
-          er = sf == 0 ? 0u : (hr == 0xFFFFu ? 1u : hr);
-        }
-        have = true;
-      }
-      if (!__any_sync(0xffffffffu, have)) break;
-      if (!have) continue;
-      bool fin = false;
-      if (start == 0 || er < live) {
-        fin = true;
-      } else if (at == 0) {  // beginning of the record: the end-of-text step of the reverse scan
-        if (a.rev_hot.eof[er] >= a.rev.match_lo) start = 0;
-        fin = true;
-      } else {
-        const uint8_t* wp = p + at - 16;  // window = bytes [at-16, at); only the last min(16, at) belong to the record
-        const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
-        const uint32_t nb = at >= 16 ? 16u : (uint32_t)at;
-        if (al >= a.text && al + 24 <= buf_hi) {
-          uint32_t v[4];
-          window16(wp, v);
-          uint32_t lj = ~0u;
+          if (sf == 0) {
+            start = kNone;
+          } else if (hr == 0xFFFFu) {
+            rcold = true;
+          } else {
+            uint32_t er = hr;
+            uint64_t at = me;
+            bool rdone = false;
+            while (at > 0 && !rdone) {
+              const uint8_t* wp = p + at - 16;  // window = bytes [at-16, at); only the last min(16, at) belong to the record
+              const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)7);
+              const uint32_t nb = at >= 16 ? 16u : (uint32_t)at;
+              if (al >= a.text && al + 24 <= buf_hi) {
+                uint32_t v[4];
+                window16(wp, v);
+                uint32_t lj = ~0u;
 #pragma unroll
-          for (int i = 15; i >= 0; i--) {
-            if ((uint32_t)(15 - i) < nb && er >= live) {
-              er = hot_next_b(rbase, window_byte(v, i), er);
-              if (er >= rthr) lj = i;
+                for (int i = 15; i >= 0; i--) {
+                  if ((uint32_t)(15 - i) < nb && !rdone) {
+                    er = hot_next_b(rbase, window_byte(v, i), er);
+                    if (er >= rthr) lj = i;
+                    if (er < rlive) rdone = true;
+                  }
+                }
+                if (lj != ~0u) start = at - 16 + lj + 1;
+                at -= nb;
+              } else {
+                for (uint32_t i = 0; i < nb && !rdone; i++) {
+                  at--;
+                  er = hot_next_b(rbase, p[at], er);
+                  if (er >= rthr) start = at + 1;
+                  if (er < rlive) rdone = true;
+                }
+              }
             }
-          }
-          if (lj != ~0u) start = at - 16 + lj + 1;
-          at -= nb;
-        } else {
-          for (uint32_t i = 0; i < nb && er >= live; i++) {
-            at--;
-            er = hot_next_b(rbase, p[at], er);
-            if (er >= rthr) start = at + 1;
+            if (er == 1u) rcold = true;
+            else if (!rdone && a.rev_hot.eof[er] >= a.rev.match_lo) start = 0;
           }
         }
-        if (er < live) fin = true;
+        if (rcold) {
+          hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+        } else if (start != kNone) {
+          hit = true;
+          ms = start;
+        }
       }
-      if (!fin) continue;
-      if (er == 1u && start != 0) {  // trap row (or a start state outside the hot set): the full tables decide
-        uint64_t ms = 0, me = 0;
-        const bool hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+      if (MODE == 1) {
         a.out_spans[2 * r] = hit ? ms : 0;
         a.out_spans[2 * r + 1] = hit ? me : 0;
-        if (hit) set_bit(r);
-      } else if (start != kNone) {
-        a.out_spans[2 * r] = start;
-        set_bit(r);
-      } else {
-        a.out_spans[2 * r] = 0;
-        a.out_spans[2 * r + 1] = 0;
       }
-      have = false;
-      r += stride;
     }
+    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) a.out_bits[r >> 5] = bits;
   }
 }
 template __global__ void batch_fast<0>(BatchArgs);

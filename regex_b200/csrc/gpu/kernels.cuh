@@ -30,7 +30,13 @@ constexpr uint64_t kTooLong = ~0ull - 2; // an anchored run of a speculative chu
 // chunk that holds a `foo` would otherwise run its automaton to the last `bar` of the haystack,
 // only to learn from the stitch that the one real match covers it.  The chunk is DEFERRED instead:
 // the stitch walks it again with its exact entry state (no cap) unless it is covered.
-constexpr uint64_t kSpecRunCap = 1ull << 18;
+constexpr uint64_t kSpecRunCap = 1ull << 16;
+// A chunk walked from its exact entry state hands a match longer than this to the host, which
+// measures it with a parallel forward scan (engine.cu resolve_long_run) instead of one thread.
+constexpr uint64_t kExactRunCap = 1ull << 18;
+// Deferred chunks are walked again only within this many chunks of the leftmost deferred one: the
+// chunks behind a long match are usually covered by it, and each walk costs up to a whole cap.
+constexpr uint32_t kDeferredWindow = 1024;
 
 struct DfaView {
   const uint16_t* trans;    // [n_states][stride], class-indexed; column stride-1 is EOF

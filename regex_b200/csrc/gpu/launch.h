@@ -66,6 +66,10 @@ struct WalkArgs {
   uint32_t* dirty_list;     // chunks to walk again (nullable: all chunks)
   const uint32_t* n_dirty;
   uint64_t seq_from;        // walk_sequential: first chunk of the sequential pass
+  uint64_t exact_cap;       // longest anchored run a chunk walked from its exact entry does itself (kNone = any)
+  const uint64_t* long_tab; // n_long (start, end) pairs of long matches measured by the host-driven parallel scan
+  uint32_t n_long;
+  unsigned long long* long_req;  // smallest start whose run exceeded exact_cap (kNone = none): the host resolves it next
   HotView fwd_hot;              // fast runner: byte-indexed forward anchored table (hot states)
   uint64_t fixed_len;           // fixed-length runner: every match has this many bytes
   uint64_t* out;  // spans: start, end pairs
@@ -177,6 +181,8 @@ __global__ void compose_fill(const uint16_t* maps, const uint16_t* kidx, uint32_
                              const uint16_t* block_entry, uint16_t* exact);
 // neighbour[t -/+ 1] := exact[t] so that verify_segments + one redo round finish the job
 __global__ void publish_exact(const uint16_t* exact, uint64_t n_seg, int reverse, uint16_t* fin);
+// last position at which the anchored automaton, entered in exact[t], is in a match state inside segment t (+1; 0 = none)
+__global__ void scan_last_match(ScanArgs a, const uint16_t* exact, unsigned long long* best, uint32_t* alive_at_end);
 __global__ void reduce_segments(const uint64_t* seg_first, const uint64_t* seg_mask, uint64_t n_seg, uint32_t mw,
                                 unsigned long long* result);
 template <int FAST>
@@ -195,7 +201,7 @@ constexpr uint32_t kMetaPatched = 0x20000000u;  // the first staged span's start
 struct ChainKey { uint64_t key, lm; };
 // counters: [0] dirty chunks, [1] changed decisions, [2] need the general loop, [3] smallest dirty chunk index
 __global__ void stitch_fast(WalkArgs a, uint32_t* counters);
-__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot);
+__global__ void entries_local(WalkArgs a, ChainKey* excl, ChainKey* block_tot, uint32_t* first_deferred);
 __global__ void entries_blocks(ChainKey* block_tot, uint64_t n_blocks, ChainKey* grand);
 __global__ void stitch_resolve(WalkArgs a, const ChainKey* excl, const ChainKey* block_tot, uint32_t* counters);
 __global__ void scan_counts_local(const uint64_t* in, uint64_t* out, uint64_t* block_sums, uint64_t n);

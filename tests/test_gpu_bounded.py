@@ -26,11 +26,11 @@ def _device_repeat(base, reps):
 
 def test_sticky_automaton_is_solved_by_state_map_composition():
     """`(?s)foo.*bar` over 256 MiB: the reverse scan's state is "a bar lies somewhere to the right" for
-    the whole haystack, which no warm-up can guess; the single match covers ~65 000 chunks (the
-    anchored run that measures it is one thread's work: DESIGN.md, known limits)."""
+    the whole haystack, which no warm-up can guess; the single match covers ~260 000 chunks and is
+    measured by the parallel long-run pass (state maps of the anchored automaton from `foo` on)."""
     import torch
     base = tiled_corpus(16 << 20)
-    reps = 16
+    reps = 64
     d = _device_repeat(base, reps)
     n = d.numel()
     first_foo = base.find(b"foo")
@@ -42,7 +42,8 @@ def test_sticky_automaton_is_solved_by_state_map_composition():
     st = r.last_stats()
     assert total == 1 and _spans(out[:1].cpu().numpy()) == [(first_foo, last_bar + 3)]
     assert st["map_passes"] > 0 and st["scan_redo_rounds"] <= 6, st
-    assert st["stitch_rounds"] <= 4 and st["sequential_passes"] == 0, st
+    assert st["stitch_rounds"] <= 4 and st["sequential_passes"] == 0 and st["long_runs"] == 1, st
+    assert st["total_ms"] < 2000, st
     # forward searches: the same stickiness left to right, plus the early exit
     assert r.shortest_match_device(d) == base.find(b"bar", first_foo + 3) + 3
     assert r.last_stats()["waves"] == 1
@@ -52,6 +53,26 @@ def test_sticky_automaton_is_solved_by_state_map_composition():
     r2.set_tuning(seg=64, chunk=256)
     assert _spans(r2.find_all(small)) == O.OracleRegex(r"(?s)foo.*bar").find_iter(small)
     assert r2.last_stats()["map_passes"] > 0
+
+
+def test_matches_longer_than_the_run_cap_against_python_re():
+    """Several multi-MiB matches next to short ones: each long one is one parallel long-run pass."""
+    filler = tiled_corpus(5 << 20).replace(b"<<", b"< ").replace(b">>", b"> ")
+    parts = []
+    for i in range(3):
+        parts += [b"x <<", filler[: (2 + i) << 20], b">> y <<short>> "]
+    text = b"".join(parts) + filler[:70000]
+    for pat in (r"(?s)<<.*?>>", r"(?s)<<(?:[^>]|>[^>])*>>", r"(?s)<<.*?>>|short"):
+        exp = [m.span() for m in pyre.finditer(pat.encode(), text)]
+        assert len(exp) >= 6
+        r = R.BytesRegex(pat)
+        assert _spans(r.find_all(text)) == exp, pat
+        st = r.last_stats()
+        assert st["long_runs"] == 3 and st["sequential_passes"] == 0, (pat, st)
+    # an automaton too large for the long-run pass keeps the one-thread run (and stays exact)
+    pat = r"(?s)<<.*?>>|" + "|".join("q%dz{3}w" % i for i in range(60))
+    r = R.BytesRegex(pat)
+    assert _spans(r.find_all(text[: 3 << 20])) == [m.span() for m in pyre.finditer(pat.encode(), text[: 3 << 20])]
 
 
 def test_lazy_dotall_comments_spanning_many_chunks():
