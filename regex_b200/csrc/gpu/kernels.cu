@@ -2,6 +2,7 @@
 #include <cuda.h>
 
 #include "kernels.cuh"
+#include <type_traits>
 #include "launch.h"
 
 namespace rbgpu {
@@ -637,7 +638,9 @@ __device__ __forceinline__ uint64_t run_end(const WalkArgs& a, const Runner& T, 
 
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
-                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz);
+                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz, uint32_t lanes);
+__device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const FastRunner& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                                    uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz, uint32_t lanes);
 
 // The chain over one chunk (bits [cb, ce) <-> positions [cb+1, ce], plus position 0
 // for the chunk that starts the haystack).  One flat loop -- find the next candidate,
@@ -646,11 +649,20 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
 // Spans are written to dst[w_at + i] while w_at + i < limit.  Returns the match count.
 // nz: bit j set iff bitmap word j of the chunk may be non-zero (all ones when unknown);
 // lets the fused scan kernel skip the words it already knows to be empty.
+// lanes: the lanes of the warp that call this together (0 = unknown): the simple walk then votes
+// once per trip, which keeps them converged -- left to itself the compiler lets lanes drift apart
+// after the divergent exits of a run and the trip loop executes twice per match.
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
-                                               uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz = ~0ull) {
-  if (!a.emulate_slice && !a.can_match_empty && a.chunk <= 4096)
-    return chunk_walk_simple(a, T, k, c, first_cand, dst, w_at, limit, nz);
+                                               uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz = ~0ull, uint32_t lanes = 0) {
+  if (!a.emulate_slice && !a.can_match_empty && a.chunk <= 4096) {
+    if constexpr (std::is_same<Runner, FastRunner>::value) {
+      bool aligned = (((uintptr_t)a.text | (uintptr_t)dst) & 31) == 0 && !(w_at & 1);
+      if (lanes) aligned = __all_sync(lanes, aligned);  // the lanes that vote together take the same version
+      if (aligned) return chunk_walk_lean(a, T, k, c, first_cand, dst, w_at, limit, nz, lanes);
+    }
+    return chunk_walk_simple(a, T, k, c, first_cand, dst, w_at, limit, nz, lanes);
+  }
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
   const uint64_t ce = min(cb + a.chunk, a.limit);
   uint64_t total = 0;
@@ -728,7 +740,7 @@ __device__ __forceinline__ uint64_t chunk_walk(const WalkArgs& a, const Runner& 
 // roughly halves the instructions per match.  Requires chunks of at most 64 words.
 template <typename Runner>
 __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const Runner& T, uint64_t k, Chain& c, uint64_t* first_cand,
-                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz) {
+                                                      uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz, uint32_t lanes) {
   const uint64_t cb = a.base + k * (uint64_t)a.chunk;
   const uint64_t ce = min(cb + a.chunk, a.limit);
   const uint32_t nbits = (uint32_t)(ce - cb);
@@ -761,12 +773,13 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
     if (pair_stores && (total & 1u) && total - 1 < room)
       *reinterpret_cast<ulonglong2*>(o + 2 * (uint64_t)(total - 1)) = make_ulonglong2(held_s, held_e);
   };
-  if (c.p == kNone) { *first_cand = fc; return 0; }
+  bool too_long = false;
+  if (c.p == kNone) { *first_cand = fc; return 0; }  // (never among `lanes`)
   if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
     fc = 0;
     const uint64_t e = run_end(a, T, 0, exact);
-    if (e == kTooLong) { *first_cand = kTooLong; return 0; }
-    if (e == kNone) { c.p = 1; c.chain = false; }
+    if (e == kTooLong) too_long = true;
+    else if (e == kNone) { c.p = 1; c.chain = false; }
     else { emit(0, e); c.p = c.lm = e; c.chain = true; }
   }
   // bit r of the chunk <-> position cb + r + 1
@@ -775,31 +788,31 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   uint64_t rem = r < nbits ? nz & (~0ull << (r >> 6)) : 0;  // words still to visit
   uint32_t cw = 0;
   uint64_t cur = 0;
-  for (;;) {
+  auto trip = [&]() -> bool {  // one candidate; false when the chunk is through
     if (cur == 0) {
-      if (rem == 0) break;
+      if (rem == 0) return false;
       cw = (uint32_t)__ffsll((long long)rem) - 1;
       rem &= rem - 1;
       cur = bm[cw];
       if (cw == (r >> 6)) cur &= ~0ull << (r & 63);
-      if (cur == 0) continue;  // rare; otherwise fall through: one trip per match keeps the lanes of a warp in phase
+      if (cur == 0) return true;  // rare; otherwise fall through: one trip per match keeps the lanes of a warp in phase
     }
     const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
     const uint64_t s = cb + sr + 1;
     if (fc == kNone) fc = s;
     const uint64_t e = run_end(a, T, s, exact);
-    if (e == kTooLong) { *first_cand = kTooLong; return 0; }
+    if (e == kTooLong) { too_long = true; return false; }
     if (e == kNone) {  // unreachable for consistent tables
       cur &= cur - 1;
       c.p = s + 1;
       c.chain = false;
-      continue;
+      return true;
     }
     emit(s, e);
     c.p = c.lm = e;
     c.chain = true;
     const uint64_t er = e - 1 - cb;  // next candidate bit >= er
-    if (er >= nbits) break;
+    if (er >= nbits) return false;
     r = (uint32_t)er;
     const uint32_t ew = r >> 6;
     if (ew == cw) {
@@ -808,9 +821,135 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
       cur = 0;
       rem &= ~0ull << ew;
     }
+    return true;
+  };
+  if (lanes) {
+    bool active = !too_long;
+    while (__any_sync(lanes, active))
+      if (active) active = trip();
+  } else if (!too_long) {
+    while (trip()) {}
   }
+  if (too_long) { *first_cand = kTooLong; return 0; }
   flush();
   *first_cand = fc;
+  return total;
+}
+
+// chunk_walk_simple once more for the fast table runner, the walk the headline kernel spends a third
+// of its time in: positions relative to the chunk in 32 bits, the first 16 bytes of every anchored
+// run without a branch (rows 0 -- dead -- and 1 -- trap -- are absorbing, so running past the end of
+// a match is harmless), everything unusual (a run still alive after 16 bytes, the trap row, the
+// last bytes of the haystack, long-run caps) handed to run_end.  About half the instructions per
+// match of the general version; same contract, dst must be the 32-byte aligned staging area.
+__device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const FastRunner& T, uint64_t k, Chain& c, uint64_t* first_cand,
+                                                    uint64_t* dst, uint64_t w_at, uint64_t limit, uint64_t nz, uint32_t lanes) {
+  const uint64_t cb = a.base + k * (uint64_t)a.chunk;
+  const uint64_t ce = min(cb + a.chunk, a.limit);
+  const uint32_t nbits = (uint32_t)(ce - cb);
+  const uint64_t* bm = a.bitmap + (cb >> 6);
+  const uint8_t* tb8 = a.text + cb;  // cb is a multiple of 64 and the haystack is 16-byte aligned
+  // a 24-byte window read at relative offset x (multiple of 8) is inside the haystack iff x < safe
+  const uint64_t left = a.n - cb;
+  const uint32_t safe = left >= 24 ? (uint32_t)min(left - 23, (uint64_t)0x7FFFFFFFu) : 0u;
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(dst) + w_at;
+  const uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
+  const bool exact = c.chain;
+  uint32_t total = 0, fc_rel = ~0u;
+  uint64_t held_s = 0, held_e = 0, last_e = kNone;
+  bool too_long = false, lost = false;
+  auto emit = [&](uint64_t ms, uint64_t e) {  // spans leave two at a time as whole 32-byte sectors
+    if (!(total & 1u)) { held_s = ms; held_e = e; }
+    else if (total < room) st_sector(reinterpret_cast<uint64_t*>(o + (total - 1)), held_s, held_e, ms, e);
+    else if (total - 1 < room) o[total - 1] = make_ulonglong2(held_s, held_e);
+    total++;
+  };
+  uint64_t fc0 = kNone;
+  if (c.p == 0 && cb == 0 && *a.flag0) {  // position 0 has no bitmap bit
+    fc0 = 0;
+    const uint64_t e = run_end(a, T, 0, exact);
+    if (e == kTooLong) too_long = true;
+    else if (e == kNone) { c.p = 1; c.chain = false; }
+    else { emit(0, e); c.p = last_e = e; c.chain = true; }
+  }
+  uint32_t r = c.p > cb + 1 ? (uint32_t)min(c.p - cb - 1, (uint64_t)nbits) : 0u;
+  if (nbits < 64 * 64) nz &= (1ull << ((nbits + 63) >> 6)) - 1;
+  uint64_t rem = r < nbits ? nz & (~0ull << (r >> 6)) : 0;
+  uint32_t cw = 0;
+  uint64_t cur = 0;
+  const uint32_t tb = T.tb, thr = T.thr, start_e = T.start_e;
+  auto trip = [&]() -> bool {
+    if (cur == 0) {
+      if (rem == 0) return false;
+      cw = (uint32_t)__ffsll((long long)rem) - 1;
+      rem &= rem - 1;
+      cur = bm[cw];
+      if (cw == (r >> 6)) cur &= ~0ull << (r & 63);
+      if (cur == 0) return true;
+    }
+    const uint32_t s_rel = cw * 64 + (uint32_t)__ffsll((long long)cur);  // bit index + 1
+    if (fc_rel == ~0u) fc_rel = s_rel;
+    const uint32_t al = s_rel & ~7u;
+    uint64_t e_abs;
+    bool fast_done = false;
+    if (al < safe) {
+      const uint64_t* wp = reinterpret_cast<const uint64_t*>(tb8 + al);
+      const uint64_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+      const uint32_t sh = (s_rel & 7u) * 8u;
+      const uint32_t x0 = __funnelshift_r((uint32_t)w0, (uint32_t)(w0 >> 32), sh);
+      const uint32_t x1 = __funnelshift_r((uint32_t)(w0 >> 32), (uint32_t)w1, sh);
+      const uint32_t x2 = __funnelshift_r((uint32_t)w1, (uint32_t)(w1 >> 32), sh);
+      const uint32_t x3 = __funnelshift_r((uint32_t)(w1 >> 32), (uint32_t)w2, sh);
+      const uint32_t x4 = __funnelshift_r((uint32_t)w2, (uint32_t)(w2 >> 32), sh);
+      const bool up = sh >= 32;
+      const uint32_t v0 = up ? x1 : x0, v1 = up ? x2 : x1, v2 = up ? x3 : x2, v3 = up ? x4 : x3;
+      uint32_t e = start_e, lj = ~0u;
+#define RB_LEAN_WORD(V, J0)                                         \
+      e = hot_next<0>(tb, V, e); if (e >= thr) lj = J0 + 0;         \
+      e = hot_next<1>(tb, V, e); if (e >= thr) lj = J0 + 1;         \
+      e = hot_next<2>(tb, V, e); if (e >= thr) lj = J0 + 2;         \
+      e = hot_next<3>(tb, V, e); if (e >= thr) lj = J0 + 3;
+      RB_LEAN_WORD(v0, 0) RB_LEAN_WORD(v1, 4) RB_LEAN_WORD(v2, 8) RB_LEAN_WORD(v3, 12)
+#undef RB_LEAN_WORD
+      if (e == 0 && lj != ~0u) { e_abs = cb + s_rel + lj; fast_done = true; }
+    }
+    if (!fast_done) {  // rare: longer than 16 bytes, left the hot set, near the end of the haystack
+      e_abs = run_end(a, T, cb + s_rel, exact);
+      if (e_abs == kTooLong) { too_long = true; return false; }
+      if (e_abs == kNone) {  // unreachable for consistent tables
+        cur &= cur - 1;
+        c.p = cb + s_rel + 1;
+        lost = true;
+        return true;
+      }
+    }
+    emit(cb + s_rel, e_abs);
+    last_e = e_abs;
+    lost = false;
+    const uint64_t er = e_abs - 1 - cb;  // next candidate bit >= er
+    if (er >= nbits) return false;
+    r = (uint32_t)er;
+    const uint32_t ew = r >> 6;
+    if (ew == cw) {
+      cur &= ~0ull << (r & 63);
+    } else {
+      cur = 0;
+      rem &= ~0ull << ew;
+    }
+    return true;
+  };
+  if (lanes) {
+    bool active = !too_long;
+    while (__any_sync(lanes, active))
+      if (active) active = trip();
+  } else if (!too_long) {
+    while (trip()) {}
+  }
+  if (too_long) { *first_cand = kTooLong; return 0; }
+  if ((total & 1u) && total - 1 < room) o[total - 1] = make_ulonglong2(held_s, held_e);
+  if (lost) c.chain = false;
+  else if (last_e != kNone) { c.p = c.lm = last_e; c.chain = true; }
+  *first_cand = fc0 != kNone ? fc0 : fc_rel != ~0u ? cb + fc_rel : kNone;
   return total;
 }
 
@@ -886,7 +1025,8 @@ __global__ void __launch_bounds__(256) walk_chunks(WalkArgs a) {
     const bool spec = !c.chain;
     if (spec) { c.p = a.base + k * (uint64_t)a.chunk + 1; c.lm = kNone; }
     uint64_t fc = kNone, total = 0;
-    if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap);
+    const uint32_t walkers = __ballot_sync(__activemask(), c.p != kNone);
+    if (c.p != kNone) total = chunk_walk(a, R, k, c, &fc, a.stage, k * (uint64_t)a.stage_cap, (k + 1) * (uint64_t)a.stage_cap, ~0ull, walkers);
     finish_chunk(a, k, c, total, fc, spec);
   }
 }
@@ -1508,8 +1648,9 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
         uint64_t fc = kNone, total = 0;
         // segments longer than 64 words, the ragged last segment and position 0 fall back to "unknown"
         const bool nz_ok = a.seg <= 4096 && !(hi & 63) && lo != 0;
+        const uint32_t walkers = __ballot_sync(__activemask(), c.p != kNone);
         if (c.p != kNone)
-          total = chunk_walk(wa, R, t, c, &fc, wa.stage, t * (uint64_t)wa.stage_cap, (t + 1) * (uint64_t)wa.stage_cap, nz_ok ? nz : ~0ull);
+          total = chunk_walk(wa, R, t, c, &fc, wa.stage, t * (uint64_t)wa.stage_cap, (t + 1) * (uint64_t)wa.stage_cap, nz_ok ? nz : ~0ull, walkers);
         finish_chunk(wa, t, c, total, fc, spec);
       }
     }
