@@ -849,9 +849,9 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
   const uint32_t nbits = (uint32_t)(ce - cb);
   const uint64_t* bm = a.bitmap + (cb >> 6);
   const uint8_t* tb8 = a.text + cb;  // cb is a multiple of 64 and the haystack is 16-byte aligned
-  // a 24-byte window read at relative offset x (multiple of 8) is inside the haystack iff x < safe
+  // a 32-byte window read at relative offset x (multiple of 16) is inside the haystack iff x < safe
   const uint64_t left = a.n - cb;
-  const uint32_t safe = left >= 24 ? (uint32_t)min(left - 23, (uint64_t)0x7FFFFFFFu) : 0u;
+  const uint32_t safe = left >= 32 ? (uint32_t)min(left - 31, (uint64_t)0x7FFFFFFFu) : 0u;
   ulonglong2* o = reinterpret_cast<ulonglong2*>(dst) + w_at;
   const uint32_t room = limit > w_at ? (uint32_t)min(limit - w_at, (uint64_t)0xFFFFFFFFu) : 0u;
   const bool exact = c.chain;
@@ -875,41 +875,59 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
   uint32_t r = c.p > cb + 1 ? (uint32_t)min(c.p - cb - 1, (uint64_t)nbits) : 0u;
   if (nbits < 64 * 64) nz &= (1ull << ((nbits + 63) >> 6)) - 1;
   uint64_t rem = r < nbits ? nz & (~0ull << (r >> 6)) : 0;
-  uint32_t cw = 0;
-  uint64_t cur = 0;
+  // Candidate words come one ahead: while the candidates of word cw are walked, the chunk's next
+  // non-zero word nw is already on its way (nxt), and the haystack line of the likely next
+  // candidate -- the first bit after the current run of ones -- is prefetched into L1.  Without
+  // this every trip paid two L2 round trips in a row (bitmap word, then haystack bytes).
+  uint32_t cw = 0, nw = 64;  // nw == 64: nothing preloaded; bit nw of rem is already taken
+  uint64_t cur = 0, nxt = 0;
+  auto preload = [&]() {
+    if (rem) { nw = (uint32_t)__ffsll((long long)rem) - 1; rem &= rem - 1; nxt = bm[nw]; }
+    else nw = 64;
+  };
   const uint32_t tb = T.tb, thr = T.thr, start_e = T.start_e;
   auto trip = [&]() -> bool {
     if (cur == 0) {
-      if (rem == 0) return false;
-      cw = (uint32_t)__ffsll((long long)rem) - 1;
-      rem &= rem - 1;
-      cur = bm[cw];
+      if (nw == 64) preload();
+      if (nw == 64) return false;
+      cw = nw;
+      cur = nxt;
+      preload();
       if (cw == (r >> 6)) cur &= ~0ull << (r & 63);
       if (cur == 0) return true;
     }
     const uint32_t s_rel = cw * 64 + (uint32_t)__ffsll((long long)cur);  // bit index + 1
     if (fc_rel == ~0u) fc_rel = s_rel;
-    const uint32_t al = s_rel & ~7u;
+    {
+      const uint64_t after_run = cur & (cur + (cur & (0 - cur)));  // the candidates of this word behind the current run of ones
+      const uint32_t g = after_run ? cw * 64 + (uint32_t)__ffsll((long long)after_run)
+                                   : (nw != 64 && nxt) ? nw * 64 + (uint32_t)__ffsll((long long)nxt) : 0u;
+      if (g != 0 && g < left) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb8 + g));
+    }
+    const uint32_t al = s_rel & ~15u;
     uint64_t e_abs;
     bool fast_done = false;
     if (al < safe) {
-      const uint64_t* wp = reinterpret_cast<const uint64_t*>(tb8 + al);
-      const uint64_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-      const uint32_t sh = (s_rel & 7u) * 8u;
-      const uint32_t x0 = __funnelshift_r((uint32_t)w0, (uint32_t)(w0 >> 32), sh);
-      const uint32_t x1 = __funnelshift_r((uint32_t)(w0 >> 32), (uint32_t)w1, sh);
-      const uint32_t x2 = __funnelshift_r((uint32_t)w1, (uint32_t)(w1 >> 32), sh);
-      const uint32_t x3 = __funnelshift_r((uint32_t)(w1 >> 32), (uint32_t)w2, sh);
-      const uint32_t x4 = __funnelshift_r((uint32_t)w2, (uint32_t)(w2 >> 32), sh);
-      const bool up = sh >= 32;
-      const uint32_t v0 = up ? x1 : x0, v1 = up ? x2 : x1, v2 = up ? x3 : x2, v3 = up ? x4 : x3;
+      // two aligned 16-byte loads (two L1 wavefronts per lane; three 8-byte loads were three), then the 16
+      // bytes from s on: word offset through two rounds of selects, byte offset through funnel shifts
+      const uint4 p0 = ldg128(tb8 + al), p1 = ldg128(tb8 + al + 16);
+      const bool by2 = (s_rel & 8u) != 0, by1 = (s_rel & 4u) != 0;
+      const uint32_t sh = (s_rel & 3u) * 8u;
+      const uint32_t a0 = by2 ? p0.z : p0.x, a1 = by2 ? p0.w : p0.y, a2 = by2 ? p1.x : p0.z, a3 = by2 ? p1.y : p0.w,
+                     a4 = by2 ? p1.z : p1.x, a5 = by2 ? p1.w : p1.y;
+      const uint32_t b0 = by1 ? a1 : a0, b1 = by1 ? a2 : a1, b2 = by1 ? a3 : a2, b3 = by1 ? a4 : a3, b4 = by1 ? a5 : a4;
+      const uint32_t v0 = __funnelshift_r(b0, b1, sh), v1 = __funnelshift_r(b1, b2, sh);
       uint32_t e = start_e, lj = ~0u;
 #define RB_LEAN_WORD(V, J0)                                         \
       e = hot_next<0>(tb, V, e); if (e >= thr) lj = J0 + 0;         \
       e = hot_next<1>(tb, V, e); if (e >= thr) lj = J0 + 1;         \
       e = hot_next<2>(tb, V, e); if (e >= thr) lj = J0 + 2;         \
       e = hot_next<3>(tb, V, e); if (e >= thr) lj = J0 + 3;
-      RB_LEAN_WORD(v0, 0) RB_LEAN_WORD(v1, 4) RB_LEAN_WORD(v2, 8) RB_LEAN_WORD(v3, 12)
+      RB_LEAN_WORD(v0, 0) RB_LEAN_WORD(v1, 4)
+      if (e >= 2) {  // still alive after 8 bytes: the second half of the window
+        const uint32_t v2 = __funnelshift_r(b2, b3, sh), v3 = __funnelshift_r(b3, b4, sh);
+        RB_LEAN_WORD(v2, 8) RB_LEAN_WORD(v3, 12)
+      }
 #undef RB_LEAN_WORD
       if (e == 0 && lj != ~0u) { e_abs = cb + s_rel + lj; fast_done = true; }
     }
@@ -935,6 +953,7 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
     } else {
       cur = 0;
       rem &= ~0ull << ew;
+      if (nw < ew) nw = 64;  // (64 is never below ew)
     }
     return true;
   };
@@ -1437,16 +1456,18 @@ __device__ __noinline__ uint32_t slow_group(const uint16_t* trans, const uint8_t
 
 template <int FUSED>
 __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap) {
-  // shared layout: [reverse hot table][forward hot table (FUSED == 1)], 256-byte aligned,
-  // then, 512-byte aligned, per warp 2 stages x 32 lanes x 64 B, then the mbarriers
+  // shared layout: 512-byte aligned, per warp 2 stages x 32 lanes x 64 B, then the mbarriers, then
+  // [reverse hot table][forward hot table (FUSED == 1)].  The rings come first so that their
+  // addresses depend on nothing but the warp index: behind the tables they were recomputed from
+  // the table sizes in every 64-byte group (the kernel has no registers to spare).
   // (the reverse table uses signed row ids: match rows below tbase, see hot_stage_signed)
-  const uint32_t tstart = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
-  const uint32_t tbase = tstart + hot_signed_below(a.hot);
-  const uint32_t fbase = tstart + hot_signed_bytes(a.hot);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t rings = (fbase + (FUSED == 1 ? hot_table_bytes(wa.fwd_hot.n) : 0u) + 511u) & ~511u;
+  const uint32_t rings = ((uint32_t)__cvta_generic_to_shared(g_smem) + 511u) & ~511u;
   const uint32_t ring = rings + wid * kRingWarpBytes;
   const uint32_t bar0 = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
+  const uint32_t tstart = rings + (blockDim.x >> 5) * (kRingWarpBytes + kRingBarBytes);  // a multiple of 256
+  const uint32_t tbase = tstart + hot_signed_below(a.hot);
+  const uint32_t fbase = tstart + hot_signed_bytes(a.hot);
   const uint32_t rml = a.hot.match_lo;
   {
     hot_stage_signed(a.hot, tbase);
@@ -1490,6 +1511,31 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       rev_block16_s(tbase, c0, e, blo);
       if (!rec) bhi = blo = 0;  // warm-up bytes: states only
       if (e == 1u) {
+        uint64_t bits;
+        const uint32_t s1 = slow_group(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo,
+                                       cold ? cold : a.hot.hot2full[hot_idx(e0, rml)], c0, c1, c2, c3, &bits);
+        bhi = rec ? (uint32_t)(bits >> 32) : 0u;
+        blo = rec ? (uint32_t)bits : 0u;
+        enter(s1);
+      }
+    };
+    // the same for a group that sits in a ring slot (swizzled, boxed mode): 16 bytes are fetched right
+    // before their turn, so that 8 registers hold haystack bytes instead of 16 (the kernel lives on 64
+    // registers and was recomputing its ring addresses in every group for lack of them); the rare
+    // trap-row exit reads the slot again
+    auto do_group_slot = [&](uint32_t b, uint32_t sw, bool rec, uint32_t& bhi, uint32_t& blo) {
+      const uint32_t e0 = e;
+      bhi = blo = 0;
+      uint4 x = lds128(b + (48u ^ sw)), y = lds128(b + (32u ^ sw));
+      rev_block16_s(tbase, x, e, bhi);
+      x = lds128(b + (16u ^ sw));
+      rev_block16_s(tbase, y, e, bhi);
+      y = lds128(b + (0u ^ sw));
+      rev_block16_s(tbase, x, e, blo);
+      rev_block16_s(tbase, y, e, blo);
+      if (!rec) bhi = blo = 0;
+      if (e == 1u) {
+        const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
         uint64_t bits;
         const uint32_t s1 = slow_group(a.dfa.trans, a.dfa.classes, a.dfa.stride, a.dfa.match_lo,
                                        cold ? cold : a.hot.hot2full[hot_idx(e0, rml)], c0, c1, c2, c3, &bits);
@@ -1569,11 +1615,10 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
       for (uint32_t k = 0; k < n_groups; k++) {
         mbar_wait(barb + slot_b * 8, par_b);
         const uint32_t b = my_b + slot_b * kRingStageBytes;
-        const uint4 c0 = lds128(b + (0u ^ sw)), c1 = lds128(b + (16u ^ sw)), c2 = lds128(b + (32u ^ sw)), c3 = lds128(b + (48u ^ sw));
         if (k == n_warm) a.guess[t] = (uint16_t)full_state();
         const bool rec = k >= n_warm;
         uint32_t bhi, blo;
-        do_group(c0, c1, c2, c3, rec, bhi, blo);
+        do_group_slot(b, sw, rec, bhi, blo);
         if (rec) {
           // Bitmap words leave as whole 32-byte sectors (four words, every fourth group):
           // an 8-byte store per group is a partial-sector write from each lane, and those
@@ -1711,11 +1756,11 @@ __device__ __noinline__ void slow_group_masks(const uint16_t* trans, const uint8
   }
 }
 __global__ void __launch_bounds__(1024, 1) scan_fwd_fast(ScanArgs a, const __grid_constant__ CUtensorMap tmap) {
-  const uint32_t tbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t rings = (tbase + hot_table_bytes(a.hot.n) + 511u) & ~511u;
+  const uint32_t rings = ((uint32_t)__cvta_generic_to_shared(g_smem) + 511u) & ~511u;  // as scan_rev_fast: rings, mbarriers, table
   const uint32_t ring = rings + wid * kRingWarpBytes;
   const uint32_t barb = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
+  const uint32_t tbase = rings + (blockDim.x >> 5) * (kRingWarpBytes + kRingBarBytes);
   hot_stage(a.hot, tbase);
   if (lane == 0) {
     for (uint32_t sidx = 0; sidx < kBoxStages; sidx++) mbar_init(barb + 8 * sidx, 1);

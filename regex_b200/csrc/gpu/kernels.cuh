@@ -55,7 +55,7 @@ struct DfaView {
 // transition left the hot set; absorbing), then non-match states, then match states.
 // A lane that lands in the trap row re-runs those bytes on the full class-indexed table.
 #ifndef RB_HOT_ROW
-#define RB_HOT_ROW 288  // bytes between hot-table rows in shared memory: 256 entries + 32 (rows start 8 banks apart)
+#define RB_HOT_ROW 280  // bytes between hot-table rows in shared memory: 256 entries + 24 (rows start 6 banks apart; tools/micro/bank_sim.py)
 #endif
 struct HotView {
   const uint16_t* next256;   // [n][256] successor hot ids
