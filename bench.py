@@ -46,7 +46,7 @@ SEED = C.SEED
 GIB = C.GIB
 sherlock_lines, host_corpus, device_corpus = C.sherlock_lines, C.host_corpus, C.device_corpus
 # ncu --set full, scan_rev_fast<1> on 1 GiB of this corpus (profiles/): dram bytes read + written per haystack byte
-TRAFFIC_PER_BYTE = (1.762146e9 + 0.22295552e9) / (1 << 30)
+TRAFFIC_PER_BYTE = (1.779481e9 + 0.225388e9) / (1 << 30)  # profiles/r02_ncu_summaries.md section 1b
 METRIC = "haystack GB/s scanned (find_iter, bit-exact spans)"
 
 
