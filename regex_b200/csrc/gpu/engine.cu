@@ -412,7 +412,7 @@ int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool 
   DeviceDfa* fwd;
   if (int rc = ensure(kFwdAnchoredLF, &fwd)) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
-  const uint32_t k = fwd->view.n_states;
+  const uint32_t k_max = fwd->view.n_states;
   const uint32_t seg = 4096;
   ScanArgs g{};
   g.dfa = fwd->view;
@@ -423,14 +423,9 @@ int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool 
   g.base = s;
   g.seg = seg;
   uint32_t* counters = (uint32_t*)counters_.ptr;
-  uint16_t* d_states = (uint16_t*)kstates_.ensure(k * 2);
+  uint16_t* d_states = (uint16_t*)kstates_.ensure(k_max * 2);
   uint16_t* d_kidx = (uint16_t*)kidx_.ensure(65536 * 2);
-  uint16_t* d_first = (uint16_t*)present_.ensure(65536);  // (two bytes of it: the entry state of the first segment)
-  if (!d_states || !d_kidx || !d_first) return fail("out of device memory (long run)");
-  std::vector<uint16_t> ident(k);
-  for (uint32_t i = 0; i < k; i++) ident[i] = (uint16_t)i;
-  RB_CUDA(cudaMemcpyAsync(d_states, ident.data(), k * 2, cudaMemcpyHostToDevice, st));
-  RB_CUDA(cudaMemcpyAsync(d_kidx, ident.data(), k * 2, cudaMemcpyHostToDevice, st));
+  if (!d_states || !d_kidx) return fail("out of device memory (long run)");
   // the start state at s: the look-behind flags come from the bytes next to s (pick_start_fwd)
   uint16_t start_state = fwd->view.start[32];
   if (!fwd->view.uniform_start) {
@@ -449,8 +444,21 @@ int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool 
     if (last) f |= 64;
     start_state = fwd->view.start[f];
   }
-  RB_CUDA(cudaMemcpyAsync(d_first, &start_state, 2, cudaMemcpyHostToDevice, st));
-  RB_CUDA(cudaStreamSynchronize(st));  // `ident` and `start_state` leave scope below
+  // K: the states the run is in at segment boundaries, closed under the per-segment maps, found as in
+  // solve_entries: start from the run's start state, run the segments from the states known so far, add
+  // the states their maps lead to, repeat (`(?s)foo.*bar`: 6 of 25 states)
+  uint8_t* present = (uint8_t*)present_.ensure(65536);
+  uint16_t* d_first = (uint16_t*)(counters + 11);
+  if (!present) return fail("out of device memory (long run)");
+  RB_CUDA(cudaMemsetAsync(present, 0, 65536, st));
+  {
+    const uint8_t one = 1;
+    RB_CUDA(cudaMemcpyAsync(present + start_state, &one, 1, cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(d_first, &start_state, 2, cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+  }
+  std::vector<uint8_t> h_present(65536);
+  std::vector<uint16_t> K, kidx;
   RB_CUDA(allow_smem(scan_map, smem));
   RB_CUDA(allow_smem(scan_last_match, smem));
   // growing windows from s: a long match is rarely the whole rest of the haystack
@@ -460,13 +468,33 @@ int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool 
     const uint64_t n_blocks = (n_seg + kMapBlock - 1) / kMapBlock;
     g.limit = end;
     g.n_seg = n_seg;
-    uint16_t* maps = (uint16_t*)maps_.ensure(n_seg * k * 2);
+    uint32_t k = 0;
+    uint16_t* maps = nullptr;
+    for (;;) {
+      RB_CUDA(d2h(h_present.data(), present, 65536));
+      K.clear();
+      kidx.assign(65536, 0xFFFF);
+      for (uint32_t v = 0; v < k_max; v++)
+        if (h_present[v]) { kidx[v] = (uint16_t)K.size(); K.push_back((uint16_t)v); }
+      k = (uint32_t)K.size();
+      maps = (uint16_t*)maps_.ensure(n_seg * k * 2);
+      if (!maps) return fail("out of device memory (long run)");
+      RB_CUDA(cudaMemcpyAsync(d_states, K.data(), k * 2, cudaMemcpyHostToDevice, st));
+      RB_CUDA(cudaMemcpyAsync(d_kidx, kidx.data(), 65536 * 2, cudaMemcpyHostToDevice, st));
+      scan_map<<<grid_for(n_seg * k, 256, tuning.blocks_per_sm), 256, smem, st>>>(g, 0, d_states, k, maps);
+      RB_LAUNCH_CHECK("scan_map");
+      stats.map_passes += k;
+      RB_CUDA(cudaMemsetAsync(counters + 8, 0, 4, st));
+      closure_check<<<grid_for(n_seg * k, 256, 8), 256, 0, st>>>(maps, n_seg * k, d_kidx, present, counters + 8);
+      RB_LAUNCH_CHECK("closure_check");
+      uint32_t n_new = 0;
+      RB_CUDA(d2h(&n_new, counters + 8, 4));
+      if (n_new == 0) break;
+    }
     uint16_t* comp = (uint16_t*)comp_.ensure(n_blocks * k * 2);
     uint16_t* bentry = (uint16_t*)bentry_.ensure(n_blocks * 2);
     uint16_t* exact = (uint16_t*)exact_.ensure(n_seg * 2);
-    if (!maps || !comp || !bentry || !exact) return fail("out of device memory (long run)");
-    scan_map<<<grid_for(n_seg * k, 256, tuning.blocks_per_sm), 256, smem, st>>>(g, 0, d_states, k, maps);
-    RB_LAUNCH_CHECK("scan_map");
+    if (!comp || !bentry || !exact) return fail("out of device memory (long run)");
     compose_blocks<<<(uint32_t)((n_blocks * k + 255) / 256), 256, 0, st>>>(maps, d_kidx, d_states, k, n_seg, 0, comp);
     RB_LAUNCH_CHECK("compose_blocks");
     compose_top<<<1, 32, 0, st>>>(comp, d_kidx, k, n_blocks, 0, d_first, bentry);
@@ -479,7 +507,6 @@ int Regex::resolve_long_run(const uint8_t* d_text, uint64_t n, uint64_t s, bool 
     RB_LAUNCH_CHECK("scan_last_match");
     uint32_t h[4] = {0, 0, 0, 0};
     RB_CUDA(d2h(h, best, 12));
-    stats.map_passes += k;
     const bool alive = h[2] != 0;
     if (alive && end < n) continue;
     const uint64_t found = (uint64_t)h[0] | ((uint64_t)h[1] << 32);

@@ -626,12 +626,15 @@ struct Chain {
 // walks from an exact entry state take matches of up to exact_cap bytes themselves, look longer
 // ones up in the table of runs the host has measured with a parallel scan, and otherwise ask for
 // that (long_req) -- in both cases kTooLong defers the chunk.
+// trip_cap: inside a voting trip loop (see kTripRunCap); kPending then means "longer than that, ask again".
 template <typename Runner>
-__device__ __forceinline__ uint64_t run_end(const WalkArgs& a, const Runner& T, uint64_t s, bool exact) {
+__device__ __forceinline__ uint64_t run_end(const WalkArgs& a, const Runner& T, uint64_t s, bool exact, uint64_t trip_cap = kNone) {
   if (exact)
     for (uint32_t i = 0; i < a.n_long; i++)
       if (a.long_tab[2 * i] == s) return a.long_tab[2 * i + 1];
-  const uint64_t e = T.end_from(a, s, exact ? a.exact_cap : kSpecRunCap);
+  const uint64_t cap = exact ? a.exact_cap : kSpecRunCap;
+  const uint64_t e = T.end_from(a, s, min(cap, trip_cap));
+  if (e == kTooLong && trip_cap < cap) return kPending;
   if (e == kTooLong && exact) atomicMin(a.long_req, (unsigned long long)s);
   return e;
 }
@@ -788,6 +791,7 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   uint64_t rem = r < nbits ? nz & (~0ull << (r >> 6)) : 0;  // words still to visit
   uint32_t cw = 0;
   uint64_t cur = 0;
+  bool pending = false;
   auto trip = [&]() -> bool {  // one candidate; false when the chunk is through
     if (cur == 0) {
       if (rem == 0) return false;
@@ -800,7 +804,9 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
     const uint32_t sr = cw * 64 + (uint32_t)__ffsll((long long)cur) - 1;
     const uint64_t s = cb + sr + 1;
     if (fc == kNone) fc = s;
-    const uint64_t e = run_end(a, T, s, exact);
+    const uint64_t e = pending ? run_end(a, T, s, exact) : run_end(a, T, s, exact, lanes ? kTripRunCap : kNone);
+    pending = e == kPending;
+    if (pending) return false;  // the same candidate again, without the trip cap, once the warp is through its short runs
     if (e == kTooLong) { too_long = true; return false; }
     if (e == kNone) {  // unreachable for consistent tables
       cur &= cur - 1;
@@ -825,8 +831,12 @@ __device__ __forceinline__ uint64_t chunk_walk_simple(const WalkArgs& a, const R
   };
   if (lanes) {
     bool active = !too_long;
-    while (__any_sync(lanes, active))
-      if (active) active = trip();
+    for (;;) {
+      while (__any_sync(lanes, active))
+        if (active) active = trip();
+      if (!__any_sync(lanes, pending)) break;
+      if (pending) active = trip();  // the long runs of the warp, side by side
+    }
   } else if (!too_long) {
     while (trip()) {}
   }
@@ -886,6 +896,7 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
     else nw = 64;
   };
   const uint32_t tb = T.tb, thr = T.thr, start_e = T.start_e;
+  bool pending = false;
   auto trip = [&]() -> bool {
     if (cur == 0) {
       if (nw == 64) preload();
@@ -932,7 +943,9 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
       if (e == 0 && lj != ~0u) { e_abs = cb + s_rel + lj; fast_done = true; }
     }
     if (!fast_done) {  // rare: longer than 16 bytes, left the hot set, near the end of the haystack
-      e_abs = run_end(a, T, cb + s_rel, exact);
+      e_abs = pending ? run_end(a, T, cb + s_rel, exact) : run_end(a, T, cb + s_rel, exact, lanes ? kTripRunCap : kNone);
+      pending = e_abs == kPending;
+      if (pending) return false;  // the same candidate again, without the trip cap, once the warp is through its short runs
       if (e_abs == kTooLong) { too_long = true; return false; }
       if (e_abs == kNone) {  // unreachable for consistent tables
         cur &= cur - 1;
@@ -959,8 +972,12 @@ __device__ __forceinline__ uint64_t chunk_walk_lean(const WalkArgs& a, const Fas
   };
   if (lanes) {
     bool active = !too_long;
-    while (__any_sync(lanes, active))
-      if (active) active = trip();
+    for (;;) {
+      while (__any_sync(lanes, active))
+        if (active) active = trip();
+      if (!__any_sync(lanes, pending)) break;
+      if (pending) active = trip();  // the long runs of the warp, side by side
+    }
   } else if (!too_long) {
     while (trip()) {}
   }

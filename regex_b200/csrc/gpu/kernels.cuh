@@ -26,6 +26,12 @@ namespace rbgpu {
 constexpr uint64_t kNone = ~0ull;        // "no position"
 constexpr uint64_t kSpec = ~0ull - 1;    // chunk entry state is speculative
 constexpr uint64_t kTooLong = ~0ull - 2; // an anchored run of a speculative chunk walk was cut off (see kSpecRunCap)
+constexpr uint64_t kPending = ~0ull - 3; // a run longer than kTripRunCap inside a voting walk: taken up again after the trip loop
+// Walks whose lanes vote once per trip (chunk_walk_simple / _lean) must not run a long match inside a
+// trip: the vote is a barrier, so the other lanes would wait, and long runs that come up in different
+// trips would execute one after the other (ncu: one thread per instruction, 0.2 s for 200 chunks).
+// A run that passes this many bytes is left pending; all pending runs of a warp then go together.
+constexpr uint64_t kTripRunCap = 2048;
 // A speculatively entered chunk gives up on a match longer than this: with `(?s)foo.*bar` every
 // chunk that holds a `foo` would otherwise run its automaton to the last `bar` of the haystack,
 // only to learn from the stitch that the one real match covers it.  The chunk is DEFERRED instead:
