@@ -91,12 +91,33 @@ class TorchDistComm:
         self.world = dist.get_world_size(group)
 
     def all_gather(self, values):
+        """One collective, one upload and one download per call: the vector goes out from a pinned host
+        buffer, `all_gather_into_tensor` fills one device tensor for all ranks, and one copy brings it
+        back (per-rank output tensors cost a device-to-host copy and a sync per rank)."""
         import torch
+        n = len(values)
+        bufs = self._bufs.get(n) if hasattr(self, "_bufs") else None
+        if bufs is None:
+            if not hasattr(self, "_bufs"):
+                self._bufs = {}
+            on_gpu = torch.device(self.device).type == "cuda"
+            h_in = torch.empty(n, dtype=torch.int64, pin_memory=on_gpu)
+            h_out = torch.empty(self.world * n, dtype=torch.int64, pin_memory=on_gpu)
+            d_in = torch.empty(n, dtype=torch.int64, device=self.device)
+            d_out = torch.empty(self.world * n, dtype=torch.int64, device=self.device)
+            bufs = self._bufs[n] = (h_in, h_out, d_in, d_out, on_gpu)
+        h_in, h_out, d_in, d_out, on_gpu = bufs
         # 64-bit patterns travel as int64 (two's complement keeps NONE / SPEC intact)
-        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in values], dtype=torch.int64, device=self.device)
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t, group=self.group)
-        return [[int(x) & ((1 << 64) - 1) for x in o.tolist()] for o in out]
+        a = h_in.numpy()
+        for i, v in enumerate(values):
+            a[i] = v - (1 << 64) if v >= (1 << 63) else v
+        d_in.copy_(h_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(d_out, d_in, group=self.group)
+        h_out.copy_(d_out, non_blocking=True)
+        if on_gpu:
+            torch.cuda.current_stream(d_out.device).synchronize()
+        flat = h_out.numpy()
+        return [[int(x) & ((1 << 64) - 1) for x in flat[g * n:(g + 1) * n]] for g in range(self.world)]
 
 
 class ThreadComm:
