@@ -379,37 +379,57 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     host = None
+    host_full = None
     if not args.no_e2e or (rank == 0 and not args.no_cpu):
-        host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        host.copy_(text[geom.own_lo:geom.own_lo + n])
+        if world > 1:  # the whole shard buffer [left context | own bytes | halo], as the sharded search wants it
+            host_full = torch.empty(text.numel(), dtype=torch.uint8, pin_memory=True)
+            host_full.copy_(text)
+            host = host_full[geom.own_lo:geom.own_lo + n]
+        else:
+            host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            host.copy_(text[geom.own_lo:geom.own_lo + n])
         torch.cuda.synchronize()
     if not args.no_e2e:
         cap = n_local + 4096
         out_t = torch.empty((cap, 2), dtype=torch.int64, pin_memory=True)  # the caller's result buffer, pinned like the haystack
         out = out_t.numpy().view(np.uint64)
         tot = R.ctypes.c_size_t()
+        if world == 1:
+            def e2e_once():
+                ok = R.lib().rure_b200_find_all(re_._h, host.data_ptr(), n, out.ctypes.data, cap, R.byref(tot))
+                assert ok
+                return tot.value
+            how = ("rure_b200_find_all on pinned host memory, the whole haystack; H2D of the haystack and D2H of all spans inside the "
+                   "timed region; the library pipelines upload, search and download in 64 MiB pieces; spans compared with the "
+                   "device-resident search")
+        else:
+            def e2e_once():  # upload the shard, the sharded protocol (boundary all_gathers included), download this rank's spans
+                text.copy_(host_full, non_blocking=True)
+                got_, _, _, _ = step()
+                out_t[:got_].copy_(engine.spans[:got_], non_blocking=True)
+                torch.cuda.synchronize()
+                return got_
+            how = ("every rank uploads its shard buffer (own bytes + left context + halo) from pinned host memory, the ranks run the "
+                   "sharded protocol of the timed steps (boundary all_gathers included), every rank downloads its spans into a pinned "
+                   "host buffer; all inside the timed region, max over ranks")
         for _ in range(2):
-            R.lib().rure_b200_find_all(re_._h, host.data_ptr(), n, out.ctypes.data, cap, R.byref(tot))
+            e2e_once()
         barrier()
         k = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(k):
-            ok = R.lib().rure_b200_find_all(re_._h, host.data_ptr(), n, out.ctypes.data, cap, R.byref(tot))
-            assert ok
+            got_e2e = e2e_once()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if world == 1:
-            mine = engine.spans[:n_local].cpu().numpy().astype(np.uint64)
-            assert tot.value == n_local and (out[:n_local] == mine).all(), "e2e spans differ from the device-resident search"
+        mine = engine.spans[:n_local].cpu().numpy().astype(np.uint64)
+        assert got_e2e == n_local and (out[:n_local] == mine).all(), "e2e spans differ from the device-resident search"
         if rank == 0:
-            result["e2e"] = {"value": round(n * world / float(t[0]) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
-                             "d2h_bytes_per_step": int(min(tot.value, cap) * 16 + 8), "haystack_bytes": n,
-                             "note": "rure_b200_find_all on pinned host memory, the whole shard per rank (at N>1: one independent haystack per rank, "
-                                     "max over ranks); H2D of the haystack and D2H of all spans inside the timed region; the library pipelines "
-                                     "upload, search and download in 64 MiB pieces; spans compared with the device-resident search"}
+            result["e2e"] = {"value": round(n * world / float(t[0]) / 1e9, 3), "unit": "GB/s",
+                             "h2d_bytes_per_step": int(host_full.numel() if world > 1 else n),
+                             "d2h_bytes_per_step": int(min(got_e2e, cap) * 16 + 8), "haystack_bytes": n, "note": how}
         del out, out_t
 
     if rank == 0:
@@ -422,7 +442,7 @@ def run_ours(args):
                                                 f"(DfaSuffix as the reference selects for this pattern, exec.rs:1176-1210), count {count} == GPU count"}
         if not args.no_extras and not args.no_cpu:
             result["rg"] = rg_leg(args.pattern, host, n, re_, text, geom)
-    del host
+    del host, host_full
     if rank == 0 and world == 1 and not args.no_extras:
         result["also"] = also_patterns(R, text, n, n_local, dev, peak)
         result["configs"] = other_configs(args, text, dev)
