@@ -365,6 +365,8 @@ def run_ours(args):
     # ---- N > 1: all spans in one buffer on rank 0 (global positions), checked and timed ----
     if world > 1:
         counts = sharded.find_all_sharded.last_counts
+        # (a 16-span gather first: NCCL sets up its point-to-point channels on first use)
+        sharded.gather_spans(engine.spans, min(n_local, 16), [min(c, 16) for c in counts], geom.buf_lo, rank, world)
         barrier()
         t0 = time.perf_counter()
         allspans = sharded.gather_spans(engine.spans, n_local, counts, geom.buf_lo, rank, world)
