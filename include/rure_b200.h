@@ -189,7 +189,7 @@ void rure_b200_last_stats_ex(rure *re, double *out, size_t n);
 void rure_b200_set_last_stats_ex(rure_set *set, double *out, size_t n);
 /* Named knobs (tests, tuning): "wave0" bytes of the first wave of is_match / shortest_match /
  * set matches (x16 per wave, 0 = one wave), "narrow_sets" 0/1, "max_stitch_rounds",
- * "max_redo_rounds", "prefilter" (0 never, 1 automatic: only for a single rare byte, 2 whenever the
+ * "max_redo_rounds", "batch_refill" 0/1 (batched is_match: lanes refill from a task of records), "prefilter" (0 never, 1 automatic: only for a single rare byte, 2 whenever the
  * pattern qualifies).  Returns false for an unknown name. */
 bool rure_b200_set_option(rure *re, const char *name, uint64_t value);
 bool rure_b200_set_set_option(rure_set *set, const char *name, uint64_t value);

@@ -477,6 +477,7 @@ static bool set_option(Regex* r, const char* name, uint64_t value) {
   const std::string k(name ? name : "");
   if (k == "wave0") t.wave0 = value;
   else if (k == "narrow_sets") t.narrow_sets = value != 0;
+  else if (k == "batch_refill") t.batch_refill = (int)value;
   else if (k == "max_stitch_rounds") t.max_stitch_rounds = (uint32_t)value;
   else if (k == "max_redo_rounds") t.max_redo_rounds = (uint32_t)value;
   else if (k == "prefilter") t.prefilter = (int)value;

@@ -255,9 +255,7 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
   // ASCII bytes (what an ASCII haystack can reach).  Row 1 is the trap.
   {
     std::vector<uint8_t> is_hot(h->n_states, 0);
-    if (h->n_states + 1 <= kFastStates) {
-      std::fill(is_hot.begin(), is_hot.end(), 1);
-    } else {
+    {
       std::vector<uint16_t> stack;
       auto push = [&](uint16_t s) { if (!is_hot[s]) { is_hot[s] = 1; stack.push_back(s); } };
       push(0);
@@ -268,6 +266,11 @@ int Regex::ensure(DfaKind k, DeviceDfa** out) {
         for (int b = 0; b < 128; b++) push(h->next(s, (uint8_t)b));
       }
     }
+    // All states when they fit -- unless the ASCII closure is a small part of the automaton: Unicode `\d`
+    // in `(\d{4})-(\d{2})-(\d{2})` makes 183 states of which 15 are reachable on ASCII, and a 51 KB table
+    // costs a block per SM and most of the L1 where 4 KB will do (non-ASCII bytes take the trap row).
+    const size_t n_closure = (size_t)std::count(is_hot.begin(), is_hot.end(), 1);
+    if (h->n_states + 1 <= kFastStates && n_closure * 4 > h->n_states) std::fill(is_hot.begin(), is_hot.end(), 1);
     const size_t n_hot = (size_t)std::count(is_hot.begin(), is_hot.end(), 1) + 1;
     if (n_hot <= kFastStates) {
       std::vector<uint16_t> full2hot(h->n_states, 0xFFFF), hot2full;
@@ -770,7 +773,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
   // runner: 2 = fixed-length (no haystack access), 1 = byte-indexed shared-memory table
   // (uniform start state, 8-byte aligned text), 0 = generic
   const bool wfixed = min_len == max_len && min_len > 0 && !emulate && !tuning.force_generic;
-  const bool wfast = !wfixed && fwd->hot.n != 0 && fwd->view.uniform_start && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic;
+  const bool wfast = !wfixed && fwd->hot.n != 0 && fwd->view.uniform_start && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic;
   const int wkind = wfixed ? 2 : wfast ? 1 : 0;
   // literal prefilter: no start bitmap at all -- literal_scan finds, verifies and chains the candidates
   const bool use_pf = tuning.prefilter && !tuning.force_generic && ((uintptr_t)d_text & 15) == 0 && plan_prefilter() &&
@@ -1358,14 +1361,25 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
   a.offsets = d_offsets;
   a.n_rec = n_rec;
   a.out_bits = d_bits;
-  if (fwd->hot.n && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic) {
+  if (fwd->hot.n && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic) {
     a.fwd_hot = fwd->hot;
     a.fwd_g = (const DfaView*)fwd->view_dev;
     const size_t fsm = hot_bytes(fwd->hot.n) + 256;
-    RB_CUDA(allow_smem(batch_fast<0>, fsm));
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
-    batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
-    RB_LAUNCH_CHECK("batch_fast<0>");
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 8192)));
+    if (tuning.batch_refill) {
+      uint32_t* counters = (uint32_t*)counters_.ensure(128);
+      if (!counters) return fail("out of device memory (batch scratch)");
+      a.task_counter = (unsigned long long*)(counters + 16);
+      RB_CUDA(cudaMemsetAsync(a.task_counter, 0, 8, (cudaStream_t)stream_));
+      // (8 KB of static shared memory for the result words on top of the table: opt in whenever the sum may pass 48 KB)
+      RB_CUDA(cudaFuncSetAttribute(batch_refill<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 48 * 1024)));
+      batch_refill<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+      RB_LAUNCH_CHECK("batch_refill<0>");
+    } else {
+      RB_CUDA(allow_smem(batch_fast<0>, fsm));
+      batch_fast<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+      RB_LAUNCH_CHECK("batch_fast<0>");
+    }
   } else {
     RB_CUDA(allow_smem(is_match_batch, smem));
     is_match_batch<<<(uint32_t)((n_rec + 255) / 256), 256, smem, (cudaStream_t)stream_>>>(a);
@@ -1390,16 +1404,26 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
   a.n_rec = n_rec;
   a.out_bits = d_bits;
   a.out_spans = d_spans;
-  if (fwd->hot.n && rev->hot.n && ((uintptr_t)d_text & 7) == 0 && !tuning.force_generic) {
+  if (fwd->hot.n && rev->hot.n && ((uintptr_t)d_text & 15) == 0 && !tuning.force_generic) {
     a.fwd_hot = fwd->hot;
     a.rev_hot = rev->hot;
     a.fwd_g = (const DfaView*)fwd->view_dev;
     a.rev_g = (const DfaView*)rev->view_dev;
     const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
-    RB_CUDA(allow_smem(batch_fast<1>, fsm));
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / fsm));
-    batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
-    RB_LAUNCH_CHECK("batch_fast<1>");
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 8192)));
+    if (tuning.batch_refill > 1) {  // find: measured slower than batch_fast<1> on log lines (two phases per step), off unless asked for
+      uint32_t* counters = (uint32_t*)counters_.ensure(128);
+      if (!counters) return fail("out of device memory (batch scratch)");
+      a.task_counter = (unsigned long long*)(counters + 16);
+      RB_CUDA(cudaMemsetAsync(a.task_counter, 0, 8, (cudaStream_t)stream_));
+      RB_CUDA(cudaFuncSetAttribute(batch_refill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 48 * 1024)));
+      batch_refill<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+      RB_LAUNCH_CHECK("batch_refill<1>");
+    } else {
+      RB_CUDA(allow_smem(batch_fast<1>, fsm));
+      batch_fast<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
+      RB_LAUNCH_CHECK("batch_fast<1>");
+    }
   } else {
     find_batch<<<(uint32_t)((n_rec + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
     RB_LAUNCH_CHECK("find_batch");

@@ -2451,6 +2451,20 @@ __device__ __forceinline__ void window16(const uint8_t* p, uint32_t (&v)[4]) {
   const bool up = sh >= 32;
   v[0] = up ? x1 : x0; v[1] = up ? x2 : x1; v[2] = up ? x3 : x2; v[3] = up ? x4 : x3;
 }
+// The same window from two aligned 16-byte loads (reads [p & ~15, (p & ~15) + 32)): two L1 wavefronts per
+// lane instead of three -- the batch kernels are bound by exactly those (every lane reads its own line).
+__device__ __forceinline__ void window16q(const uint8_t* p, uint32_t (&v)[4]) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint8_t* al = reinterpret_cast<const uint8_t*>(addr & ~(uintptr_t)15);
+  const uint4 p0 = ldg128(al), p1 = ldg128(al + 16);
+  const bool by2 = (addr & 8u) != 0, by1 = (addr & 4u) != 0;
+  const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+  const uint32_t a0 = by2 ? p0.z : p0.x, a1 = by2 ? p0.w : p0.y, a2 = by2 ? p1.x : p0.z, a3 = by2 ? p1.y : p0.w,
+                 a4 = by2 ? p1.z : p1.x, a5 = by2 ? p1.w : p1.y;
+  const uint32_t b0 = by1 ? a1 : a0, b1 = by1 ? a2 : a1, b2 = by1 ? a3 : a2, b3 = by1 ? a4 : a3, b4 = by1 ? a5 : a4;
+  v[0] = __funnelshift_r(b0, b1, sh); v[1] = __funnelshift_r(b1, b2, sh);
+  v[2] = __funnelshift_r(b2, b3, sh); v[3] = __funnelshift_r(b3, b4, sh);
+}
 __device__ __forceinline__ uint32_t window_byte(const uint32_t (&v)[4], int i) {  // byte i, i compile-time
   return (v[i >> 2] >> (8 * (i & 3))) & 0xFFu;
 }
@@ -2624,6 +2638,193 @@ __global__ void __launch_bounds__(512) batch_fast(BatchArgs a) {
 }
 template __global__ void batch_fast<0>(BatchArgs);
 template __global__ void batch_fast<1>(BatchArgs);
+
+// ---- batch_refill: batch_fast<0> with the lanes of a warp kept busy ----
+// batch_fast gives every lane one record and waits for the slowest of the 32: on log lines 70 % of the
+// records are decided inside their first window and their lanes idle until the longest line of the warp
+// is through (ncu: 8.5 of 32 threads per instruction).  Here a warp owns a task of kBatchTask consecutive
+// records; a lane that has decided its record takes the next one of the task as soon as kBatchRefill lanes
+// are free (the refill code runs for all of them together), so a step of the loop is one 16-byte window for
+// (nearly) every lane.  Result bits are collected in shared memory and leave as whole words.
+constexpr uint32_t kBatchTask = 2048, kBatchRefill = 8;
+// MODE 0: is_match; MODE 1: find -- a lane's record is first in the forward phase (leftmost-first end),
+// then in the reverse phase (start, exec.rs:651-657 with the record as its own slice); one window per step.
+template <int MODE>
+__global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
+  __shared__ uint32_t task_bits[16][kBatchTask / 32];  // blockDim.x == 512
+  const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
+  const uint32_t rbase = fbase + hot_table_bytes(a.fwd_hot.n);
+  hot_stage(a.fwd_hot, fbase);
+  if (MODE == 1) hot_stage(a.rev_hot, rbase);
+  __syncthreads();
+  const uint32_t fthr = a.fwd_hot.match_lo, flive = 2;
+  const uint32_t rthr = a.rev_hot.match_lo, rlive = 2;
+  const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t n_tasks = (a.n_rec + kBatchTask - 1) / kBatchTask;
+  uint32_t* bits = task_bits[wid];
+  for (;;) {
+    // tasks are handed out through a global counter: with a fixed assignment the warps that get one task
+    // more than the others decide the kernel's time
+    unsigned long long task = 0;
+    if (lane == 0) task = atomicAdd(a.task_counter, 1ull);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    const uint64_t r_lo = task * kBatchTask, r_hi = min(r_lo + kBatchTask, a.n_rec);
+    for (uint32_t i = lane; i < kBatchTask / 32; i += 32) bits[i] = 0;
+    __syncwarp();
+    uint64_t next = r_lo;  // warp-uniform: first record of the task not handed out yet
+    bool idle = true;
+    uint64_t r = 0, len = 0, q = 0;  // q: forward position, then (reverse phase) the position the reverse scan stands at
+    const uint8_t* p = a.text;
+    uint32_t e = 0, mx = 0;
+    uint64_t last = kNone, start = kNone;  // MODE 1: match end (forward), match start (reverse)
+    bool rev_phase = false;
+    auto finish = [&](bool hit, uint64_t ms, uint64_t me) {
+      if (hit) atomicOr(&bits[(uint32_t)(r - r_lo) >> 5], 1u << ((uint32_t)(r - r_lo) & 31u));
+      if (MODE == 1) {
+        a.out_spans[2 * r] = hit ? ms : 0;
+        a.out_spans[2 * r + 1] = hit ? me : 0;
+      }
+      idle = true;
+    };
+    auto finish_slow = [&]() {  // the record left the hot set: again on the full tables
+      if (MODE == 0) {
+        finish(slow_is_match_record(a.fwd_g, p, len), 0, 0);
+      } else {
+        uint64_t ms = 0, me = 0;
+        const bool hit = slow_find_record(a.fwd_g, a.rev_g, p, len, &ms, &me);
+        finish(hit, ms, me);
+      }
+    };
+    for (;;) {
+      const uint32_t idle_m = __ballot_sync(0xffffffffu, idle);
+      if (idle_m == 0xffffffffu && next >= r_hi) break;
+      if (next < r_hi && ((uint32_t)__popc(idle_m) >= kBatchRefill || idle_m == 0xffffffffu)) {
+        const uint64_t mine = next + (uint32_t)__popc(idle_m & ((1u << lane) - 1u));
+        if (idle && mine < r_hi) {
+          r = mine;
+          const uint64_t lo = a.offsets[r];
+          len = a.offsets[r + 1] - lo;
+          p = a.text + lo;
+          q = 0;
+          mx = 0;
+          last = start = kNone;
+          rev_phase = false;
+          const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
+          e = h0 == 0xFFFFu ? 1u : h0;
+          idle = false;
+        }
+        next = min(next + (uint64_t)__popc(idle_m), r_hi);
+      }
+      if (idle) continue;
+      if (!rev_phase) {
+        // ---- forward: one window of this lane's record ----
+        bool done = false;
+        const uint64_t left = len - q;
+        if (left == 0) {  // EOF step
+          if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { mx = 0xFFFFFFFFu; last = len; }
+          done = true;
+        } else if (e < flive) {
+          done = true;  // dead or trap from the start state
+        } else {
+          const uint8_t* wp = p + q;
+          const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)15);
+          if (al + 32 <= buf_hi) {
+            uint32_t v[4];
+            window16q(wp, v);
+            const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
+            uint32_t lj = ~0u;
+            if (nb == 16) {
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+                e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
+                e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
+                e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
+                e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 15; i++)
+                if ((uint32_t)i < nb) {
+                  e = hot_next_b(fbase, window_byte(v, i), e);
+                  if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = i;
+                }
+            }
+            if (MODE == 1 && lj != ~0u && e != 1u) last = q + lj;
+            q += nb;
+          } else {  // the last bytes of the whole buffer: byte loads
+            for (uint64_t i = 0; i < left && e >= flive && (MODE == 1 || mx < fthr); i++) {
+              e = hot_next_b(fbase, p[q + i], e);
+              if (MODE == 0) mx = max(mx, e); else if (e >= fthr) last = q + i;
+            }
+            q += left;
+          }
+          if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
+        }
+        if (done) {
+          if (e == 1u && !(MODE == 0 && mx >= fthr)) {
+            finish_slow();
+          } else if (MODE == 0) {
+            finish(mx >= fthr, 0, 0);
+          } else if (last == kNone) {
+            finish(false, 0, 0);
+          } else if (last == 0) {
+            finish(true, 0, 0);
+          } else {  // on to the reverse phase
+            const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, last)];
+            const uint32_t hr = a.rev_hot.full2hot[sf];
+            if (sf == 0) finish(false, 0, 0);
+            else if (hr == 0xFFFFu) finish_slow();
+            else { e = hr; q = last; rev_phase = true; }
+          }
+        }
+      } else {
+        // ---- reverse from the match end: one window, bytes [q-16, q) ----
+        bool rdone = false;
+        const uint8_t* wp = p + q - 16;  // only the last min(16, q) bytes of the window belong to the record
+        const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)15);
+        const uint32_t nb = q >= 16 ? 16u : (uint32_t)q;
+        if (al >= a.text && al + 32 <= buf_hi) {
+          uint32_t v[4];
+          window16q(wp, v);
+          uint32_t lj = ~0u;
+#pragma unroll
+          for (int i = 15; i >= 0; i--) {
+            if ((uint32_t)(15 - i) < nb && !rdone) {
+              e = hot_next_b(rbase, window_byte(v, i), e);
+              if (e >= rthr) lj = i;
+              if (e < rlive) rdone = true;
+            }
+          }
+          if (lj != ~0u) start = q - 16 + lj + 1;
+          q -= nb;
+        } else {
+          for (uint32_t i = 0; i < nb && !rdone; i++) {
+            q--;
+            e = hot_next_b(rbase, p[q], e);
+            if (e >= rthr) start = q + 1;
+            if (e < rlive) rdone = true;
+          }
+        }
+        if (rdone || q == 0) {
+          if (e == 1u) {
+            finish_slow();
+          } else {
+            if (!rdone && a.rev_hot.eof[e] >= a.rev.match_lo) start = 0;
+            finish(start != kNone, start, last);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < kBatchTask / 32; i += 32)
+      if (r_lo + 32ull * i < r_hi) a.out_bits[(r_lo >> 5) + i] = bits[i];
+    __syncwarp();
+  }
+}
+template __global__ void batch_refill<0>(BatchArgs);
+template __global__ void batch_refill<1>(BatchArgs);
 
 // dfa.rs:525-570 per record: OR of the per-state pattern masks along the scan.
 __global__ void set_matches_batch(BatchArgs a) {

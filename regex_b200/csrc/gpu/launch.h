@@ -152,10 +152,13 @@ struct BatchArgs {
   uint32_t* out_bits;   // ballot words
   uint64_t* out_spans;  // 2 per record
   uint64_t* out_masks;  // mask_words per record
+  unsigned long long* task_counter;  // batch_refill: next task to hand out (zeroed before the launch)
 };
 
 template <int MODE>
 __global__ void batch_fast(BatchArgs a);
+template <int MODE>
+__global__ void batch_refill(BatchArgs a);
 __global__ void scan_rev_bitmap(ScanArgs a);
 template <int FUSED>
 __global__ void scan_rev_fast(ScanArgs a, WalkArgs wa, const __grid_constant__ CUtensorMap tmap);

@@ -297,17 +297,19 @@ def test_batched_lines_match_scalar_api():
     for pat in [r"(\d{4})-(\d{2})-(\d{2})", r"(?-u)(\d{4})-(\d{2})-(\d{2})", r"^\d+ host", r"svc\[\d+\]:$", r"(?i)holmes", r"\n$",
                 r"\w+\s\w+$", r"(?-u:\b)\d{2}(?-u:\b)", r"^$", r"[a-z]+ing"]:
         o = O.OracleRegex(pat)
-        for generic in (False, True):
+        # batch_fast (one record per lane per round), batch_refill for is_match (the default) and for find, generic
+        for generic, refill in ((False, 1), (False, 0), (False, 2), (True, 1)):
             r = R.BytesRegex(pat)
             r.force_generic(generic)
+            r.set_option("batch_refill", refill)
             m = r.is_match_batch(text, off)
             found, spans = r.find_batch(text, off)
             for i, l in enumerate(lines):
                 exp = o.find_at(l)
-                assert bool(m[i]) == (exp is not None), (pat, i, generic)
-                assert bool(found[i]) == (exp is not None), (pat, i, generic)
+                assert bool(m[i]) == (exp is not None), (pat, i, generic, refill)
+                assert bool(found[i]) == (exp is not None), (pat, i, generic, refill)
                 if exp:
-                    assert tuple(int(v) for v in spans[i]) == exp, (pat, i, generic)
+                    assert tuple(int(v) for v in spans[i]) == exp, (pat, i, generic, refill)
 
 
 SET_PATTERNS = [r"\w+", r"\d+", r"\s+", r"[A-Z][a-z]+", "Holmes", "Watson", "Sherlock", r"Holmes|Watson", r"^The", r"\.$",
