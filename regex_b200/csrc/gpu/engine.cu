@@ -1410,7 +1410,7 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
     a.fwd_g = (const DfaView*)fwd->view_dev;
     a.rev_g = (const DfaView*)rev->view_dev;
     const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 8192)));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 16384)));
     if (tuning.batch_refill > 1) {  // find: measured slower than batch_fast<1> on log lines (two phases per step), off unless asked for
       uint32_t* counters = (uint32_t*)counters_.ensure(128);
       if (!counters) return fail("out of device memory (batch scratch)");

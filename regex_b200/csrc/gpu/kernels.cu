@@ -2647,11 +2647,14 @@ template __global__ void batch_fast<1>(BatchArgs);
 // are free (the refill code runs for all of them together), so a step of the loop is one 16-byte window for
 // (nearly) every lane.  Result bits are collected in shared memory and leave as whole words.
 constexpr uint32_t kBatchTask = 2048, kBatchRefill = 8;
-// MODE 0: is_match; MODE 1: find -- a lane's record is first in the forward phase (leftmost-first end),
-// then in the reverse phase (start, exec.rs:651-657 with the record as its own slice); one window per step.
+// MODE 0: is_match.  MODE 1: find -- two such loops per task: the forward one leaves the leftmost-first end of
+// every record that matches (and a bit in `todo`), the reverse one takes those records again for their start
+// (exec.rs:651-657 with the record as its own slice).  One loop with both phases mixed ran both code paths in
+// every step and was slower than batch_fast<1>.
 template <int MODE>
 __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
-  __shared__ uint32_t task_bits[16][kBatchTask / 32];  // blockDim.x == 512
+  __shared__ uint32_t task_bits[16][kBatchTask / 32];                   // blockDim.x == 512
+  __shared__ uint32_t task_todo[MODE == 1 ? 16 : 1][kBatchTask / 32];  // MODE 1: records that wait for the reverse loop
   const uint32_t fbase = ((uint32_t)__cvta_generic_to_shared(g_smem) + 255u) & ~255u;
   const uint32_t rbase = fbase + hot_table_bytes(a.fwd_hot.n);
   hot_stage(a.fwd_hot, fbase);
@@ -2663,6 +2666,7 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t n_tasks = (a.n_rec + kBatchTask - 1) / kBatchTask;
   uint32_t* bits = task_bits[wid];
+  uint32_t* todo = task_todo[MODE == 1 ? wid : 0];
   for (;;) {
     // tasks are handed out through a global counter: with a fixed assignment the warps that get one task
     // more than the others decide the kernel's time
@@ -2671,15 +2675,14 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= n_tasks) break;
     const uint64_t r_lo = task * kBatchTask, r_hi = min(r_lo + kBatchTask, a.n_rec);
-    for (uint32_t i = lane; i < kBatchTask / 32; i += 32) bits[i] = 0;
+    for (uint32_t i = lane; i < kBatchTask / 32; i += 32) { bits[i] = 0; if (MODE == 1) todo[i] = 0; }
     __syncwarp();
     uint64_t next = r_lo;  // warp-uniform: first record of the task not handed out yet
     bool idle = true;
-    uint64_t r = 0, len = 0, q = 0;  // q: forward position, then (reverse phase) the position the reverse scan stands at
+    uint64_t r = 0, len = 0, q = 0;
     const uint8_t* p = a.text;
     uint32_t e = 0, mx = 0;
-    uint64_t last = kNone, start = kNone;  // MODE 1: match end (forward), match start (reverse)
-    bool rev_phase = false;
+    uint64_t last = kNone;  // MODE 1: match end
     auto finish = [&](bool hit, uint64_t ms, uint64_t me) {
       if (hit) atomicOr(&bits[(uint32_t)(r - r_lo) >> 5], 1u << ((uint32_t)(r - r_lo) & 31u));
       if (MODE == 1) {
@@ -2697,6 +2700,7 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
         finish(hit, ms, me);
       }
     };
+    // ---- forward loop ----
     for (;;) {
       const uint32_t idle_m = __ballot_sync(0xffffffffu, idle);
       if (idle_m == 0xffffffffu && next >= r_hi) break;
@@ -2709,8 +2713,7 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
           p = a.text + lo;
           q = 0;
           mx = 0;
-          last = start = kNone;
-          rev_phase = false;
+          last = kNone;
           const uint32_t h0 = a.fwd.uniform_start ? a.fwd_hot.start : a.fwd_hot.full2hot[a.fwd.start[flags_forward(p, len, 0)]];
           e = h0 == 0xFFFFu ? 1u : h0;
           idle = false;
@@ -2718,71 +2721,100 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
         next = min(next + (uint64_t)__popc(idle_m), r_hi);
       }
       if (idle) continue;
-      if (!rev_phase) {
-        // ---- forward: one window of this lane's record ----
-        bool done = false;
-        const uint64_t left = len - q;
-        if (left == 0) {  // EOF step
-          if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { mx = 0xFFFFFFFFu; last = len; }
-          done = true;
-        } else if (e < flive) {
-          done = true;  // dead or trap from the start state
-        } else {
-          const uint8_t* wp = p + q;
-          const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)15);
-          if (al + 32 <= buf_hi) {
-            uint32_t v[4];
-            window16q(wp, v);
-            const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
-            uint32_t lj = ~0u;
-            if (nb == 16) {
+      bool done = false;
+      const uint64_t left = len - q;
+      if (left == 0) {  // EOF step
+        if (e >= flive && a.fwd_hot.eof[e] >= a.fwd.match_lo) { mx = 0xFFFFFFFFu; last = len; }
+        done = true;
+      } else if (e < flive) {
+        done = true;  // dead or trap from the start state
+      } else {
+        const uint8_t* wp = p + q;
+        const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)15);
+        if (al + 32 <= buf_hi) {
+          uint32_t v[4];
+          window16q(wp, v);
+          const uint32_t nb = left >= 16 ? 16u : (uint32_t)left;
+          uint32_t lj = ~0u;
+          if (nb == 16) {
 #pragma unroll
-              for (int g = 0; g < 4; g++) {
-                e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
-                e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
-                e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
-                e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
+            for (int g = 0; g < 4; g++) {
+              e = hot_next<0>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 0;
+              e = hot_next<1>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 1;
+              e = hot_next<2>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 2;
+              e = hot_next<3>(fbase, v[g], e); if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = 4 * g + 3;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 15; i++)
+              if ((uint32_t)i < nb) {
+                e = hot_next_b(fbase, window_byte(v, i), e);
+                if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = i;
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 15; i++)
-                if ((uint32_t)i < nb) {
-                  e = hot_next_b(fbase, window_byte(v, i), e);
-                  if (MODE == 0) mx = max(mx, e); else if (e >= fthr) lj = i;
-                }
-            }
-            if (MODE == 1 && lj != ~0u && e != 1u) last = q + lj;
-            q += nb;
-          } else {  // the last bytes of the whole buffer: byte loads
-            for (uint64_t i = 0; i < left && e >= flive && (MODE == 1 || mx < fthr); i++) {
-              e = hot_next_b(fbase, p[q + i], e);
-              if (MODE == 0) mx = max(mx, e); else if (e >= fthr) last = q + i;
-            }
-            q += left;
           }
-          if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
+          if (MODE == 1 && lj != ~0u && e != 1u) last = q + lj;
+          q += nb;
+        } else {  // the last bytes of the whole buffer: byte loads
+          for (uint64_t i = 0; i < left && e >= flive && (MODE == 1 || mx < fthr); i++) {
+            e = hot_next_b(fbase, p[q + i], e);
+            if (MODE == 0) mx = max(mx, e); else if (e >= fthr) last = q + i;
+          }
+          q += left;
         }
-        if (done) {
-          if (e == 1u && !(MODE == 0 && mx >= fthr)) {
-            finish_slow();
-          } else if (MODE == 0) {
-            finish(mx >= fthr, 0, 0);
-          } else if (last == kNone) {
-            finish(false, 0, 0);
-          } else if (last == 0) {
-            finish(true, 0, 0);
-          } else {  // on to the reverse phase
+        if (e < flive || (MODE == 0 && mx >= fthr)) done = true;
+      }
+      if (done) {
+        if (e == 1u && !(MODE == 0 && mx >= fthr)) {
+          finish_slow();
+        } else if (MODE == 0) {
+          finish(mx >= fthr, 0, 0);
+        } else if (last == kNone) {
+          finish(false, 0, 0);
+        } else if (last == 0) {
+          finish(true, 0, 0);
+        } else {  // the reverse loop finds the start
+          a.out_spans[2 * r + 1] = last;
+          atomicOr(&todo[(uint32_t)(r - r_lo) >> 5], 1u << ((uint32_t)(r - r_lo) & 31u));
+          idle = true;
+        }
+      }
+    }
+    if (MODE == 1) {
+      // ---- reverse loop over the records marked in `todo` ----
+      __syncwarp();
+      uint32_t w = 0, m = todo[0];  // warp-uniform cursor: word index and its bits not handed out yet
+      uint64_t start = kNone;
+      idle = true;
+      for (;;) {
+        while (m == 0 && w + 1 < kBatchTask / 32) m = todo[++w];
+        const uint32_t idle_m = __ballot_sync(0xffffffffu, idle);
+        if (idle_m == 0xffffffffu && m == 0) break;
+        if (m != 0 && ((uint32_t)__popc(idle_m) >= kBatchRefill || idle_m == 0xffffffffu)) {
+          const uint32_t rank = (uint32_t)__popc(idle_m & ((1u << lane) - 1u));
+          const uint32_t take = min((uint32_t)__popc(idle_m), (uint32_t)__popc(m));
+          if (idle && rank < take) {
+            const uint32_t bit = __fns(m, 0, rank + 1);
+            r = r_lo + w * 32u + bit;
+            const uint64_t lo = a.offsets[r];
+            len = a.offsets[r + 1] - lo;
+            p = a.text + lo;
+            last = a.out_spans[2 * r + 1];
+            q = last;
+            start = kNone;
+            idle = false;
             const uint32_t sf = a.rev.uniform_start ? a.rev.start[32] : a.rev.start[flags_reverse(p, len, last)];
             const uint32_t hr = a.rev_hot.full2hot[sf];
             if (sf == 0) finish(false, 0, 0);
             else if (hr == 0xFFFFu) finish_slow();
-            else { e = hr; q = last; rev_phase = true; }
+            else e = hr;
           }
+          const uint32_t cut = take == (uint32_t)__popc(m) ? 32u : __fns(m, 0, take + 1);  // position of the first bit left
+          m = cut >= 32u ? 0u : m & ~((1u << cut) - 1u);
         }
-      } else {
-        // ---- reverse from the match end: one window, bytes [q-16, q) ----
+        if (idle) continue;
+        // one window, bytes [q-16, q): only the last min(16, q) belong to the record
         bool rdone = false;
-        const uint8_t* wp = p + q - 16;  // only the last min(16, q) bytes of the window belong to the record
+        const uint8_t* wp = p + q - 16;
         const uint8_t* al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(wp) & ~(uintptr_t)15);
         const uint32_t nb = q >= 16 ? 16u : (uint32_t)q;
         if (al >= a.text && al + 32 <= buf_hi) {
