@@ -1366,7 +1366,12 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
     a.fwd_g = (const DfaView*)fwd->view_dev;
     const size_t fsm = hot_bytes(fwd->hot.n) + 256;
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 8192)));
-    if (tuning.batch_refill) {
+    // tasks of 96..2048 records, at least four per warp of the grid; smaller batches keep one record per lane
+    const uint32_t grid0 = grid_for(n_rec, 512, per_sm);
+    const uint64_t per_task = n_rec / ((uint64_t)grid0 * 16 * 4);
+    a.task_recs = (uint32_t)std::min<uint64_t>(2048, per_task / 32 * 32);
+    if (tuning.batch_refill >= 2) a.task_recs = std::max<uint32_t>(a.task_recs, 32);  // tests: whatever the size
+    if (tuning.batch_refill && a.task_recs >= (tuning.batch_refill >= 2 ? 32u : 96u)) {
       uint32_t* counters = (uint32_t*)counters_.ensure(128);
       if (!counters) return fail("out of device memory (batch scratch)");
       a.task_counter = (unsigned long long*)(counters + 16);
@@ -1411,7 +1416,9 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
     a.rev_g = (const DfaView*)rev->view_dev;
     const size_t fsm = hot_bytes(fwd->hot.n) + hot_bytes(rev->hot.n) + 256;
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (fsm + 16384)));
-    if (tuning.batch_refill > 1) {  // find: measured slower than batch_fast<1> on log lines (two phases per step), off unless asked for
+    const uint64_t per_task = n_rec / ((uint64_t)grid_for(n_rec, 512, per_sm) * 16 * 4);
+    a.task_recs = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(2048, per_task / 32 * 32));
+    if (tuning.batch_refill > 1) {  // find: measured slower than batch_fast<1> on log lines, off unless asked for
       uint32_t* counters = (uint32_t*)counters_.ensure(128);
       if (!counters) return fail("out of device memory (batch scratch)");
       a.task_counter = (unsigned long long*)(counters + 16);

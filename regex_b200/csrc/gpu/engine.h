@@ -36,7 +36,7 @@ struct Tuning {
   uint32_t blocks_per_sm = 8;
   uint64_t wave0 = 64ull << 20;  // first wave of a forward search in bytes (x16 per wave); 0 = one wave
   bool narrow_sets = true;
-  int batch_refill = 1;          // 0 off, 1 is_match, 2 also find: batched is_match: lanes take the next record as soon as theirs is decided (batch_refill) instead of one record per lane per round
+  int batch_refill = 1;          // 0 off, 1 is_match on large batches, 2 always and also find: batched is_match: lanes take the next record as soon as theirs is decided (batch_refill) instead of one record per lane per round
   int prefilter = 1;             // literal_scan instead of the DFA scan: 0 never, 1 when the scanned byte is estimated rare enough
                                  // to win (one byte, <= ~0.12 % of the haystack), 2 whenever the pattern qualifies structurally       // RegexSet::matches: continue with the automaton of the still-unmatched patterns
   uint32_t max_stitch_rounds = 16;  // re-walk rounds before the stitch falls back to one sequential pass

@@ -2664,7 +2664,8 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
   const uint32_t rthr = a.rev_hot.match_lo, rlive = 2;
   const uint8_t* const buf_hi = a.text + a.offsets[a.n_rec];
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint64_t n_tasks = (a.n_rec + kBatchTask - 1) / kBatchTask;
+  const uint32_t task_recs = a.task_recs;  // multiple of 32, at most kBatchTask (the host sizes it so that every warp gets several)
+  const uint64_t n_tasks = (a.n_rec + task_recs - 1) / task_recs;
   uint32_t* bits = task_bits[wid];
   uint32_t* todo = task_todo[MODE == 1 ? wid : 0];
   for (;;) {
@@ -2674,8 +2675,8 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
     if (lane == 0) task = atomicAdd(a.task_counter, 1ull);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= n_tasks) break;
-    const uint64_t r_lo = task * kBatchTask, r_hi = min(r_lo + kBatchTask, a.n_rec);
-    for (uint32_t i = lane; i < kBatchTask / 32; i += 32) { bits[i] = 0; if (MODE == 1) todo[i] = 0; }
+    const uint64_t r_lo = task * task_recs, r_hi = min(r_lo + task_recs, a.n_rec);
+    for (uint32_t i = lane; i < task_recs / 32; i += 32) { bits[i] = 0; if (MODE == 1) todo[i] = 0; }
     __syncwarp();
     uint64_t next = r_lo;  // warp-uniform: first record of the task not handed out yet
     bool idle = true;
@@ -2786,7 +2787,7 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
       uint64_t start = kNone;
       idle = true;
       for (;;) {
-        while (m == 0 && w + 1 < kBatchTask / 32) m = todo[++w];
+        while (m == 0 && w + 1 < task_recs / 32) m = todo[++w];
         const uint32_t idle_m = __ballot_sync(0xffffffffu, idle);
         if (idle_m == 0xffffffffu && m == 0) break;
         if (m != 0 && ((uint32_t)__popc(idle_m) >= kBatchRefill || idle_m == 0xffffffffu)) {
@@ -2850,7 +2851,7 @@ __global__ void __launch_bounds__(512) batch_refill(BatchArgs a) {
       }
     }
     __syncwarp();
-    for (uint32_t i = lane; i < kBatchTask / 32; i += 32)
+    for (uint32_t i = lane; i < task_recs / 32; i += 32)
       if (r_lo + 32ull * i < r_hi) a.out_bits[(r_lo >> 5) + i] = bits[i];
     __syncwarp();
   }

@@ -153,6 +153,7 @@ struct BatchArgs {
   uint64_t* out_spans;  // 2 per record
   uint64_t* out_masks;  // mask_words per record
   unsigned long long* task_counter;  // batch_refill: next task to hand out (zeroed before the launch)
+  uint32_t task_recs;                // batch_refill: records per task (multiple of 32, <= 2048)
 };
 
 template <int MODE>
