@@ -172,6 +172,15 @@ bool rure_b200_shortest_match_shard_device(rure *re, const uint8_t *d_buffer, si
 bool rure_b200_set_matches_shard_device(rure_set *set, const uint8_t *d_buffer, size_t n_buffer,
                                         rure_b200_fwd_shard *io);
 
+/* ---- threads ----------------------------------------------------------------
+ * As in rure.h (regex-capi/include/rure.h:27-34) one compiled rure / rure_set may be used from
+ * several threads at once.  The scalar entry points (rure_is_match, rure_find, rure_shortest_match,
+ * rure_find_captures, rure_set_is_match, rure_set_matches and their rure_b200_* twins with an error
+ * return) run concurrently: the engine keeps its device scratch per object, so a call that finds the
+ * object busy runs on a clone compiled from the same source, kept with the handle.  The bulk,
+ * device-pointer and shard entry points use the handle's primary engine and serialise; give every
+ * thread (or shard) its own handle for those.  rure_b200_last_stats* and the options describe the
+ * primary engine. */
 /* ---- diagnostics ----------------------------------------------------------- */
 const char *rure_b200_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */

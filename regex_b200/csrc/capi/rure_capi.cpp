@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,11 +19,44 @@ struct rure_options {
 struct rure_error {
   std::string msg = "no error";
 };
-struct rure {
-  Regex* re = nullptr;
+// rure.h:27-34: a compiled regex may be used from several threads at once.  The engine keeps its device
+// scratch (bitmap, staging, counters, stream) per object, so a scalar call that finds the object busy takes a
+// clone compiled from the same source; the clones stay with the handle.  Bulk, device and shard entry points
+// run on the primary engine and serialise.
+struct EnginePool {
+  Regex* re = nullptr;  // primary
+  std::vector<std::string> pats;
+  rbgpu::CompileOptions opts;
+  std::mutex mu;
+  std::vector<Regex*> clones;
+  ~EnginePool() {
+    for (Regex* c : clones) delete c;
+    delete re;
+  }
 };
-struct rure_set {
-  Regex* re = nullptr;
+struct rure : EnginePool {};
+struct rure_set : EnginePool {};
+struct Lease {
+  Regex* r;
+  explicit Lease(EnginePool* h) {
+    if (h->re->try_acquire()) { r = h->re; return; }
+    std::lock_guard<std::mutex> g(h->mu);
+    for (Regex* c : h->clones)
+      if (c->try_acquire()) { r = c; return; }
+    rb::Error err;
+    Regex* c = Regex::compile(h->pats, h->opts, &err);
+    if (!c) {  // cannot happen for a source that compiled once; wait for the primary then
+      h->re->acquire();
+      r = h->re;
+      return;
+    }
+    c->tuning = h->re->tuning;
+    c->acquire();
+    h->clones.push_back(c);
+    r = c;
+  }
+  ~Lease() { r->release(); }
+  Regex* operator->() const { return r; }
 };
 struct rure_captures {
   size_t n_groups = 1;
@@ -63,8 +97,9 @@ static bool ok(Regex* re, int rc) {
   std::abort();
 }
 
-static Regex* compile_common(const std::vector<std::string>& pats, uint32_t flags, rure_options* options,
-                             rure_error* error, bool only_utf8, bool as_set) {
+template <typename Handle>
+static Handle* compile_common(const std::vector<std::string>& pats, uint32_t flags, rure_options* options,
+                              rure_error* error, bool only_utf8, bool as_set) {
   rbgpu::CompileOptions o;
   o.flags = flags;
   o.only_utf8 = only_utf8;
@@ -75,25 +110,22 @@ static Regex* compile_common(const std::vector<std::string>& pats, uint32_t flag
   if (!re) {
     if (error) error->msg = err.msg;
     g_last_error = err.msg;
+    return nullptr;
   }
-  return re;
+  Handle* h = new Handle();
+  h->re = re;
+  h->pats = pats;
+  h->opts = o;
+  return h;
 }
 
 extern "C" {
 
 rure* rure_compile(const uint8_t* pattern, size_t length, uint32_t flags, rure_options* options, rure_error* error) {
-  Regex* re = compile_common({std::string((const char*)pattern, length)}, flags, options, error, false, false);
-  if (!re) return nullptr;
-  rure* r = new rure();
-  r->re = re;
-  return r;
+  return compile_common<rure>({std::string((const char*)pattern, length)}, flags, options, error, false, false);
 }
 rure* rure_b200_compile_str(const uint8_t* pattern, size_t length, uint32_t flags, rure_options* options, rure_error* error) {
-  Regex* re = compile_common({std::string((const char*)pattern, length)}, flags, options, error, true, false);
-  if (!re) return nullptr;
-  rure* r = new rure();
-  r->re = re;
-  return r;
+  return compile_common<rure>({std::string((const char*)pattern, length)}, flags, options, error, true, false);
 }
 rure* rure_compile_must(const char* pattern) {
   rure_error err;
@@ -104,36 +136,36 @@ rure* rure_compile_must(const char* pattern) {
   }
   return r;
 }
-void rure_free(rure* re) {
-  if (!re) return;
-  delete re->re;
-  delete re;
-}
+void rure_free(rure* re) { delete re; }
 
 bool rure_is_match(rure* re, const uint8_t* haystack, size_t length, size_t start) {
   bool found = false;
   uint64_t end = 0;
-  if (!ok(re->re, re->re->shortest_match_host(haystack, length, start, &found, &end))) die("rure_is_match");
+  Lease l(re);
+  if (!ok(l.r, l->shortest_match_host(haystack, length, start, &found, &end))) die("rure_is_match");
   return found;
 }
 bool rure_shortest_match(rure* re, const uint8_t* haystack, size_t length, size_t start, size_t* end) {
   bool found = false;
   uint64_t e = 0;
-  if (!ok(re->re, re->re->shortest_match_host(haystack, length, start, &found, &e))) die("rure_shortest_match");
+  Lease l(re);
+  if (!ok(l.r, l->shortest_match_host(haystack, length, start, &found, &e))) die("rure_shortest_match");
   if (found && end) *end = e;
   return found;
 }
 bool rure_find(rure* re, const uint8_t* haystack, size_t length, size_t start, rure_match* match) {
   bool found = false;
   uint64_t s = 0, e = 0;
-  if (!ok(re->re, re->re->find_at_host(haystack, length, start, &found, &s, &e))) die("rure_find");
+  Lease l(re);
+  if (!ok(l.r, l->find_at_host(haystack, length, start, &found, &s, &e))) die("rure_find");
   if (found && match) { match->start = s; match->end = e; }
   return found;
 }
 bool rure_find_captures(rure* re, const uint8_t* haystack, size_t length, size_t start, rure_captures* captures) {
   bool found = false;
   std::vector<uint64_t> slots(2 * (size_t)re->re->n_groups(), ~0ull);
-  if (!ok(re->re, re->re->captures_at_host(haystack, length, start, &found, slots.data()))) die("rure_find_captures");
+  Lease l(re);
+  if (!ok(l.r, l->captures_at_host(haystack, length, start, &found, slots.data()))) die("rure_find_captures");
   if (captures) {
     captures->has = found;
     captures->slots = found ? slots : std::vector<uint64_t>(slots.size(), ~0ull);
@@ -258,7 +290,8 @@ bool rure_b200_captures_all(rure* re, const uint8_t* haystack, size_t length, si
   return r;
 }
 bool rure_b200_captures(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, size_t* slots) {
-  return ok(re->re, re->re->captures_at_host(haystack, length, start, found, (uint64_t*)slots));
+  Lease l(re);
+  return ok(l.r, l->captures_at_host(haystack, length, start, found, (uint64_t*)slots));
 }
 size_t rure_b200_captures_len(rure* re) { return (size_t)re->re->n_groups(); }
 
@@ -271,31 +304,20 @@ rure_set* rure_compile_set(const uint8_t** patterns, const size_t* lengths, size
                            rure_options* options, rure_error* error) {
   std::vector<std::string> pats;
   for (size_t i = 0; i < count; i++) pats.emplace_back((const char*)patterns[i], lengths[i]);
-  Regex* re = compile_common(pats, flags, options, error, false, true);
-  if (!re) return nullptr;
-  rure_set* s = new rure_set();
-  s->re = re;
-  return s;
+  return compile_common<rure_set>(pats, flags, options, error, false, true);
 }
 rure_set* rure_b200_compile_set_str(const uint8_t** patterns, const size_t* lengths, size_t count, uint32_t flags,
                                     rure_options* options, rure_error* error) {
   std::vector<std::string> pats;
   for (size_t i = 0; i < count; i++) pats.emplace_back((const char*)patterns[i], lengths[i]);
-  Regex* re = compile_common(pats, flags, options, error, true, true);
-  if (!re) return nullptr;
-  rure_set* s = new rure_set();
-  s->re = re;
-  return s;
+  return compile_common<rure_set>(pats, flags, options, error, true, true);
 }
-void rure_set_free(rure_set* s) {
-  if (!s) return;
-  delete s->re;
-  delete s;
-}
+void rure_set_free(rure_set* s) { delete s; }
 bool rure_set_is_match(rure_set* s, const uint8_t* haystack, size_t length, size_t start) {
   bool found = false;
   uint64_t end = 0;
-  if (!ok(s->re, s->re->shortest_match_host(haystack, length, start, &found, &end))) die("rure_set_is_match");
+  Lease l(s);
+  if (!ok(l.r, l->shortest_match_host(haystack, length, start, &found, &end))) die("rure_set_is_match");
   return found;
 }
 bool rure_set_matches(rure_set* s, const uint8_t* haystack, size_t length, size_t start, bool* matches) {
@@ -303,7 +325,8 @@ bool rure_set_matches(rure_set* s, const uint8_t* haystack, size_t length, size_
   for (size_t i = 0; i < n; i++) matches[i] = false;
   uint64_t masks[4] = {0, 0, 0, 0};
   bool any = false;
-  if (!ok(s->re, s->re->set_matches_host(haystack, length, start, &any, masks))) die("rure_set_matches");
+  Lease l(s);
+  if (!ok(l.r, l->set_matches_host(haystack, length, start, &any, masks))) die("rure_set_matches");
   for (size_t i = 0; i < n; i++) matches[i] = (masks[i / 64] >> (i % 64)) & 1;
   return any;
 }
@@ -318,23 +341,27 @@ const char* rure_error_message(rure_error* e) { return e->msg.c_str(); }
 // the GPU search cannot run (no device, out of memory).  Hosts that prefer an error code use these.
 bool rure_b200_is_match(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* matched) {
   uint64_t end = 0;
-  return ok(re->re, re->re->shortest_match_host(haystack, length, start, matched, &end));
+  Lease l(re);
+  return ok(l.r, l->shortest_match_host(haystack, length, start, matched, &end));
 }
 bool rure_b200_shortest_match(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, size_t* end) {
   uint64_t e = 0;
-  const bool r = ok(re->re, re->re->shortest_match_host(haystack, length, start, found, &e));
+  Lease l(re);
+  const bool r = ok(l.r, l->shortest_match_host(haystack, length, start, found, &e));
   if (r && *found && end) *end = e;
   return r;
 }
 bool rure_b200_find(rure* re, const uint8_t* haystack, size_t length, size_t start, bool* found, rure_match* match) {
   uint64_t s = 0, e = 0;
-  const bool r = ok(re->re, re->re->find_at_host(haystack, length, start, found, &s, &e));
+  Lease l(re);
+  const bool r = ok(l.r, l->find_at_host(haystack, length, start, found, &s, &e));
   if (r && *found && match) { match->start = s; match->end = e; }
   return r;
 }
 bool rure_b200_set_is_match(rure_set* set, const uint8_t* haystack, size_t length, size_t start, bool* matched) {
   uint64_t end = 0;
-  return ok(set->re, set->re->shortest_match_host(haystack, length, start, matched, &end));
+  Lease l(set);
+  return ok(l.r, l->shortest_match_host(haystack, length, start, matched, &end));
 }
 
 // ------------------------------------------------------------ bulk extension --

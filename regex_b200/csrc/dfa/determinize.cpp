@@ -366,7 +366,7 @@ static bool has_unresolvable_look_pair(const Program& prog) {
 
 bool determinize(const Program& prog, const DfaOptions& opt, Dfa* out, Error* err) {
   if (has_unresolvable_look_pair(prog)) {
-    err->kind = Error::UnicodeWordBoundary;
+    err->kind = Error::UnresolvableLookPair;  // its own class: not one of the two rejections the north star grants
     err->msg = "look-around sequence not supported by the B200 DFA backend: a word boundary directly followed by a "
                "multi-line `^`, or a multi-line `$` directly followed by a word boundary, cannot be resolved inside a "
                "DFA scan (the reference's own DFA and NFA engines disagree on such patterns).";

@@ -63,7 +63,7 @@ struct Flags {
 };
 
 struct Error {
-  enum Kind { None = 0, Syntax, CompiledTooBig, DfaTooBig, UnicodeWordBoundary, InvalidUtf8Pattern } kind = None;
+  enum Kind { None = 0, Syntax, CompiledTooBig, DfaTooBig, UnicodeWordBoundary, InvalidUtf8Pattern, UnresolvableLookPair } kind = None;
   std::string msg;
   explicit operator bool() const { return kind != None; }
 };

@@ -88,6 +88,11 @@ class Regex {
 
   size_t n_patterns() const { return patterns_.size(); }
   bool is_set() const { return is_set_; }
+  // Exclusive use of this object's device scratch for one call (the entry points lock mu_ themselves; the C ABI
+  // uses these to find an idle engine when several threads share one rure*).
+  bool try_acquire() { return mu_.try_lock(); }
+  void acquire() { mu_.lock(); }
+  void release() { mu_.unlock(); }
   const rb::Dfa* host_dfa(DfaKind k, rb::Error* err);  // builds lazily (also used by tests to inspect tables)
 
   // ---- single haystack, device-resident text --------------------------------

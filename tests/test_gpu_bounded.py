@@ -245,3 +245,37 @@ def test_scalar_find_searches_in_growing_windows():
         for start in (0, 1, 255, 256, 257, 65535, 65536, 65537, 131072, 600000, 2000001, len(small) - 3, len(small)):
             assert r.find_at(small, start) == o.find_at(small, start), (pat, start)
             assert r.shortest_match_at(small, start) == o.shortest_match_at(small, start), (pat, start)
+
+
+def test_one_compiled_regex_from_several_threads():
+    """rure.h:27-34: a compiled regex may be used from multiple threads simultaneously.  The engine's device
+    scratch is per object; the scalar entry points lease an idle engine (a clone when the object is busy)."""
+    import threading
+    base = tiled_corpus(1 << 20)
+    pats = [r"[a-zA-Z]+ing", r"(?i)holmes\s+\w+", r"\d{3,}"]
+    regs = [R.BytesRegex(p) for p in pats]
+    sets = R.BytesRegexSet([r"Holmes", r"Watson", r"zzzzqq", r"\d+"])
+    hays = [base[i * 50000:(i + 3) * 50000 + 17 * i] for i in range(8)]
+    exp = [[(m.span() if m else None) for m in (pyre.search(p.encode(), h) for h in hays)] for p in pats]
+    exp_set = [[i for i, p in enumerate([rb"Holmes", rb"Watson", rb"zzzzqq", rb"\d+"]) if pyre.search(p, h)] for h in hays]
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(6):
+                for j in range(len(hays)):
+                    k = (j + tid + rep) % len(hays)
+                    for pi, r in enumerate(regs):
+                        got = r.find(hays[k])
+                        assert (tuple(got) if got else None) == exp[pi][k], (pats[pi], k)
+                        assert r.is_match(hays[k]) == (exp[pi][k] is not None)
+                    assert list(sets.matches(hays[k])) == exp_set[k]
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
