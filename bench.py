@@ -210,6 +210,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (regex_b200 has no CPU path)"
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local_rank) if world > 1 else None  # pinned host buffers next to this rank's GPU
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL_DEBUG=VERSION/INFO writes to stdout by default: the contract is ONE JSON line there
@@ -432,11 +434,14 @@ def run_ours(args):
             result["e2e"] = {"value": round(n * world / float(t[0]) / 1e9, 3), "unit": "GB/s",
                              "h2d_bytes_per_step": int(host_full.numel() if world > 1 else n),
                              "d2h_bytes_per_step": int(min(got_e2e, cap) * 16 + 8), "haystack_bytes": n, "note": how}
+            if numa:
+                result["e2e"]["host_cpus_rank0"] = f"{len(numa)} CPUs local to GPU {local_rank} (NVML affinity; pinned buffers first-touched there)"
         del out, out_t
 
     if rank == 0:
         threads = os.cpu_count() or 1
         if not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)  # the CPU leg uses every host core again
             gbs, dt, count = cpu_reference_ptr(args.pattern, host.data_ptr(), n, threads, 1, 1)
             assert count == n_local, ("parity check failed: CPU count != GPU count", count, n_local)
             result["cpu_baseline"] = {"value": round(gbs, 4), "unit": "GB/s", "cores": threads, "kind": "port",
@@ -518,6 +523,26 @@ def other_configs(args, text, dev):
             out[name] = {"failed": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.empty_cache()
     return out
+
+
+def bind_near_gpu(index):
+    """Run this process on the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers it
+    allocates (first touch) sit on that GPU's NUMA node: with several ranks uploading at once the e2e leg is
+    otherwise limited by cross-socket traffic.  Returns the CPU list, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
 
 
 def main():
