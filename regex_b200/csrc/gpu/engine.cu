@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "launch.h"
 
@@ -325,10 +327,22 @@ static size_t smem_for(const DfaView& v) {
   size_t need = ((size_t)v.table_bytes + 15) / 16 * 16 + 256;
   return need <= 200 * 1024 ? need : 0;
 }
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the function, not to the
+// caller: it is only ever RAISED (per-kernel maximum under a lock) -- two regex objects with different table
+// sizes searching from two threads would otherwise lower it under each other's launches ("invalid argument").
+// min_bytes: kernels with static shared memory on top pass 48 KB so that the sum may exceed the default limit.
 template <typename K>
-static cudaError_t allow_smem(K kernel, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+static cudaError_t allow_smem(K kernel, size_t bytes, size_t min_bytes = 0) {
+  bytes = std::max(bytes, min_bytes);
+  if (bytes <= 48 * 1024 && min_bytes == 0) return cudaSuccess;
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[(const void*)kernel];
+  if (bytes <= have) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 static uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t blocks_per_sm) {
   uint64_t blocks = (threads_needed + block - 1) / block;
@@ -648,9 +662,9 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     block = 1024;
     const bool fw_fixed = fw && fw->fixed_len != 0;
     smem = fast_scan_smem(hot_bytes_signed(rev->hot) + (fw && !fw_fixed ? hot_bytes(fw->fwd_hot.n) : 0));
-    if (fw_fixed) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else if (fw) RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else RB_CUDA(cudaFuncSetAttribute(scan_rev_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (fw_fixed) RB_CUDA(allow_smem(scan_rev_fast<2>, smem));
+    else if (fw) RB_CUDA(allow_smem(scan_rev_fast<1>, smem));
+    else RB_CUDA(allow_smem(scan_rev_fast<0>, smem));
   } else {
     smem = smem_for(rev->view);
     a.use_smem = smem != 0;
@@ -868,7 +882,7 @@ int Regex::find_all_shard_device(const uint8_t* d_text, uint64_t n, ShardIO* io,
 #define RB_PF(F, N)                                                                \
     {                                                                              \
       /* the kernel also has ~9 KB of static shared memory: opt in whenever the sum could pass 48 KB */ \
-      cudaError_t e__ = cudaFuncSetAttribute(literal_scan<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(wsmem, 48 * 1024)); \
+      cudaError_t e__ = allow_smem(literal_scan<F, N>, wsmem, 48 * 1024); \
       if (e__ != cudaSuccess) return e__;                                          \
       literal_scan<F, N><<<g, 256, wsmem, st>>>(args, pf, mode);                   \
       return cudaSuccess;                                                          \
@@ -1115,7 +1129,7 @@ int Regex::forward_range(const uint8_t* d_text, uint64_t n, uint64_t start, uint
       a.skip_lo = skip_lo;
       a.skip_hi = skip_hi;
       const size_t fsm = fast_scan_smem(hot_bytes(fwd->hot.n));
-      RB_CUDA(cudaFuncSetAttribute(scan_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      RB_CUDA(allow_smem(scan_fwd_fast, fsm));
       RB_CUDA(cudaEventRecord((cudaEvent_t)fork_event_, st));  // the side stream starts once everything before this point is done
       scan_fwd_fast<<<grid_for(skip_hi - skip_lo, 1024, 1), 1024, fsm, st>>>(a, tmap);
       RB_LAUNCH_CHECK("scan_fwd_fast");
@@ -1377,7 +1391,7 @@ int Regex::is_match_batch_device(const uint8_t* d_text, const uint64_t* d_offset
       a.task_counter = (unsigned long long*)(counters + 16);
       RB_CUDA(cudaMemsetAsync(a.task_counter, 0, 8, (cudaStream_t)stream_));
       // (8 KB of static shared memory for the result words on top of the table: opt in whenever the sum may pass 48 KB)
-      RB_CUDA(cudaFuncSetAttribute(batch_refill<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 48 * 1024)));
+      RB_CUDA(allow_smem(batch_refill<0>, fsm, 48 * 1024));
       batch_refill<0><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
       RB_LAUNCH_CHECK("batch_refill<0>");
     } else {
@@ -1423,7 +1437,7 @@ int Regex::find_batch_device(const uint8_t* d_text, const uint64_t* d_offsets, u
       if (!counters) return fail("out of device memory (batch scratch)");
       a.task_counter = (unsigned long long*)(counters + 16);
       RB_CUDA(cudaMemsetAsync(a.task_counter, 0, 8, (cudaStream_t)stream_));
-      RB_CUDA(cudaFuncSetAttribute(batch_refill<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 48 * 1024)));
+      RB_CUDA(allow_smem(batch_refill<1>, fsm, 48 * 1024));
       batch_refill<1><<<grid_for(n_rec, 512, per_sm), 512, fsm, (cudaStream_t)stream_>>>(a);
       RB_LAUNCH_CHECK("batch_refill<1>");
     } else {

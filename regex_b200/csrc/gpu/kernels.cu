@@ -1098,32 +1098,44 @@ __global__ void __launch_bounds__(256) compact_spans(WalkArgs a) {
       chunk_walk(a, R, k, c, &fc, a.out, my_at, a.cap, ~0ull, walkers);  // voting together: without it the lanes drift apart, 13x slower on `\w+`
     }
     __syncwarp();
-    uint32_t todo = __ballot_sync(0xffffffffu, my_cnt != 0 && my_cnt <= a.stage_cap);
-    while (todo) {
-      // four chunks per trip: their loads are in flight together (one chunk at a time was
-      // a dependent load -> store chain per lane)
-      int j[4];
-      uint64_t cnt[4], at[4];
-      uint32_t sk[4];
+    // The staged spans of the warp's 32 chunks as ONE list: lane i of a row takes element 32 * row + i whatever
+    // chunk it belongs to (a chunk holds ~19 spans on the headline pattern: one chunk per instruction left a
+    // third of the lanes idle and the stores in pieces).  Four rows per trip keep four loads per lane in flight.
+    const uint32_t copy_cnt = my_cnt <= a.stage_cap ? (uint32_t)my_cnt : 0u;  // overflowed chunks were written above
+    uint32_t pre = copy_cnt;  // exclusive prefix over the lanes
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
+      if ((int)lane >= o) pre += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+    pre -= copy_cnt;
+    for (uint32_t row0 = 0; row0 < total; row0 += 128) {
       ulonglong2 v[4];
+      uint64_t to[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        j[u] = todo ? __ffs(todo) - 1 : -1;
-        if (todo) todo &= todo - 1;
-        cnt[u] = j[u] >= 0 ? __shfl_sync(0xffffffffu, my_cnt, j[u] & 31) : 0;
-        at[u] = __shfl_sync(0xffffffffu, my_at, j[u] & 31);
-        sk[u] = __shfl_sync(0xffffffffu, my_skip, j[u] & 31);
+        const uint32_t i = row0 + 32 * u + lane;
+        // the chunk of element i: the last lane whose prefix is <= i (chunks without spans share a prefix with
+        // their successor and are passed over)
+        uint32_t j = 0;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const uint32_t cand = j + step;
+          const uint32_t pv = __shfl_sync(0xffffffffu, pre, cand & 31);
+          if (cand < 32 && pv <= i) j = cand;
+        }
+        const uint32_t pj = __shfl_sync(0xffffffffu, pre, j);
+        const uint32_t sj = __shfl_sync(0xffffffffu, my_skip, j);
+        const uint64_t aj = __shfl_sync(0xffffffffu, my_at, j);
+        to[u] = ~0ull;
+        if (i < total) {
+          v[u] = stage[(g * 32 + j) * (uint64_t)a.stage_cap + sj + (i - pj)];
+          to[u] = aj + (i - pj);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (lane < cnt[u]) v[u] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + sk[u] + lane];
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (lane < cnt[u] && at[u] + lane < a.cap) dst[at[u] + lane] = v[u];
-#pragma unroll
-      for (int u = 0; u < 4; u++)  // chunks with more than 32 staged spans
-        for (uint64_t i = lane + 32; i < cnt[u]; i += 32)
-          if (at[u] + i < a.cap) dst[at[u] + i] = stage[(g * 32 + j[u]) * (uint64_t)a.stage_cap + sk[u] + i];
+        if (to[u] < a.cap) dst[to[u]] = v[u];
     }
   }
 }
