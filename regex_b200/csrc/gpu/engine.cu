@@ -662,6 +662,11 @@ int Regex::scan_starts(const uint8_t* d_text, uint64_t n, uint64_t base, uint64_
     block = 1024;
     const bool fw_fixed = fw && fw->fixed_len != 0;
     smem = fast_scan_smem(hot_bytes_signed(rev->hot) + (fw && !fw_fixed ? hot_bytes(fw->fwd_hot.n) : 0));
+    {  // kernels.cu: rings and mbarriers of the block's warps first, then the tables (hot_signed_below / hot_signed_bytes)
+      const uint32_t after_rings = (block / 32) * (2 * 2048 + 64);
+      a.tbase_off = after_rings + (uint32_t)hot_bytes(rev->hot.n - rev->hot.match_lo);
+      a.fbase_off = after_rings + (uint32_t)hot_bytes_signed(rev->hot);
+    }
     if (fw_fixed) RB_CUDA(allow_smem(scan_rev_fast<2>, smem));
     else if (fw) RB_CUDA(allow_smem(scan_rev_fast<1>, smem));
     else RB_CUDA(allow_smem(scan_rev_fast<0>, smem));

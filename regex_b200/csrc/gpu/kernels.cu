@@ -1495,9 +1495,8 @@ __global__ void __launch_bounds__(1024, 1) scan_rev_fast(ScanArgs a, WalkArgs wa
   const uint32_t rings = ((uint32_t)__cvta_generic_to_shared(g_smem) + 511u) & ~511u;
   const uint32_t ring = rings + wid * kRingWarpBytes;
   const uint32_t bar0 = rings + (blockDim.x >> 5) * kRingWarpBytes + wid * kRingBarBytes;
-  const uint32_t tstart = rings + (blockDim.x >> 5) * (kRingWarpBytes + kRingBarBytes);  // a multiple of 256
-  const uint32_t tbase = tstart + hot_signed_below(a.hot);
-  const uint32_t fbase = tstart + hot_signed_bytes(a.hot);
+  const uint32_t tbase = rings + a.tbase_off;  // = rings + warps * (ring + barriers) + hot_signed_below(a.hot), a multiple of 256
+  const uint32_t fbase = rings + a.fbase_off;  // = ... + hot_signed_bytes(a.hot)
   const uint32_t rml = a.hot.match_lo;
   {
     hot_stage_signed(a.hot, tbase);

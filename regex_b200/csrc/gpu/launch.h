@@ -34,6 +34,8 @@ struct ScanArgs {
   uint64_t skip_lo, skip_hi;  // scan_fwd_reduce: segments [skip_lo, skip_hi) belong to scan_fwd_fast
   uint64_t fwd_limit;   // forward scan: positions [base, fwd_limit) are stepped; n + 1 includes the end-of-text step
   uint32_t entry0;      // forward scan: exact state at `base` (a later wave of one search), kNoEntry = start state by flags
+  uint32_t tbase_off, fbase_off;  // scan_rev_fast: row 0 of the reverse table and the forward table, in bytes from the ring base (host-computed:
+                                  // derived from the table sizes in the kernel they were recomputed for every 16 haystack bytes)
 };
 
 struct WalkArgs {
